@@ -1,0 +1,136 @@
+/* libtapclip — C ABI of the B200-native TAP-CLIP hot path (attribution-instrumented CLIP forward
+ * + backward to the prompt context vectors).
+ *
+ * The reference (3300786/TAP-CLIP) is pure Python and has no FFI of its own; the boundary it exposes
+ * for this path is the Python surface of `CLIPWrapper` (models/clip_wrapper.py:9-65) and `FullModel`
+ * (models/model_wrapper.py:12-100).  `tapclip_b200/` keeps that surface and binds the functions below
+ * through ctypes; each export cites the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; `tapclip_last_error()` then returns a
+ *     thread-local message.  Unsupported shapes / dtypes / devices are errors: there is NO CPU fallback.
+ *   - all pointers are DEVICE pointers (borrowed for the duration of the call, never freed by the
+ *     library) unless stated; tensors are dense row-major fp32 unless stated; `stream` is a cudaStream_t
+ *     passed as void* (0 = default stream).  All work is enqueued on `stream`; no hidden host syncs.
+ *   - a handle owns its converted weights and workspaces; it is not thread-safe; one handle per device.
+ */
+#ifndef TAPCLIP_H_
+#define TAPCLIP_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define TAPCLIP_API __attribute__((visibility("default")))
+#else
+#define TAPCLIP_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tapclip_engine* tapclip_handle;
+
+enum { TAPCLIP_ACT_GELU_ERF = 0, TAPCLIP_ACT_QUICK_GELU = 1 };
+enum { TAPCLIP_DTYPE_FP32 = 0, TAPCLIP_DTYPE_BF16 = 1 };        /* compute type of GEMM/attention operands */
+enum { TAPCLIP_ATTR_LITERAL = 0, TAPCLIP_ATTR_INTENDED = 1 };  /* SURVEY.md 8a "mode definitions" */
+
+typedef struct {
+    int32_t image_size, patch_size;
+    int32_t vision_width, vision_layers, vision_heads;
+    int32_t text_width, text_layers, text_heads;
+    int32_t embed_dim;
+    int32_t context_length;   /* tokens per class prompt in the token bank (77) */
+    int32_t act;              /* TAPCLIP_ACT_* : open_clip `quick_gelu` flag */
+    int32_t dtype;            /* TAPCLIP_DTYPE_* */
+} tapclip_config;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+/* Replaces open_clip.create_model_and_transforms + .to(device).eval() + freeze (clip_wrapper.py:13-20).
+ * Uses the calling thread's current CUDA device; fails if it is not sm_100. */
+TAPCLIP_API int tapclip_create(const tapclip_config* cfg, tapclip_handle* out);
+TAPCLIP_API int tapclip_destroy(tapclip_handle h);
+TAPCLIP_API const char* tapclip_last_error(void);
+TAPCLIP_API const char* tapclip_version(void);
+
+/* Replaces model.load_state_dict (clip_wrapper.py:14-15): one call per open_clip state-dict entry
+ * (`visual.conv1.weight`, `visual.transformer.resblocks.3.attn.in_proj_weight`, `text_projection`, ...).
+ * `data` is an fp32 device tensor of the given shape; the engine keeps its own converted copy.
+ * Entries the hot path does not use (token_embedding.weight, positional_embedding, ln_final.*,
+ * logit_scale) are accepted and ignored.  Returns non-zero for unknown names or wrong shapes. */
+TAPCLIP_API int tapclip_load_weight(tapclip_handle h, const char* name, const float* data, int32_t ndim, const int64_t* shape,
+                        void* stream);
+/* Non-zero (with the list of missing entries in last_error) until every weight has been loaded. */
+TAPCLIP_API int tapclip_weights_complete(tapclip_handle h);
+
+/* ---- hot path ------------------------------------------------------------------------------------ */
+/* CLIPWrapper.encode_image (clip_wrapper.py:46-47; row A4): images [B,3,R,R] -> out_feat [B,E] (NOT
+ * normalised).  out_cls_rows (nullable): north-star extension, per-layer per-head CLS-row attention
+ * probabilities [B, L, H, N] emitted by the attention kernel's probe epilogue. */
+TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int32_t B, float* out_feat, float* out_cls_rows,
+                         void* stream);
+
+/* Rows A2,A6-A10 for `C` class prompts at once (model_wrapper.py:32-35,47-75; prompt_learner.py:45-66;
+ * attribution_monitor.py:24-34; prompt_adjustor.py:35-36):
+ *   ctx [C,P,D] learnable context vectors, tok [C,L,D] frozen token embeddings (L = context_length)
+ *   mode INTENDED: attribution pass on the un-adjusted prompt, a = softmax_P(mean_h P_last[h, 0:P, T-1]),
+ *                  out_attr_raw / out_attr [C,P];   mode LITERAL: a == 1, out_attr [C,1] (raw not produced)
+ *   feature pass on [ctx*a | tok], last position, @ text_projection, L2-norm -> out_text_feat [C,E].
+ * save_for_backward != 0 keeps the activations `tapclip_text_backward` needs. */
+TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const float* tok, int32_t C, int32_t P, int32_t mode,
+                         int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat,
+                         void* stream);
+
+/* Rows A5,A11,A12 (model_wrapper.py:41,79,83,90-93): out_img_norm [B,E] = L2-normalised image features,
+ * out_logits [B,C] = exp(*logit_scale) * img_norm . text_feat^T.  If labels (int64 [B], device) is
+ * non-null: out_loss[0] = sum_b CE_b * inv_batch_total and out_dlogits [B,C] = dloss/dlogits. */
+TAPCLIP_API int tapclip_logits(tapclip_handle h, const float* img_feat, const float* text_feat, const float* logit_scale,
+                   const int64_t* labels, int32_t B, int32_t C, float inv_batch_total, float* out_img_norm,
+                   float* out_logits, float* out_loss, float* out_dlogits, void* stream);
+
+/* Backward of the logit contraction: out_d_text [C,E] = exp(s) * dlogits^T . img_norm,
+ * out_d_logit_scale[0] = sum dlogits*logits. */
+TAPCLIP_API int tapclip_logits_backward(tapclip_handle h, const float* dlogits, const float* logits, const float* img_norm,
+                            const float* logit_scale, int32_t B, int32_t C, float* out_d_text,
+                            float* out_d_logit_scale, void* stream);
+
+/* Row A13 (autograd of model_wrapper.py:68-75 down to prompt_learner.context_bank): d_text_feat [C,E]
+ * -> out_dctx [C,P,D]; activation gradients only (frozen weights), attribution treated as constant.
+ * Must follow a tapclip_text_forward(..., save_for_backward=1) with the same C, P. */
+TAPCLIP_API int tapclip_text_backward(tapclip_handle h, const float* d_text_feat, float* out_dctx, void* stream);
+
+/* train.py:65-67,105: torch.optim.AdamW step fused over a flat fp32 bank of n elements. */
+TAPCLIP_API int tapclip_adamw_step(tapclip_handle h, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
+/* utils/eval_metrics.py:19-29: argmax over classes into out_pred (int64 [B], nullable) and
+ * atomically adds the number of (pred == label) to out_correct[0] (int32, nullable with labels). */
+TAPCLIP_API int tapclip_argmax_count(tapclip_handle h, const float* logits, const int64_t* labels, int32_t B, int32_t C,
+                         int64_t* out_pred, int32_t* out_correct, void* stream);
+
+/* Workspace bytes currently held by the handle (for memory accounting). */
+TAPCLIP_API int64_t tapclip_workspace_bytes(tapclip_handle h);
+/* Number of kernel launches issued by this handle since creation (bench.py `gpu_launches`). */
+TAPCLIP_API int64_t tapclip_launch_count(tapclip_handle h);
+
+/* ---- single-kernel entry points (used by the per-kernel parity tests and micro-benchmarks) -------- */
+/* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias).  dtype BF16: A,W bf16, tcgen05 path; FP32: SIMT path.
+ * epi: 0 = store activation type (+act, optional out_pre), 1 = store fp32, 2 = fp32 += .  block_n: 0|128|256 */
+TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N,
+                    int64_t K, int32_t dtype, int32_t epi, int32_t act, int32_t block_n, void* stream);
+TAPCLIP_API int tapclip_op_layernorm(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out,
+                         int32_t out_dtype, float* x_copy, int64_t rows, int32_t d, void* stream);
+TAPCLIP_API int tapclip_op_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast,
+                             int32_t cast_dtype, int64_t rows, int32_t d, void* stream);
+/* probe_mode: 0 none, 1 text column (out [S,H,P]), 2 CLS row (out [S,H,N] with probe_seq_stride) */
+TAPCLIP_API int tapclip_op_attention(const void* qkv, void* out, int32_t dtype, int32_t S, int32_t N, int32_t H, int32_t probe_mode,
+                         float* probe_out, int32_t probe_P, int64_t probe_seq_stride, void* stream);
+TAPCLIP_API int tapclip_op_attention_bwd(const void* qkv, const void* d_out, void* dqkv, int32_t dtype, int32_t S, int32_t N, int32_t H,
+                             void* stream);
+TAPCLIP_API int tapclip_op_attribution(const float* probe, float* raw, float* attr, int32_t C, int32_t H, int32_t P, void* stream);
+TAPCLIP_API int tapclip_op_cast(const float* src, void* dst, int32_t dst_dtype, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAPCLIP_H_ */

@@ -1,0 +1,393 @@
+// K2 — fused attention (head dim 64, no mask) with a probe epilogue.
+//
+// Replaces nn.MultiheadAttention's scaled-dot-product attention inside open_clip's residual blocks
+//  AND the forward hook of models/clip_wrapper.py:29-40: the probabilities the
+// attribution needs (text: column T-1 for the P ctx query rows; vision extension: the CLS row) are
+// emitted from the softmax registers, so the [S,H,N,N] maps the hook would capture never reach HBM.
+//
+//  * attn_fwd_mma_kernel   bf16, mma.sync m16n8k16 tensor-core path, flash-style online softmax over
+//                          32-key steps, K/V/Q staged in XOR-swizzled smem by cp.async.
+//  * attn_fwd_simt_kernel  fp32 parity mode (one warp per query row).
+//  * attn_bwd_kernel       dQ,dK,dV for the text tower (N <= 128), probabilities recomputed in smem.
+#include "kernels.h"
+
+namespace tapclip {
+namespace {
+
+constexpr int DH = 64;
+constexpr int KC = 32;
+
+// ------------------------------------------------------------------------------------------------
+// bf16 tensor-core forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N, int H, int npad, float scale_log2,
+                    int probe_mode, float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x / H, h = blockIdx.x % H;
+    const int d = H * DH;
+    const int qrows = nwarps * 16;
+    const int q0 = blockIdx.y * qrows;
+    uint8_t* Qs = smem;
+    uint8_t* Ks = Qs + qrows * 128;
+    uint8_t* Vs = Ks + npad * 128;
+
+    const bf16* base = qkv + (int64_t)s * N * 3 * d + h * DH;
+    for (int idx = threadIdx.x; idx < qrows * 8; idx += blockDim.x) {
+        const int row = idx >> 3, ch = idx & 7, grow = q0 + row;
+        const bool ok = grow < N;
+        cp_async_16(smem_u32(Qs + row * 128 + ((ch ^ (row & 7)) << 4)), base + (int64_t)(ok ? grow : 0) * 3 * d + ch * 8, ok);
+    }
+    for (int idx = threadIdx.x; idx < npad * 8; idx += blockDim.x) {
+        const int row = idx >> 3, ch = idx & 7;
+        const bool ok = row < N;
+        const bf16* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
+        const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
+        cp_async_16(smem_u32(Ks + off), src + d, ok);
+        cp_async_16(smem_u32(Vs + off), src + 2 * d, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int r0 = q0 + warp * 16;          // first query row of this warp
+    if (r0 >= N) return;
+    const int g = lane >> 2, tq = lane & 3, mat = lane >> 3, l7 = lane & 7;
+
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int row = warp * 16 + (mat & 1) * 8 + l7, ch = ks * 2 + (mat >> 1);
+        ldmatrix_x4(qf[ks], smem_u32(Qs + row * 128 + ((ch ^ (row & 7)) << 4)));
+    }
+
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float ps0 = 0.f, ps1 = 0.f;             // probed (scaled, log2-domain) score of key N-1 for rows g / g+8
+    const bool cls_probe = (probe_mode == PROBE_CLS_ROW) && r0 == 0 && g == 0;
+    float* cls_out = probe_out ? probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N : nullptr;
+
+    for (int kc = 0; kc < npad; kc += KC) {
+        float sc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int nbp = 0; nbp < 2; ++nbp) {
+                const int key = kc + (nbp * 2 + (mat >> 1)) * 8 + l7, ch = ks * 2 + (mat & 1);
+                uint32_t b[4];
+                ldmatrix_x4(b, smem_u32(Ks + key * 128 + ((ch ^ (key & 7)) << 4)));
+                mma_bf16_16816(sc[nbp * 2], qf[ks], b[0], b[1]);
+                mma_bf16_16816(sc[nbp * 2 + 1], qf[ks], b[2], b[3]);
+            }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = kc + nb * 8 + tq * 2 + e;
+                float v0 = sc[nb][e] * scale_log2, v1 = sc[nb][e + 2] * scale_log2;
+                if (key >= N) { v0 = -INFINITY; v1 = -INFINITY; }
+                if (key == N - 1) { ps0 = v0; ps1 = v1; }
+                if (cls_probe && key < N) cls_out[key] = v0;
+                sc[nb][e] = v0; sc[nb][e + 2] = v1;
+                mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        l0 *= a0; l1 *= a1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+        uint32_t pa[2][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            const float p0 = exp2f(sc[nb][0] - mn0), p1 = exp2f(sc[nb][1] - mn0);
+            const float p2 = exp2f(sc[nb][2] - mn1), p3 = exp2f(sc[nb][3] - mn1);
+            l0 += p0 + p1; l1 += p2 + p3;
+            pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+#pragma unroll
+        for (int ks2 = 0; ks2 < 2; ++ks2) {
+#pragma unroll
+            for (int dbp = 0; dbp < 4; ++dbp) {
+                const int key = kc + ks2 * 16 + (mat & 1) * 8 + l7, ch = dbp * 2 + (mat >> 1);
+                uint32_t b[4];
+                ldmatrix_x4_trans(b, smem_u32(Vs + key * 128 + ((ch ^ (key & 7)) << 4)));
+                mma_bf16_16816(o[dbp * 2], pa[ks2], b[0], b[1]);
+                mma_bf16_16816(o[dbp * 2 + 1], pa[ks2], b[2], b[3]);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+
+    // ---- probe epilogue -------------------------------------------------------------------------
+    if (probe_mode == PROBE_TEXT_COL) {
+        if (tq == (((N - 1) & 7) >> 1)) {
+            // ps0/ps1 were captured from element e = (N-1)&1 of this thread's column pair
+            const int ra = r0 + g, rb = r0 + g + 8;
+            float* po = probe_out + ((int64_t)s * H + h) * probe_P;
+            if (ra < probe_P) po[ra] = exp2f(ps0 - m0) * inv0;
+            if (rb < probe_P) po[rb] = exp2f(ps1 - m1) * inv1;
+        }
+    } else if (cls_probe) {
+        for (int k8 = 0; k8 < N; k8 += 8) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = k8 + tq * 2 + e;
+                if (key < N) cls_out[key] = exp2f(cls_out[key] - m0) * inv0;      // own earlier writes
+            }
+        }
+    }
+
+    // ---- output: registers -> this warp's (now free) Q rows in smem -> 16-byte global stores ------
+    __syncwarp();
+    uint8_t* Ws = Qs + warp * 16 * 128;
+#pragma unroll
+    for (int db = 0; db < 8; ++db) {
+        *reinterpret_cast<uint32_t*>(Ws + g * 128 + ((db ^ (g & 7)) << 4) + tq * 4) = pack_bf16x2(o[db][0] * inv0, o[db][1] * inv0);
+        *reinterpret_cast<uint32_t*>(Ws + (g + 8) * 128 + ((db ^ ((g + 8) & 7)) << 4) + tq * 4) = pack_bf16x2(o[db][2] * inv1, o[db][3] * inv1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int idx = it * 32 + lane, row = idx >> 3, ch = idx & 7;
+        if (r0 + row < N) {
+            const uint4 v = *reinterpret_cast<const uint4*>(Ws + row * 128 + ((ch ^ (row & 7)) << 4));
+            *reinterpret_cast<uint4*>(out + ((int64_t)s * N + r0 + row) * d + h * DH + ch * 8) = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 parity-mode forward: one warp per query row, lanes own keys for the scores and dims for P*V
+// ------------------------------------------------------------------------------------------------
+constexpr int KMAX = 19;   // keys per lane -> N <= 608
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, float scale, int probe_mode,
+                     float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride) {
+    __shared__ float qs[4][DH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.y / H, h = blockIdx.y % H;
+    const int row = blockIdx.x * 4 + warp;
+    const int d = H * DH;
+    if (row >= N) return;
+    const T* base = qkv + (int64_t)s * N * 3 * d + h * DH;
+    qs[warp][lane] = to_f32<T>(base[(int64_t)row * 3 * d + lane]);
+    qs[warp][lane + 32] = to_f32<T>(base[(int64_t)row * 3 * d + lane + 32]);
+    __syncwarp();
+    float pr[KMAX];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int kk = 0; kk < KMAX; ++kk) {
+        const int key = kk * 32 + lane;
+        float v = -INFINITY;
+        if (key < N) {
+            const T* kp = base + (int64_t)key * 3 * d + d;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < DH; ++j) acc = fmaf(qs[warp][j], to_f32<T>(kp[j]), acc);
+            v = acc * scale;
+        }
+        pr[kk] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KMAX; ++kk) {
+        const float e = (kk * 32 + lane < N) ? expf(pr[kk] - mx) : 0.f;
+        pr[kk] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KMAX; ++kk) {
+        pr[kk] *= inv;
+        if (kk * 32 < N) {
+            for (int src = 0; src < 32; ++src) {
+                const float p = __shfl_sync(0xffffffffu, pr[kk], src);
+                const int key = kk * 32 + src;
+                if (key < N) {
+                    const T* vp = base + (int64_t)key * 3 * d + 2 * d;
+                    o0 = fmaf(p, to_f32<T>(vp[lane]), o0);
+                    o1 = fmaf(p, to_f32<T>(vp[lane + 32]), o1);
+                }
+            }
+        }
+    }
+    T* op = out + ((int64_t)s * N + row) * d + h * DH;
+    op[lane] = from_f32<T>(o0);
+    op[lane + 32] = from_f32<T>(o1);
+    if (probe_mode == PROBE_TEXT_COL && row < probe_P) {
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk)
+            if (kk * 32 + lane == N - 1) probe_out[((int64_t)s * H + h) * probe_P + row] = pr[kk];
+    } else if (probe_mode == PROBE_CLS_ROW && row == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk)
+            if (kk * 32 + lane < N) probe_out[(int64_t)s * probe_seq_stride + (int64_t)h * N + kk * 32 + lane] = pr[kk];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (text tower only: N <= 128): one CTA per (sequence, head), fp32 math in shared memory
+//   P = softmax(scale*QK^T); dV = P^T dO; dP = dO V^T; dS = P o (dP - rowsum(P o dP)) * scale;
+//   dQ = dS K; dK = dS^T Q
+// ------------------------------------------------------------------------------------------------
+constexpr int LDH = DH + 1;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __restrict__ dqkv, int N, int H, float scale) {
+    extern __shared__ __align__(16) float sm[];
+    float* Q = sm;
+    float* K = Q + N * LDH;
+    float* V = K + N * LDH;
+    float* dO = V + N * LDH;
+    float* Pm = dO + N * LDH;            // [N][N+1]
+    const int LDP = N + 1;
+    const int s = blockIdx.x / H, h = blockIdx.x % H;
+    const int d = H * DH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const T* base = qkv + (int64_t)s * N * 3 * d + h * DH;
+    for (int i = tid; i < N * DH; i += blockDim.x) {
+        const int r = i / DH, c = i % DH;
+        Q[r * LDH + c] = to_f32<T>(base[(int64_t)r * 3 * d + c]);
+        K[r * LDH + c] = to_f32<T>(base[(int64_t)r * 3 * d + d + c]);
+        V[r * LDH + c] = to_f32<T>(base[(int64_t)r * 3 * d + 2 * d + c]);
+        dO[r * LDH + c] = to_f32<T>(d_out[((int64_t)s * N + r) * d + h * DH + c]);
+    }
+    __syncthreads();
+    // scores
+    for (int i = tid; i < N * N; i += blockDim.x) {
+        const int r = i / N, c = i % N;
+        float acc = 0.f;
+#pragma unroll 16
+        for (int j = 0; j < DH; ++j) acc = fmaf(Q[r * LDH + j], K[c * LDH + j], acc);
+        Pm[r * LDP + c] = acc * scale;
+    }
+    __syncthreads();
+    // row softmax
+    for (int r = warp; r < N; r += nwarps) {
+        float mx = -INFINITY;
+        for (int c = lane; c < N; c += 32) mx = fmaxf(mx, Pm[r * LDP + c]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int c = lane; c < N; c += 32) { const float e = expf(Pm[r * LDP + c] - mx); Pm[r * LDP + c] = e; sum += e; }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        for (int c = lane; c < N; c += 32) Pm[r * LDP + c] *= inv;
+    }
+    __syncthreads();
+    // dV[j][c] = sum_i P[i][j] dO[i][c]
+    T* dbase = dqkv + (int64_t)s * N * 3 * d + h * DH;
+    for (int i = tid; i < N * DH; i += blockDim.x) {
+        const int j = i / DH, c = i % DH;
+        float acc = 0.f;
+        for (int r = 0; r < N; ++r) acc = fmaf(Pm[r * LDP + j], dO[r * LDH + c], acc);
+        dbase[(int64_t)j * 3 * d + 2 * d + c] = from_f32<T>(acc);
+    }
+    __syncthreads();
+    // dS in place of P (one warp per row; up to 4 keys per lane)
+    for (int r = warp; r < N; r += nwarps) {
+        float dp[4], pv[4];
+        float dsum = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = lane + 32 * u;
+            dp[u] = 0.f; pv[u] = 0.f;
+            if (c < N) {
+                float acc = 0.f;
+#pragma unroll 16
+                for (int j = 0; j < DH; ++j) acc = fmaf(dO[r * LDH + j], V[c * LDH + j], acc);
+                dp[u] = acc;
+                pv[u] = Pm[r * LDP + c];
+                dsum = fmaf(pv[u], acc, dsum);
+            }
+        }
+        dsum = warp_sum(dsum);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = lane + 32 * u;
+            if (c < N) Pm[r * LDP + c] = pv[u] * (dp[u] - dsum) * scale;
+        }
+    }
+    __syncthreads();
+    // dQ[i][c] = sum_j dS[i][j] K[j][c] ; dK[j][c] = sum_i dS[i][j] Q[i][c]
+    for (int i = tid; i < N * DH; i += blockDim.x) {
+        const int r = i / DH, c = i % DH;
+        float aq = 0.f, ak = 0.f;
+        for (int j = 0; j < N; ++j) {
+            aq = fmaf(Pm[r * LDP + j], K[j * LDH + c], aq);
+            ak = fmaf(Pm[j * LDP + r], Q[j * LDH + c], ak);
+        }
+        dbase[(int64_t)r * 3 * d + c] = from_f32<T>(aq);
+        dbase[(int64_t)r * 3 * d + d + c] = from_f32<T>(ak);
+    }
+}
+
+}  // namespace
+
+void attention_fwd(const void* qkv, void* out, bool is_bf16, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream) {
+    if (S == 0) return;
+    TC_CHECK(N >= 1 && H >= 1, "bad attention shape");
+    if (probe.mode == PROBE_TEXT_COL) TC_CHECK(probe.out && probe.P >= 1 && probe.P <= N, "bad text probe");
+    if (probe.mode == PROBE_CLS_ROW) TC_CHECK(probe.out && probe.seq_stride >= (int64_t)H * N, "bad CLS probe");
+    if (is_bf16) {
+        const int npad = (int)round_up(N, KC);
+        const int nrb = (int)ceil_div(N, 16);
+        int nwarps = nrb <= 8 ? nrb : (int)ceil_div(nrb, ceil_div(nrb, 8));
+        const int nz = (int)ceil_div(nrb, nwarps);
+        const size_t smem = (size_t)(nwarps * 16 + 2 * npad) * 128;
+        TC_CHECK(smem <= 227 * 1024, "sequence length %d too long for the attention kernel", N);
+        static size_t configured = 0;
+        if (smem > configured) {
+            TC_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        dim3 grid((unsigned)(S * H), (unsigned)nz);
+        attn_fwd_mma_kernel<<<grid, nwarps * 32, smem, stream>>>((const bf16*)qkv, (bf16*)out, N, H, npad,
+                                                                 0.125f * 1.4426950408889634f, probe.mode, probe.out, probe.P,
+                                                                 probe.seq_stride);
+    } else {
+        TC_CHECK(N <= KMAX * 32, "sequence length %d too long for the fp32 attention kernel", N);
+        dim3 grid((unsigned)ceil_div(N, 4), (unsigned)(S * H));
+        attn_fwd_simt_kernel<float><<<grid, 128, 0, stream>>>((const float*)qkv, (float*)out, N, H, 0.125f, probe.mode, probe.out,
+                                                              probe.P, probe.seq_stride);
+    }
+    TC_LAUNCH_CHECK();
+}
+
+void attention_bwd(const void* qkv, const void* d_out, void* dqkv, bool is_bf16, int S, int N, int H, cudaStream_t stream) {
+    if (S == 0) return;
+    TC_CHECK(N <= 128, "attention backward supports sequence length <= 128 (got %d)", N);
+    const size_t smem = ((size_t)4 * N * LDH + (size_t)N * (N + 1)) * sizeof(float);
+    static size_t conf_bf16 = 0, conf_f32 = 0;
+    if (is_bf16) {
+        if (smem > conf_bf16) { TC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf_bf16 = smem; }
+        attn_bwd_kernel<bf16><<<S * H, 256, smem, stream>>>((const bf16*)qkv, (const bf16*)d_out, (bf16*)dqkv, N, H, 0.125f);
+    } else {
+        if (smem > conf_f32) { TC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf_f32 = smem; }
+        attn_bwd_kernel<float><<<S * H, 256, smem, stream>>>((const float*)qkv, (const float*)d_out, (float*)dqkv, N, H, 0.125f);
+    }
+    TC_LAUNCH_CHECK();
+}
+
+}  // namespace tapclip

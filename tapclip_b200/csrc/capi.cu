@@ -1,0 +1,174 @@
+// extern "C" surface of libtapclip (see include/tapclip.h for the contract and the reference lines replaced).
+#include "engine.h"
+
+using namespace tapclip;
+
+#define TC_API_BEGIN try {
+#define TC_API_END                                                     \
+    return 0;                                                          \
+    }                                                                  \
+    catch (const tapclip::Error& e) { set_error(e.msg); return 1; }    \
+    catch (const std::exception& e) { set_error(e.what()); return 2; } \
+    catch (...) { set_error("unknown error"); return 3; }
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+#define NEED(h) TC_CHECK((h) != nullptr, "null tapclip handle")
+
+extern "C" {
+
+TAPCLIP_API const char* tapclip_last_error(void) { return get_error(); }
+TAPCLIP_API const char* tapclip_version(void) { return "tapclip-b200 0.1 (sm_100a: tcgen05/TMEM/TMA GEMM, mma.sync attention)"; }
+
+TAPCLIP_API int tapclip_create(const tapclip_config* cfg, tapclip_handle* out) {
+    TC_API_BEGIN
+    TC_CHECK(cfg != nullptr && out != nullptr, "null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    TC_CHECK(e == cudaSuccess && n > 0, "no CUDA device available: libtapclip has no CPU fallback");
+    *out = new tapclip_engine(*cfg);
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_destroy(tapclip_handle h) {
+    TC_API_BEGIN
+    delete h;
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_load_weight(tapclip_handle h, const char* name, const float* data, int32_t ndim, const int64_t* shape, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(name != nullptr && shape != nullptr, "null argument");
+    h->impl.load_weight(name, data, ndim, shape, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_weights_complete(tapclip_handle h) {
+    TC_API_BEGIN
+    NEED(h);
+    const std::string m = h->impl.missing_weights();
+    TC_CHECK(m.empty(), "weights missing: %s", m.c_str());
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int32_t B, float* out_feat, float* out_cls_rows, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(B == 0 || (images != nullptr && out_feat != nullptr), "null argument");
+    h->impl.encode_image(images, B, out_feat, out_cls_rows, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const float* tok, int32_t C, int32_t P, int32_t mode,
+                         int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(C == 0 || (ctx != nullptr && tok != nullptr), "null argument");
+    h->impl.text_forward(ctx, tok, C, P, mode, save_for_backward != 0, out_attr_raw, out_attr, out_text_feat, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_logits(tapclip_handle h, const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels,
+                   int32_t B, int32_t C, float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss,
+                   float* out_dlogits, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(img_feat && text_feat && logit_scale && out_img_norm && out_logits, "null argument");
+    h->impl.logits(img_feat, text_feat, logit_scale, labels, B, C, inv_batch_total, out_img_norm, out_logits, out_loss, out_dlogits, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_logits_backward(tapclip_handle h, const float* dlogits, const float* logits, const float* img_norm, const float* logit_scale,
+                            int32_t B, int32_t C, float* out_d_text, float* out_d_logit_scale, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(dlogits && logits && img_norm && logit_scale && out_d_text && out_d_logit_scale, "null argument");
+    h->impl.logits_backward(dlogits, logits, img_norm, logit_scale, B, C, out_d_text, out_d_logit_scale, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_text_backward(tapclip_handle h, const float* d_text_feat, float* out_dctx, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(d_text_feat && out_dctx, "null argument");
+    h->impl.text_backward(d_text_feat, out_dctx, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_adamw_step(tapclip_handle h, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(step >= 1, "AdamW step counter starts at 1");
+    adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, S(stream));
+    ++h->impl.launches;
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_argmax_count(tapclip_handle h, const float* logits, const int64_t* labels, int32_t B, int32_t C, int64_t* out_pred,
+                         int32_t* out_correct, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    argmax_count(logits, labels, out_pred, out_correct, B, C, S(stream));
+    ++h->impl.launches;
+    TC_API_END
+}
+
+TAPCLIP_API int64_t tapclip_workspace_bytes(tapclip_handle h) { return h ? h->impl.workspace_bytes() : -1; }
+TAPCLIP_API int64_t tapclip_launch_count(tapclip_handle h) { return h ? h->impl.launches : -1; }
+
+// ---- single-kernel entry points ------------------------------------------------------------------------
+TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K,
+                    int32_t dtype, int32_t epi, int32_t act, int32_t block_n, void* stream) {
+    TC_API_BEGIN
+    GemmArgs g;
+    g.a = a; g.w = w; g.bias = bias; g.out = out; g.out_pre = out_pre;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.block_n = block_n;
+    if (dtype == DT_BF16) gemm_tc(g, S(stream));
+    else gemm_simt_f32(g, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_layernorm(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out, int32_t out_dtype,
+                         float* x_copy, int64_t rows, int32_t d, void* stream) {
+    TC_API_BEGIN
+    layernorm_fwd(x, x_row_stride, gamma, beta, out, out_dtype == DT_BF16, x_copy, rows, d, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast, int32_t cast_dtype,
+                             int64_t rows, int32_t d, void* stream) {
+    TC_API_BEGIN
+    layernorm_bwd(dy, x, gamma, dx_acc, dx_cast, cast_dtype == DT_BF16, rows, d, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_attention(const void* qkv, void* out, int32_t dtype, int32_t S_, int32_t N, int32_t H, int32_t probe_mode,
+                         float* probe_out, int32_t probe_P, int64_t probe_seq_stride, void* stream) {
+    TC_API_BEGIN
+    AttnProbe p;
+    p.mode = probe_mode; p.out = probe_out; p.P = probe_P; p.seq_stride = probe_seq_stride;
+    attention_fwd(qkv, out, dtype == DT_BF16, S_, N, H, p, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_attention_bwd(const void* qkv, const void* d_out, void* dqkv, int32_t dtype, int32_t S_, int32_t N, int32_t H,
+                             void* stream) {
+    TC_API_BEGIN
+    attention_bwd(qkv, d_out, dqkv, dtype == DT_BF16, S_, N, H, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_attribution(const float* probe, float* raw, float* attr, int32_t C, int32_t H, int32_t P, void* stream) {
+    TC_API_BEGIN
+    attribution_reduce(probe, raw, attr, C, H, P, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_cast(const float* src, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
+    TC_API_BEGIN
+    cast_f32(src, dst, dst_dtype == DT_BF16, n, S(stream));
+    TC_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+// Engine behind the C ABI (include/tapclip.h): owns converted frozen weights + workspaces and enqueues the
+// kernel sequence of the attribution-instrumented CLIP forward and of the ctx-only backward.
+//
+// Schedule (SURVEY.md 3.2 de-duplicated): the reference runs 2*B*n_cls text-transformer calls per forward
+// (models/model_wrapper.py:48-75); none of them depends on the sample index b, so the engine runs ONE image
+// pass and at most TWO passes over [C,T,D] (attribution pass on the raw prompt, feature pass on the adjusted
+// prompt).  Residual streams stay fp32; bf16 is used only for tensor-core operands.
+#include "engine.h"
+
+#include <cstring>
+#include <map>
+#include <sstream>
+
+namespace tapclip {
+
+namespace {
+thread_local std::string g_error;
+}
+void set_error(const std::string& msg) { g_error = msg; }
+const char* get_error() { return g_error.c_str(); }
+
+namespace {
+
+template <typename T>
+__global__ void convert_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int R, int C, int dst_ld, int transpose) {
+    // dst is [R, dst_ld] (transpose == 0, dst[r][c] = src[r][c]) or [C, dst_ld] (transpose, dst[c][r] = src[r][c])
+    const int64_t total = (int64_t)R * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / C), c = (int)(i % C);
+        const float v = src[i];
+        if (transpose) dst[(int64_t)c * dst_ld + r] = from_f32<T>(v);
+        else dst[(int64_t)r * dst_ld + c] = from_f32<T>(v);
+    }
+}
+
+__global__ void fill_kernel(float* p, float v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------------
+void DevBuf::ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) TC_CUDA(cudaFree(p));
+    p = nullptr; bytes = 0;
+    const size_t want = (n + 255) & ~(size_t)255;
+    TC_CUDA(cudaMalloc(&p, want));
+    bytes = want;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+}
+
+Engine::Engine(const tapclip_config& c) : cfg(c) {
+    TC_CHECK(c.dtype == DT_F32 || c.dtype == DT_BF16, "dtype must be 0 (fp32) or 1 (bf16)");
+    TC_CHECK(c.act == ACT_GELU_ERF || c.act == ACT_QUICK_GELU, "act must be 0 (gelu_erf) or 1 (quick_gelu)");
+    TC_CHECK(c.image_size > 0 && c.patch_size > 0 && c.image_size % c.patch_size == 0, "image_size %% patch_size != 0");
+    TC_CHECK(c.vision_width == c.vision_heads * 64 && c.text_width == c.text_heads * 64,
+             "head dim must be 64 (vision %d/%d, text %d/%d)", c.vision_width, c.vision_heads, c.text_width, c.text_heads);
+    TC_CHECK(c.vision_width % 128 == 0 && c.text_width % 128 == 0 && c.embed_dim % 128 == 0 && c.vision_width <= 1024 &&
+                 c.text_width <= 1024 && c.embed_dim <= 1024,
+             "widths must be multiples of 128 and <= 1024");
+    TC_CHECK(c.vision_layers >= 1 && c.text_layers >= 1 && c.context_length >= 1, "bad layer count / context length");
+    int dev;
+    TC_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    TC_CUDA(cudaGetDeviceProperties(&prop, dev));
+    TC_CHECK(prop.major == 10, "libtapclip needs an sm_100 (B200) device, found sm_%d%d; there is no fallback path", prop.major, prop.minor);
+    bf = (c.dtype == DT_BF16);
+    esz = bf ? 2 : 4;
+    grid = c.image_size / c.patch_size;
+    n_tok = grid * grid + 1;
+    kpatch = 3 * c.patch_size * c.patch_size;
+    kpatch_pad = (int)round_up(kpatch, 64);
+    vis.resize(c.vision_layers);
+    txt.resize(c.text_layers);
+}
+
+Engine::~Engine() {
+    for (auto& kv : weights) cudaFree(kv.second);
+    for (DevBuf* b : all_bufs()) b->release();
+}
+
+std::vector<DevBuf*> Engine::all_bufs() {
+    return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled,
+            &t_x, &t_ln, &t_qkv, &t_attn, &t_h, &t_pooled, &t_feat, &t_tfeat, &t_inv_norm, &t_probe, &t_attr, &t_attr_raw,
+            &t_save_x, &t_save_qkv, &t_save_h, &b_dx, &b_dxc, &b_dh, &b_dln, &b_dattn, &b_dqkv, &b_dfeat, &b_dfeatc, &b_dpool,
+            &s_rows, &s_cls};
+}
+
+int64_t Engine::workspace_bytes() {
+    int64_t n = 0;
+    for (DevBuf* b : all_bufs()) n += (int64_t)b->bytes;
+    return n;
+}
+
+// ---- weights ---------------------------------------------------------------------------------------
+void* Engine::store(const std::string& key, const float* src, int R, int C, int dst_ld, bool transpose, bool as_act, cudaStream_t st) {
+    const bool to_bf16 = as_act && bf;
+    const int rows = transpose ? C : R;
+    const size_t bytes = (size_t)rows * dst_ld * (to_bf16 ? 2 : 4);
+    void* dst = nullptr;
+    auto it = weights.find(key);
+    if (it != weights.end()) { cudaFree(it->second); weights.erase(it); }
+    TC_CUDA(cudaMalloc(&dst, bytes));
+    weights[key] = dst;
+    TC_CUDA(cudaMemsetAsync(dst, 0, bytes, st));
+    const int64_t total = (int64_t)R * C;
+    const unsigned g = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
+    if (to_bf16) convert_weight_kernel<bf16><<<g, 256, 0, st>>>(src, (bf16*)dst, R, C, dst_ld, transpose ? 1 : 0);
+    else convert_weight_kernel<float><<<g, 256, 0, st>>>(src, (float*)dst, R, C, dst_ld, transpose ? 1 : 0);
+    TC_LAUNCH_CHECK();
+    ++launches;
+    return dst;
+}
+
+static bool shape_is(int ndim, const int64_t* s, std::initializer_list<int64_t> want) {
+    if (ndim != (int)want.size()) return false;
+    int i = 0;
+    for (int64_t w : want)
+        if (s[i++] != w) return false;
+    return true;
+}
+
+void Engine::load_weight(const std::string& name, const float* data, int ndim, const int64_t* shape, cudaStream_t st) {
+    TC_CHECK(data != nullptr, "null weight pointer for %s", name.c_str());
+    const int dv = cfg.vision_width, dt = cfg.text_width, E = cfg.embed_dim;
+    auto bad_shape = [&]() {
+        std::ostringstream os;
+        os << "weight " << name << " has unexpected shape [";
+        for (int i = 0; i < ndim; ++i) os << (i ? "," : "") << shape[i];
+        os << "]";
+        throw Error{os.str()};
+    };
+    // entries the hot path does not use
+    if (name == "token_embedding.weight" || name == "positional_embedding" || name == "ln_final.weight" ||
+        name == "ln_final.bias" || name == "logit_scale" || name == "attn_mask")
+        return;
+    if (name == "visual.conv1.weight") {
+        if (!shape_is(ndim, shape, {dv, 3, cfg.patch_size, cfg.patch_size})) bad_shape();
+        w_patch = store(name, data, dv, kpatch, kpatch_pad, false, true, st);
+        return;
+    }
+    if (name == "visual.class_embedding") { if (!shape_is(ndim, shape, {dv})) bad_shape(); cls_emb = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
+    if (name == "visual.positional_embedding") { if (!shape_is(ndim, shape, {n_tok, dv})) bad_shape(); pos_emb = (float*)store(name, data, n_tok, dv, dv, false, false, st); return; }
+    if (name == "visual.ln_pre.weight") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_pre_g = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
+    if (name == "visual.ln_pre.bias") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_pre_b = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
+    if (name == "visual.ln_post.weight") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_post_g = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
+    if (name == "visual.ln_post.bias") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_post_b = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
+    if (name == "visual.proj") { if (!shape_is(ndim, shape, {dv, E})) bad_shape(); w_vproj = store(name, data, dv, E, dv, true, true, st); return; }
+    if (name == "text_projection") {
+        if (!shape_is(ndim, shape, {dt, E})) bad_shape();
+        w_tproj = store(name, data, dt, E, dt, true, true, st);                 // [E, D] forward operand
+        wt_tproj = store(name + "#T", data, dt, E, E, false, true, st);         // [D, E] dgrad operand
+        return;
+    }
+    // transformer blocks
+    const std::string vp = "visual.transformer.resblocks.", tp = "transformer.resblocks.";
+    bool is_vis = name.compare(0, vp.size(), vp) == 0, is_txt = name.compare(0, tp.size(), tp) == 0;
+    TC_CHECK(is_vis || is_txt, "unknown weight name '%s'", name.c_str());
+    const std::string rest = name.substr(is_vis ? vp.size() : tp.size());
+    const size_t dot = rest.find('.');
+    TC_CHECK(dot != std::string::npos, "unknown weight name '%s'", name.c_str());
+    const int layer = atoi(rest.substr(0, dot).c_str());
+    const std::string leaf = rest.substr(dot + 1);
+    auto& blocks = is_vis ? vis : txt;
+    TC_CHECK(layer >= 0 && layer < (int)blocks.size(), "layer index out of range in '%s'", name.c_str());
+    BlockWeights& b = blocks[layer];
+    const int d = is_vis ? dv : dt;
+    const bool need_t = is_txt;          // dgrad copies only for the text tower (the image tower gets no gradient)
+    auto vec = [&](float*& slot, int n) { if (!shape_is(ndim, shape, {n})) bad_shape(); slot = (float*)store(name, data, 1, n, n, false, false, st); };
+    auto mat = [&](void*& w, void*& wt, int N, int K) {
+        if (!shape_is(ndim, shape, {N, K})) bad_shape();
+        w = store(name, data, N, K, K, false, true, st);
+        if (need_t) wt = store(name + "#T", data, N, K, N, true, true, st);     // [K, N]
+    };
+    if (leaf == "ln_1.weight") vec(b.ln1_g, d);
+    else if (leaf == "ln_1.bias") vec(b.ln1_b, d);
+    else if (leaf == "ln_2.weight") vec(b.ln2_g, d);
+    else if (leaf == "ln_2.bias") vec(b.ln2_b, d);
+    else if (leaf == "attn.in_proj_weight") mat(b.w_qkv, b.wt_qkv, 3 * d, d);
+    else if (leaf == "attn.in_proj_bias") vec(b.b_qkv, 3 * d);
+    else if (leaf == "attn.out_proj.weight") mat(b.w_o, b.wt_o, d, d);
+    else if (leaf == "attn.out_proj.bias") vec(b.b_o, d);
+    else if (leaf == "mlp.c_fc.weight") mat(b.w_fc, b.wt_fc, 4 * d, d);
+    else if (leaf == "mlp.c_fc.bias") vec(b.b_fc, 4 * d);
+    else if (leaf == "mlp.c_proj.weight") mat(b.w_proj, b.wt_proj, d, 4 * d);
+    else if (leaf == "mlp.c_proj.bias") vec(b.b_proj, d);
+    else TC_CHECK(false, "unknown weight name '%s'", name.c_str());
+}
+
+std::string Engine::missing_weights() const {
+    std::ostringstream os;
+    auto need = [&](const void* p, const std::string& n) { if (!p) os << n << " "; };
+    need(w_patch, "visual.conv1.weight"); need(cls_emb, "visual.class_embedding"); need(pos_emb, "visual.positional_embedding");
+    need(ln_pre_g, "visual.ln_pre.weight"); need(ln_pre_b, "visual.ln_pre.bias"); need(ln_post_g, "visual.ln_post.weight");
+    need(ln_post_b, "visual.ln_post.bias"); need(w_vproj, "visual.proj"); need(w_tproj, "text_projection");
+    for (int t = 0; t < 2; ++t) {
+        const auto& blocks = t ? txt : vis;
+        const std::string pre = t ? "transformer.resblocks." : "visual.transformer.resblocks.";
+        for (size_t i = 0; i < blocks.size(); ++i) {
+            const BlockWeights& b = blocks[i];
+            const std::string p = pre + std::to_string(i) + ".";
+            need(b.ln1_g, p + "ln_1.weight"); need(b.ln1_b, p + "ln_1.bias"); need(b.ln2_g, p + "ln_2.weight"); need(b.ln2_b, p + "ln_2.bias");
+            need(b.w_qkv, p + "attn.in_proj_weight"); need(b.b_qkv, p + "attn.in_proj_bias"); need(b.w_o, p + "attn.out_proj.weight");
+            need(b.b_o, p + "attn.out_proj.bias"); need(b.w_fc, p + "mlp.c_fc.weight"); need(b.b_fc, p + "mlp.c_fc.bias");
+            need(b.w_proj, p + "mlp.c_proj.weight"); need(b.b_proj, p + "mlp.c_proj.bias");
+        }
+    }
+    return os.str();
+}
+
+// ---- primitive wrappers ------------------------------------------------------------------------------
+void Engine::gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K,
+                  int epi, int act, cudaStream_t st) {
+    GemmArgs g;
+    g.a = a; g.w = w; g.bias = bias; g.out = out; g.out_pre = out_pre;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act;
+    if (bf) gemm_tc(g, st);
+    else gemm_simt_f32(g, st);
+    ++launches;
+}
+
+// one residual attention block on x [S*N, d] (fp32, updated in place).
+//   probe      : attention probe for this layer (or PROBE_NONE)
+//   stop_after_attention_probs : attribution pass, last block: only the probabilities are needed
+//   save       : keep x copies / qkv / h_pre for the backward pass (slot = layer)
+void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
+                           DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st) {
+    const int64_t M = (int64_t)S * N;
+    float* sx0 = nullptr; float* sx1 = nullptr; void* sqkv = qkv.p; void* shpre = nullptr;
+    if (save_slot >= 0) {
+        sx0 = (float*)t_save_x.p + (int64_t)(2 * save_slot) * M * d;
+        sx1 = (float*)t_save_x.p + (int64_t)(2 * save_slot + 1) * M * d;
+        sqkv = (uint8_t*)t_save_qkv.p + (int64_t)save_slot * M * 3 * d * esz;
+        shpre = (uint8_t*)t_save_h.p + (int64_t)save_slot * M * 4 * d * esz;
+    }
+    layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, bf, sx0, M, d, st); ++launches;
+    gemm(ln.p, b.w_qkv, b.b_qkv, sqkv, nullptr, M, 3 * d, d, EPI_BF16, ACT_NONE, st);
+    attention_fwd(sqkv, attn.p, bf, S, N, H, probe, st); ++launches;
+    if (probs_only) return;
+    gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, st);
+    layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, bf, sx1, M, d, st); ++launches;
+    gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, M, 4 * d, d, EPI_BF16, cfg.act, st);
+    gemm(hbuf.p, b.w_proj, b.b_proj, x, nullptr, M, d, 4 * d, EPI_F32_ADD, ACT_NONE, st);
+}
+
+// ---- image tower (row A4) ---------------------------------------------------------------------------
+void Engine::encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, cudaStream_t st) {
+    TC_CHECK(B >= 0, "negative batch");
+    if (B == 0) return;
+    const std::string miss = missing_weights();
+    TC_CHECK(miss.empty(), "weights missing: %s", miss.c_str());
+    const int d = cfg.vision_width, H = cfg.vision_heads, N = n_tok, L = cfg.vision_layers, E = cfg.embed_dim;
+    const int64_t Mp = (int64_t)B * grid * grid, M = (int64_t)B * N;
+    v_patches.ensure(Mp * kpatch_pad * esz);
+    v_patch_out.ensure(Mp * d * 4);
+    v_x.ensure(M * d * 4);
+    v_ln.ensure(M * d * esz);
+    v_qkv.ensure(M * 3 * d * esz);
+    v_attn.ensure(M * d * esz);
+    v_h.ensure(M * 4 * d * esz);
+    v_pooled.ensure((int64_t)B * d * esz);
+
+    patchify(images, v_patches.p, bf, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
+    gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, st);
+    assemble_tokens((const float*)v_patch_out.p, cls_emb, pos_emb, (float*)v_x.p, B, N, d, st); ++launches;
+    layernorm_fwd((const float*)v_x.p, d, ln_pre_g, ln_pre_b, v_x.p, false, nullptr, M, d, st); ++launches;
+    for (int l = 0; l < L; ++l) {
+        AttnProbe probe;
+        if (out_cls_rows) {
+            probe.mode = PROBE_CLS_ROW;
+            probe.out = out_cls_rows + (int64_t)l * H * N;
+            probe.seq_stride = (int64_t)L * H * N;
+        }
+        block_forward(vis[l], (float*)v_x.p, B, N, d, H, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st);
+    }
+    layernorm_fwd((const float*)v_x.p, (int64_t)N * d, ln_post_g, ln_post_b, v_pooled.p, bf, nullptr, B, d, st); ++launches;
+    gemm(v_pooled.p, w_vproj, nullptr, out_feat, nullptr, B, E, d, EPI_F32, ACT_NONE, st);
+}
+
+// ---- text side (rows A2, A6-A10) ----------------------------------------------------------------------
+void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw,
+                          float* out_attr, float* out_text_feat, cudaStream_t st) {
+    TC_CHECK(C >= 0 && P >= 1, "bad class count / prompt length");
+    TC_CHECK(mode == 0 || mode == 1, "attribution mode must be 0 (literal) or 1 (intended)");
+    saved.valid = false;
+    if (C == 0) return;
+    const std::string miss = missing_weights();
+    TC_CHECK(miss.empty(), "weights missing: %s", miss.c_str());
+    const int D = cfg.text_width, H = cfg.text_heads, Lc = cfg.context_length, T = P + Lc, L = cfg.text_layers, E = cfg.embed_dim;
+    const int64_t M = (int64_t)C * T;
+    t_x.ensure(M * D * 4);
+    t_ln.ensure(M * D * esz);
+    t_qkv.ensure(M * 3 * D * esz);
+    t_attn.ensure(M * D * esz);
+    t_h.ensure(M * 4 * D * esz);
+    t_pooled.ensure((int64_t)C * D * esz);
+    t_feat.ensure((int64_t)C * E * 4);
+    t_tfeat.ensure((int64_t)C * E * 4);
+    t_inv_norm.ensure((int64_t)C * 4);
+    const int PA = (mode == 1) ? P : 1;
+    t_attr.ensure((int64_t)C * PA * 4);
+    t_attr_raw.ensure((int64_t)C * PA * 4);
+    if (save) {
+        TC_CHECK(T <= 128, "training needs prompt_len + context_length <= 128 (attention backward), got %d", T);
+        t_save_x.ensure((int64_t)2 * L * M * D * 4);
+        t_save_qkv.ensure((int64_t)L * M * 3 * D * esz);
+        t_save_h.ensure((int64_t)L * M * 4 * D * esz);
+    }
+    float* x = (float*)t_x.p;
+    const float* attr = nullptr;
+    if (mode == 1) {
+        // attribution pass (rows A7/A8): un-adjusted prompt, probabilities of the last block only
+        TC_CHECK(P <= 64, "prompt_len %d unsupported (<= 64)", P);
+        t_probe.ensure((int64_t)C * H * P * 4);
+        splice_prompts(ctx, tok, nullptr, 1, x, C, P, Lc, D, st); ++launches;
+        for (int l = 0; l < L; ++l) {
+            AttnProbe probe;
+            const bool last = (l == L - 1);
+            if (last) { probe.mode = PROBE_TEXT_COL; probe.out = (float*)t_probe.p; probe.P = P; }
+            block_forward(txt[l], x, C, T, D, H, t_ln, t_qkv, t_attn, t_h, probe, last, -1, st);
+        }
+        attribution_reduce((const float*)t_probe.p, (float*)t_attr_raw.p, (float*)t_attr.p, C, H, P, st); ++launches;
+        attr = (const float*)t_attr.p;
+        if (out_attr_raw) TC_CUDA(cudaMemcpyAsync(out_attr_raw, t_attr_raw.p, (size_t)C * P * 4, cudaMemcpyDeviceToDevice, st));
+        if (out_attr) TC_CUDA(cudaMemcpyAsync(out_attr, t_attr.p, (size_t)C * P * 4, cudaMemcpyDeviceToDevice, st));
+    } else if (out_attr) {
+        // literal mode: the reference's attribution is identically 1.0; ctx*1 == ctx
+        fill_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(out_attr, 1.0f, C);
+        TC_LAUNCH_CHECK(); ++launches;
+    }
+    // feature pass (rows A9/A10)
+    splice_prompts(ctx, tok, attr, PA, x, C, P, Lc, D, st); ++launches;
+    for (int l = 0; l < L; ++l) {
+        AttnProbe none;
+        block_forward(txt[l], x, C, T, D, H, t_ln, t_qkv, t_attn, t_h, none, false, save ? l : -1, st);
+    }
+    gather_rows(x, t_pooled.p, bf, C, T, T - 1, D, st); ++launches;
+    gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, st);
+    l2norm_fwd((const float*)t_feat.p, (float*)t_tfeat.p, (float*)t_inv_norm.p, C, E, st); ++launches;
+    if (out_text_feat) TC_CUDA(cudaMemcpyAsync(out_text_feat, t_tfeat.p, (size_t)C * E * 4, cudaMemcpyDeviceToDevice, st));
+    if (save) { saved.valid = true; saved.C = C; saved.P = P; saved.T = T; saved.PA = PA; saved.has_attr = (mode == 1); }
+}
+
+// ---- backward to ctx (row A13) ---------------------------------------------------------------------------
+void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st) {
+    TC_CHECK(saved.valid, "tapclip_text_backward needs a preceding tapclip_text_forward(save_for_backward=1)");
+    const int C = saved.C, P = saved.P, T = saved.T;
+    const int D = cfg.text_width, H = cfg.text_heads, L = cfg.text_layers, E = cfg.embed_dim;
+    const int64_t M = (int64_t)C * T;
+    b_dx.ensure(M * D * 4);
+    b_dxc.ensure(M * D * esz);
+    b_dh.ensure(M * 4 * D * esz);
+    b_dln.ensure(M * D * 4);
+    b_dattn.ensure(M * D * esz);
+    b_dqkv.ensure(M * 3 * D * esz);
+    b_dfeat.ensure((int64_t)C * E * 4);
+    b_dfeatc.ensure((int64_t)C * E * esz);
+    b_dpool.ensure((int64_t)C * D * 4);
+    // L2-norm and projection backward (model_wrapper.py:74-75), then scatter into the last position (:73)
+    l2norm_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, (float*)b_dfeat.p, b_dfeatc.p, bf, C, E, st); ++launches;
+    gemm(b_dfeatc.p, wt_tproj, nullptr, b_dpool.p, nullptr, C, D, E, EPI_F32, ACT_NONE, st);
+    TC_CUDA(cudaMemsetAsync(b_dx.p, 0, (size_t)M * D * 4, st));
+    TC_CUDA(cudaMemsetAsync(b_dxc.p, 0, (size_t)M * D * esz, st));
+    scatter_rows((const float*)b_dpool.p, (float*)b_dx.p, b_dxc.p, bf, C, T, T - 1, D, st); ++launches;
+    for (int l = L - 1; l >= 0; --l) {
+        const BlockWeights& b = txt[l];
+        const float* x0 = (const float*)t_save_x.p + (int64_t)(2 * l) * M * D;
+        const float* x1 = (const float*)t_save_x.p + (int64_t)(2 * l + 1) * M * D;
+        const void* qkv = (const uint8_t*)t_save_qkv.p + (int64_t)l * M * 3 * D * esz;
+        const void* hpre = (const uint8_t*)t_save_h.p + (int64_t)l * M * 4 * D * esz;
+        // MLP branch
+        gemm(b_dxc.p, b.wt_proj, nullptr, b_dh.p, nullptr, M, 4 * D, D, EPI_BF16, ACT_NONE, st);
+        act_bwd_inplace(b_dh.p, hpre, bf, cfg.act, M * 4 * D, st); ++launches;
+        gemm(b_dh.p, b.wt_fc, nullptr, b_dln.p, nullptr, M, D, 4 * D, EPI_F32, ACT_NONE, st);
+        layernorm_bwd((const float*)b_dln.p, x1, b.ln2_g, (float*)b_dx.p, b_dxc.p, bf, M, D, st); ++launches;
+        // attention branch
+        gemm(b_dxc.p, b.wt_o, nullptr, b_dattn.p, nullptr, M, D, D, EPI_BF16, ACT_NONE, st);
+        attention_bwd(qkv, b_dattn.p, b_dqkv.p, bf, C, T, H, st); ++launches;
+        gemm(b_dqkv.p, b.wt_qkv, nullptr, b_dln.p, nullptr, M, D, 3 * D, EPI_F32, ACT_NONE, st);
+        layernorm_bwd((const float*)b_dln.p, x0, b.ln1_g, (float*)b_dx.p, b_dxc.p, bf, M, D, st); ++launches;
+    }
+    splice_bwd((const float*)b_dx.p, saved.has_attr ? (const float*)t_attr.p : nullptr, saved.PA, out_dctx, C, P, T, D, st); ++launches;
+}
+
+// ---- logits / loss (rows A5, A11, A12) ------------------------------------------------------------------------
+void Engine::logits(const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels, int B, int C,
+                    float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss, float* out_dlogits,
+                    cudaStream_t st) {
+    if (B == 0 || C == 0) return;
+    const int E = cfg.embed_dim;
+    l2norm_fwd(img_feat, out_img_norm, nullptr, B, E, st); ++launches;
+    cosine_logits(out_img_norm, text_feat, logit_scale, out_logits, B, C, E, st); ++launches;
+    if (labels) {
+        TC_CHECK(out_loss != nullptr, "out_loss is required when labels are given");
+        s_rows.ensure((size_t)B * 4);
+        cross_entropy(out_logits, labels, out_loss, out_dlogits, (float*)s_rows.p, B, C, inv_batch_total, st); launches += 2;
+    }
+}
+
+void Engine::logits_backward(const float* dlogits, const float* logits_, const float* img_norm, const float* logit_scale, int B,
+                             int C, float* out_d_text, float* out_d_scale, cudaStream_t st) {
+    if (C == 0) return;
+    s_cls.ensure((size_t)C * 4);
+    logits_bwd(dlogits, logits_, img_norm, logit_scale, out_d_text, out_d_scale, (float*)s_cls.p, B, C, cfg.embed_dim, st);
+    launches += 2;
+}
+
+}  // namespace tapclip

@@ -1,0 +1,76 @@
+// Engine state behind the opaque tapclip_handle.
+#pragma once
+#include "../../include/tapclip.h"
+#include "gemm.h"
+#include "kernels.h"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace tapclip {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t n);      // grow-only
+    void release();
+};
+
+struct BlockWeights {
+    float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    float *b_qkv = nullptr, *b_o = nullptr, *b_fc = nullptr, *b_proj = nullptr;
+    void *w_qkv = nullptr, *w_o = nullptr, *w_fc = nullptr, *w_proj = nullptr;        // [N,K], activation type
+    void *wt_qkv = nullptr, *wt_o = nullptr, *wt_fc = nullptr, *wt_proj = nullptr;    // [K,N] dgrad operands (text tower)
+};
+
+struct Engine {
+    tapclip_config cfg;
+    bool bf = true;             // activation / GEMM operand type is bf16 (else fp32)
+    int esz = 2;                // bytes per activation element
+    int grid = 0, n_tok = 0, kpatch = 0, kpatch_pad = 0;
+    int64_t launches = 0;
+
+    std::map<std::string, void*> weights;     // owning storage, keyed by state-dict name (+"#T" for transposes)
+    void* w_patch = nullptr; float* cls_emb = nullptr; float* pos_emb = nullptr;
+    float *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
+    void *w_vproj = nullptr, *w_tproj = nullptr, *wt_tproj = nullptr;
+    std::vector<BlockWeights> vis, txt;
+
+    // workspaces (grow-only)
+    DevBuf v_patches, v_patch_out, v_x, v_ln, v_qkv, v_attn, v_h, v_pooled;
+    DevBuf t_x, t_ln, t_qkv, t_attn, t_h, t_pooled, t_feat, t_tfeat, t_inv_norm, t_probe, t_attr, t_attr_raw;
+    DevBuf t_save_x, t_save_qkv, t_save_h;
+    DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
+    DevBuf s_rows, s_cls;
+    struct { bool valid = false; int C = 0, P = 0, T = 0, PA = 1; bool has_attr = false; } saved;
+
+    explicit Engine(const tapclip_config& c);
+    ~Engine();
+    std::vector<DevBuf*> all_bufs();
+    int64_t workspace_bytes();
+
+    void* store(const std::string& key, const float* src, int R, int C, int dst_ld, bool transpose, bool as_act, cudaStream_t st);
+    void load_weight(const std::string& name, const float* data, int ndim, const int64_t* shape, cudaStream_t st);
+    std::string missing_weights() const;
+
+    void gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int epi,
+              int act, cudaStream_t st);
+    void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf,
+                       const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st);
+    void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, cudaStream_t st);
+    void text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
+                      float* out_text_feat, cudaStream_t st);
+    void text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st);
+    void logits(const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels, int B, int C,
+                float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss, float* out_dlogits, cudaStream_t st);
+    void logits_backward(const float* dlogits, const float* logits_, const float* img_norm, const float* logit_scale, int B, int C,
+                         float* out_d_text, float* out_d_scale, cudaStream_t st);
+};
+
+}  // namespace tapclip
+
+struct tapclip_engine {
+    tapclip::Engine impl;
+    explicit tapclip_engine(const tapclip_config& c) : impl(c) {}
+};

@@ -1,0 +1,34 @@
+// GEMM entry points shared by the engine:  out[M,N] = epilogue(A[M,K] * W[N,K]^T + bias[N])
+#pragma once
+#include "common.cuh"
+#include <algorithm>
+
+namespace tapclip {
+
+enum Epi : int {
+    EPI_BF16 = 0,      // out (bf16) = act(acc + bias);  optional out_pre (bf16) = acc + bias
+    EPI_F32 = 1,       // out (f32)  = acc + bias
+    EPI_F32_ADD = 2,   // out (f32) += acc + bias        (residual stream update)
+};
+
+struct GemmArgs {
+    const void* a = nullptr;   // [M, K] row-major, leading dimension lda (elements); bf16 (tc) or f32 (simt)
+    const void* w = nullptr;   // [N, K] row-major (nn.Linear weight layout), leading dimension ldw
+    void* out = nullptr;       // [M, N], leading dimension ldo
+    void* out_pre = nullptr;   // optional pre-activation copy (same type/ld as out)
+    const float* bias = nullptr;
+    int64_t M = 0, N = 0, K = 0;
+    int64_t lda = 0, ldw = 0, ldo = 0;
+    int epi = EPI_F32;
+    int act = ACT_NONE;
+    int block_n = 0;           // 0 = choose; 128 or 256 force a tile width (tcgen05 path only)
+};
+
+// tcgen05/TMEM/TMA path: A and W bf16; out bf16 (EPI_BF16) or f32
+void gemm_tc(const GemmArgs& g, cudaStream_t stream);
+
+// fp32 SIMT path for the fp32 parity mode: A, W, out all f32; EPI_BF16 means "store in the activation
+// type" (f32 here) with the optional activation / pre-activation copy
+void gemm_simt_f32(const GemmArgs& g, cudaStream_t stream);
+
+}  // namespace tapclip

@@ -1,0 +1,210 @@
+// Row-wise normalisation kernels (HBM-bound): LayerNorm fwd/bwd and L2-norm fwd/bwd.
+// One warp per row, the whole row lives in registers (d <= 1024, d % 128 == 0), float4 loads,
+// statistics in fp32 via warp shuffles.  Replaces ATen layer_norm and the
+// `x / x.norm(dim=-1, keepdim=True)` pairs of models/model_wrapper.py:41,75.
+#include "kernels.h"
+
+namespace tapclip {
+namespace {
+
+constexpr int MAXV = 8;          // float4 per lane -> d <= 1024
+constexpr int WARPS = 8;
+
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+layernorm_fwd_kernel(const float* x, int64_t x_row_stride, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, T* out, float* x_copy, int64_t rows, int d) {
+    const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, nv = d >> 7;
+    const float* xr = x + row * x_row_stride;
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + e * e);
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            if (x_copy) *reinterpret_cast<float4*>(x_copy + row * d + c) = v[i];
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * g.x + b.x;
+            o.y = (v[i].y - mean) * rstd * g.y + b.y;
+            o.z = (v[i].z - mean) * rstd * g.z + b.z;
+            o.w = (v[i].w - mean) * rstd * g.w + b.w;
+            store4<T>(out + row * d + c, o);
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     float* dx_acc, T* dx_cast, int64_t rows, int d) {
+    const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, nv = d >> 7;
+    float4 v[MAXV], g[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            v[i] = *reinterpret_cast<const float4*>(x + row * d + (i * 32 + lane) * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+    // g = dy * gamma ; xhat = (x-mean)*rstd ; dx = rstd * (g - mean(g) - xhat*mean(g*xhat))
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            const float4 dyv = *reinterpret_cast<const float4*>(dy + row * d + c);
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            g[i].x = dyv.x * gm.x; g[i].y = dyv.y * gm.y; g[i].z = dyv.z * gm.z; g[i].w = dyv.w * gm.w;
+            v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;
+            sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+            sgx += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+        }
+    const float mg = warp_sum(sg) / (float)d, mgx = warp_sum(sgx) / (float)d;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            float4 a = *reinterpret_cast<const float4*>(dx_acc + row * d + c);
+            a.x += rstd * (g[i].x - mg - v[i].x * mgx);
+            a.y += rstd * (g[i].y - mg - v[i].y * mgx);
+            a.z += rstd * (g[i].z - mg - v[i].z * mgx);
+            a.w += rstd * (g[i].w - mg - v[i].w * mgx);
+            *reinterpret_cast<float4*>(dx_acc + row * d + c) = a;
+            if (dx_cast) store4<T>(dx_cast + row * d + c, a);
+        }
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+l2norm_fwd_kernel(const float* __restrict__ x, float* out, float* inv_norm, int64_t rows, int d) {
+    const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, nv = d >> 7;
+    float4 v[MAXV];
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            v[i] = *reinterpret_cast<const float4*>(x + row * d + (i * 32 + lane) * 4);
+            q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+    const float inv = 1.0f / sqrtf(warp_sum(q));
+    if (inv_norm && lane == 0) inv_norm[row] = inv;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            float4 o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+            *reinterpret_cast<float4*>(out + row * d + (i * 32 + lane) * 4) = o;
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+l2norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xhat, const float* __restrict__ inv_norm,
+                  float* dx, T* dx_cast, int64_t rows, int d) {
+    const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, nv = d >> 7;
+    float4 gv[MAXV], xv[MAXV];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            gv[i] = *reinterpret_cast<const float4*>(g + row * d + c);
+            xv[i] = *reinterpret_cast<const float4*>(xhat + row * d + c);
+            dot += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+        }
+    dot = warp_sum(dot);
+    const float inv = inv_norm[row];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            float4 o;
+            o.x = (gv[i].x - xv[i].x * dot) * inv; o.y = (gv[i].y - xv[i].y * dot) * inv;
+            o.z = (gv[i].z - xv[i].z * dot) * inv; o.w = (gv[i].w - xv[i].w * dot) * inv;
+            *reinterpret_cast<float4*>(dx + row * d + c) = o;
+            if (dx_cast) store4<T>(dx_cast + row * d + c, o);
+        }
+}
+
+void check_d(int d) { TC_CHECK(d % 128 == 0 && d >= 128 && d <= 128 * MAXV, "row width %d unsupported (need d %% 128 == 0, d <= 1024)", d); }
+
+}  // namespace
+
+void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out, bool out_is_bf16,
+                   float* x_copy, int64_t rows, int d, cudaStream_t stream) {
+    check_d(d);
+    if (rows == 0) return;
+    const unsigned grid = (unsigned)ceil_div(rows, WARPS);
+    if (out_is_bf16) layernorm_fwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (bf16*)out, x_copy, rows, d);
+    else layernorm_fwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (float*)out, x_copy, rows, d);
+    TC_LAUNCH_CHECK();
+}
+
+void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast, bool cast_is_bf16,
+                   int64_t rows, int d, cudaStream_t stream) {
+    check_d(d);
+    if (rows == 0) return;
+    const unsigned grid = (unsigned)ceil_div(rows, WARPS);
+    if (cast_is_bf16) layernorm_bwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d);
+    else layernorm_bwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(dy, x, gamma, dx_acc, (float*)dx_cast, rows, d);
+    TC_LAUNCH_CHECK();
+}
+
+void l2norm_fwd(const float* x, float* out, float* inv_norm, int64_t rows, int d, cudaStream_t stream) {
+    check_d(d);
+    if (rows == 0) return;
+    l2norm_fwd_kernel<<<(unsigned)ceil_div(rows, WARPS), WARPS * 32, 0, stream>>>(x, out, inv_norm, rows, d);
+    TC_LAUNCH_CHECK();
+}
+
+void l2norm_bwd(const float* g, const float* xhat, const float* inv_norm, float* dx, void* dx_cast, bool cast_is_bf16,
+                int64_t rows, int d, cudaStream_t stream) {
+    check_d(d);
+    if (rows == 0) return;
+    const unsigned grid = (unsigned)ceil_div(rows, WARPS);
+    if (cast_is_bf16) l2norm_bwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(g, xhat, inv_norm, dx, (bf16*)dx_cast, rows, d);
+    else l2norm_bwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(g, xhat, inv_norm, dx, (float*)dx_cast, rows, d);
+    TC_LAUNCH_CHECK();
+}
+
+}  // namespace tapclip

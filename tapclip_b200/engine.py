@@ -1,0 +1,138 @@
+"""Thin Python handle around libtapclip's engine: tensors in, tensors out, all work on the current stream."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .configs import ModelConfig
+
+
+def _check_cuda_f32(t: torch.Tensor, name: str):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous fp32 CUDA tensor (got {t.dtype}, {t.device}, contiguous={t.is_contiguous()})")
+
+
+class Engine:
+    """One engine per device.  ``dtype``: 'bf16' (tcgen05 tensor-core path) or 'fp32' (SIMT parity mode)."""
+
+    def __init__(self, cfg: ModelConfig, dtype: str = "bf16", device="cuda"):
+        if dtype not in _lib.DTYPE:
+            raise ValueError(f"dtype must be one of {sorted(_lib.DTYPE)}, got {dtype!r}")
+        if not torch.cuda.is_available():
+            raise _lib.TapclipError("tapclip_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg, self.dtype = cfg, dtype
+        self.device = torch.device(device if device != "cuda" else f"cuda:{torch.cuda.current_device()}")
+        c = _lib.TapclipConfig(cfg.image_size, cfg.patch_size, cfg.vision_width, cfg.vision_layers, cfg.vision_heads,
+                               cfg.text_width, cfg.text_layers, cfg.text_heads, cfg.embed_dim, cfg.context_length,
+                               _lib.ACT["quick_gelu" if cfg.quick_gelu else "gelu_erf"], _lib.DTYPE[dtype])
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tapclip_create(C.byref(c), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self.lib.tapclip_destroy(h)
+            except Exception:
+                pass
+            self._h = C.c_void_p()
+
+    # ---- weights -----------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict):
+        """One tapclip_load_weight per entry (open_clip key names); replaces clip_wrapper.py:14-15."""
+        with torch.cuda.device(self.device):
+            for name, t in state_dict.items():
+                w = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+                shape = (C.c_int64 * max(w.dim(), 1))(*w.shape)
+                _lib.check(self.lib.tapclip_load_weight(self._h, name.encode(), _lib.ptr(w), w.dim(), shape, _lib.stream_ptr()))
+            torch.cuda.current_stream().synchronize()      # staging copies `w` may be freed after this
+            _lib.check(self.lib.tapclip_weights_complete(self._h))
+
+    # ---- hot path -------------------------------------------------------------------------------------
+    def encode_image(self, images: torch.Tensor, want_cls_rows: bool = False):
+        _check_cuda_f32(images, "images")
+        cfg = self.cfg
+        if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != cfg.image_size or images.shape[3] != cfg.image_size:
+            raise ValueError(f"images must be [B,3,{cfg.image_size},{cfg.image_size}], got {tuple(images.shape)}")
+        B = images.shape[0]
+        feat = torch.empty(B, cfg.embed_dim, device=images.device, dtype=torch.float32)
+        rows = None
+        if want_cls_rows:
+            rows = torch.empty(B, cfg.vision_layers, cfg.vision_heads, cfg.vision_tokens, device=images.device, dtype=torch.float32)
+        _lib.check(self.lib.tapclip_encode_image(self._h, _lib.ptr(images), B, _lib.ptr(feat), _lib.ptr(rows), _lib.stream_ptr()))
+        return (feat, rows) if want_cls_rows else feat
+
+    def text_forward(self, ctx: torch.Tensor, tok: torch.Tensor, mode: str, save_for_backward: bool):
+        _check_cuda_f32(ctx, "ctx")
+        _check_cuda_f32(tok, "tok")
+        cfg = self.cfg
+        Cn, P, D = ctx.shape
+        if tok.shape != (Cn, cfg.context_length, D) or D != cfg.text_width:
+            raise ValueError(f"Unexpected token shape: {tuple(tok.shape)} for ctx {tuple(ctx.shape)}")
+        pa = P if mode == "intended" else 1
+        attr = torch.empty(Cn, pa, device=ctx.device, dtype=torch.float32)
+        raw = torch.empty(Cn, pa, device=ctx.device, dtype=torch.float32) if mode == "intended" else None
+        feat = torch.empty(Cn, cfg.embed_dim, device=ctx.device, dtype=torch.float32)
+        _lib.check(self.lib.tapclip_text_forward(self._h, _lib.ptr(ctx), _lib.ptr(tok), Cn, P, _lib.ATTR_MODE[mode],
+                                                 1 if save_for_backward else 0, _lib.ptr(raw), _lib.ptr(attr), _lib.ptr(feat),
+                                                 _lib.stream_ptr()))
+        return feat, attr, raw
+
+    def logits(self, img_feat, text_feat, logit_scale, labels=None, inv_batch_total=None):
+        B, Cn = img_feat.shape[0], text_feat.shape[0]
+        dev = img_feat.device
+        img_norm = torch.empty_like(img_feat)
+        logits = torch.empty(B, Cn, device=dev, dtype=torch.float32)
+        loss = dlogits = None
+        if labels is not None:
+            if labels.dtype != torch.int64 or not labels.is_cuda:
+                raise ValueError("labels must be an int64 CUDA tensor")
+            loss = torch.zeros((), device=dev, dtype=torch.float32)
+            dlogits = torch.empty_like(logits)
+            labels = labels.contiguous()
+        inv = float(inv_batch_total) if inv_batch_total is not None else (1.0 / max(B, 1))
+        _lib.check(self.lib.tapclip_logits(self._h, _lib.ptr(img_feat), _lib.ptr(text_feat), _lib.ptr(logit_scale), _lib.ptr(labels),
+                                           B, Cn, inv, _lib.ptr(img_norm), _lib.ptr(logits), _lib.ptr(loss), _lib.ptr(dlogits),
+                                           _lib.stream_ptr()))
+        return logits, loss, dlogits, img_norm
+
+    def logits_backward(self, dlogits, logits, img_norm, logit_scale):
+        B, Cn = logits.shape
+        d_text = torch.empty(Cn, self.cfg.embed_dim, device=logits.device, dtype=torch.float32)
+        d_scale = torch.zeros((), device=logits.device, dtype=torch.float32)
+        _lib.check(self.lib.tapclip_logits_backward(self._h, _lib.ptr(dlogits), _lib.ptr(logits), _lib.ptr(img_norm),
+                                                    _lib.ptr(logit_scale), B, Cn, _lib.ptr(d_text), _lib.ptr(d_scale),
+                                                    _lib.stream_ptr()))
+        return d_text, d_scale
+
+    def text_backward(self, d_text_feat, n_cls: int, prompt_len: int):
+        _check_cuda_f32(d_text_feat, "d_text_feat")
+        dctx = torch.empty(n_cls, prompt_len, self.cfg.text_width, device=d_text_feat.device, dtype=torch.float32)
+        _lib.check(self.lib.tapclip_text_backward(self._h, _lib.ptr(d_text_feat), _lib.ptr(dctx), _lib.stream_ptr()))
+        return dctx
+
+    def adamw_step(self, param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step):
+        for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+            _check_cuda_f32(t, n)
+        _lib.check(self.lib.tapclip_adamw_step(self._h, _lib.ptr(param), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
+                                               param.numel(), lr, betas[0], betas[1], eps, weight_decay, step, _lib.stream_ptr()))
+
+    def argmax_count(self, logits, labels=None):
+        B, Cn = logits.shape
+        pred = torch.empty(B, device=logits.device, dtype=torch.int64)
+        correct = torch.zeros((), device=logits.device, dtype=torch.int32) if labels is not None else None
+        _lib.check(self.lib.tapclip_argmax_count(self._h, _lib.ptr(logits.contiguous()), _lib.ptr(labels), B, Cn, _lib.ptr(pred),
+                                                 _lib.ptr(correct), _lib.stream_ptr()))
+        return pred, correct
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.tapclip_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.tapclip_workspace_bytes(self._h))

@@ -1,0 +1,140 @@
+"""Drop-in for ``models/model_wrapper.py`` (FullModel, lines 12-100) on B200.
+
+Same constructor, same ``forward(images, labels=None) -> {"logits", "loss", "loss_cls"}``, same parameter /
+state-dict names; ``loss.backward()`` fills ``.grad`` of every ``prompt_learner.context_bank[cls]`` and of
+``logit_scale``.  The schedule underneath is the de-duplicated one:
+
+    reference (model_wrapper.py:47-81)             here
+    ---------------------------------------------  ---------------------------------------------------
+    B*n_cls batch-1 text passes for attribution    ONE [C,T,D] attribution pass (probe epilogue, K2+K3)
+    n_cls batch-B text passes for features         ONE [C,T,D] feature pass on [ctx*a | tok]   (K4, K1, K2)
+    n_cls x (mul, sum, exp, cat)                   one cosine-logit kernel + fused cross-entropy
+
+Multi-GPU (one process per GPU, ``torch.distributed`` initialised by the caller): images are data-parallel,
+class prompts are sharded across ranks, text features are all-gathered, the text-feature gradient is
+all-reduced and the ctx gradients are all-gathered so that every replica holds the full, identical gradient
+(SURVEY.md 8e).  Pass ``distributed=True`` (default: auto when a process group exists).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .attribution_monitor import AttributionMonitor
+from .parallel import ClassSharding, all_gather_rows, all_reduce_sum_
+from .prompt_adjustor import PromptAdjustor
+from .prompt_learner import PromptLearner
+
+
+class _TapClipFunction(torch.autograd.Function):
+    """images, labels, ctx bank, token bank -> logits (+ loss); backward -> ctx / logit_scale gradients."""
+
+    @staticmethod
+    def forward(ctx, model, images, labels, logit_scale, *ctx_params):
+        eng = model.clip.engine
+        pl = model.prompt_learner
+        mode = model.clip.attribution
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in ctx_params)
+        shard = model._sharding()
+        n_cls, P = pl.n_cls, pl.prompt_len
+        lo, hi = shard.bounds(n_cls)
+
+        img_feat = eng.encode_image(images)                                       # row A4
+        text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad)   # rows A6-A10 on this rank's classes
+        text_feat = all_gather_rows(text_local, shard, n_cls)                     # [C, E]
+        if labels is not None:
+            b_total = shard.global_batch(images.shape[0])
+            logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale, labels, 1.0 / b_total)
+            loss = all_reduce_sum_(loss.clone(), shard) if shard.world > 1 else loss
+        else:
+            logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale)
+        model.clip.attention_maps[:] = [raw_local if raw_local is not None else attr_local]   # compact probe, see clip_wrapper.py
+        model.last_attribution = attr_local
+        ctx.model, ctx.shard, ctx.dims = model, shard, (n_cls, P, lo, hi)
+        ctx.need_grad = need_grad
+        ctx.save_for_backward(logits, dlogits_ce if dlogits_ce is not None else logits.new_empty(0), img_norm, logit_scale)
+        ctx.has_ce = dlogits_ce is not None
+        ctx.set_materialize_grads(False)
+        if loss is None:
+            loss = logits.new_zeros(())
+        return logits, loss
+
+    @staticmethod
+    def backward(ctx, g_logits, g_loss):
+        model, shard = ctx.model, ctx.shard
+        eng = model.clip.engine
+        n_cls, P, lo, hi = ctx.dims
+        logits, dlogits_ce, img_norm, logit_scale = ctx.saved_tensors
+        dl = None
+        if ctx.has_ce and g_loss is not None:
+            dl = dlogits_ce * g_loss
+        if g_logits is not None:
+            dl = g_logits.contiguous() if dl is None else dl + g_logits
+        n_in = 4 + n_cls
+        if dl is None:
+            return (None,) * n_in
+        d_text, d_scale = eng.logits_backward(dl.contiguous(), logits, img_norm, logit_scale)
+        if shard.world > 1:
+            all_reduce_sum_(d_text, shard)
+            all_reduce_sum_(d_scale, shard)
+        grads = [None] * n_cls
+        if ctx.need_grad:
+            d_local = d_text[lo:hi].contiguous()
+            dctx_local = eng.text_backward(d_local, hi - lo, P)                    # row A13
+            dctx = all_gather_rows(dctx_local.view(hi - lo, -1), shard, n_cls).view(n_cls, P, -1)
+            grads = list(dctx.unbind(0))
+        return (None, None, None, d_scale.reshape(logit_scale.shape) if logit_scale.requires_grad else None, *grads)
+
+
+class FullModel(nn.Module):
+    """models/model_wrapper.py:12-100."""
+
+    def __init__(self, class_names, clip_wrapper, prompt_len=5, attr_lambda=1.0, stab_lambda=0.1,
+                 adjustor_method="scale", class_specific=False, *, distributed=None, cache_text_features=True):
+        super().__init__()
+        self.clip = clip_wrapper
+        self.class_names = class_names
+        self.prompt_learner = PromptLearner(class_names, clip_wrapper, prompt_len, class_specific,
+                                            device=clip_wrapper.device)
+        self.n_cls = len(class_names)
+        self.attribution_monitor = AttributionMonitor(prompt_len)
+        self.prompt_adjustor = PromptAdjustor(method=adjustor_method)
+        self.attr_lambda = attr_lambda          # stored, never read — as in the reference (model_wrapper.py:24-25)
+        self.stab_lambda = stab_lambda
+        dev = clip_wrapper.model.text_projection.device
+        self.logit_scale = nn.Parameter((torch.ones([]) * torch.log(torch.tensor(1 / 0.07))).to(dev))
+        self.distributed = distributed
+        self.cache_text_features = cache_text_features
+        self._text_cache = None
+        self.last_attribution = None
+
+    @property
+    def prompt_len(self):
+        return self.prompt_learner.prompt_len
+
+    def _sharding(self) -> ClassSharding:
+        return ClassSharding.current(self.distributed)
+
+    def _text_features(self, lo, hi, need_grad):
+        """Rows A6-A10 for classes [lo, hi).  With ctx unchanged and no gradient needed (evaluation: the reference
+        recomputes the text side for every batch, test_cross_domain.py:84) the result is reused."""
+        pl = self.prompt_learner
+        ctx_bank = pl.flat_ctx()
+        use_cache = self.cache_text_features and not need_grad and not self.training
+        if use_cache:
+            key = (ctx_bank.data_ptr(), tuple(p._version for p in pl.context_bank.values()), lo, hi, self.clip.attribution)
+            if self._text_cache is not None and self._text_cache[0] == key:
+                return self._text_cache[1]
+        out = self.clip.engine.text_forward(ctx_bank[lo:hi], pl.flat_tok()[lo:hi], self.clip.attribution, need_grad)
+        self._text_cache = (key, out) if use_cache else None
+        return out
+
+    def forward(self, images, labels=None):
+        pl = self.prompt_learner
+        params = [pl.context_bank[k] for k in pl.context_bank.keys()]          # model_wrapper.py:47 (insertion order)
+        images = images.contiguous().float()
+        logits, loss = _TapClipFunction.apply(self, images, labels, self.logit_scale, *params)
+        outputs = {"logits": logits}                                           # model_wrapper.py:88
+        if labels is not None:                                                 # model_wrapper.py:90-93
+            outputs.update({"loss": loss, "loss_cls": loss})
+        return outputs

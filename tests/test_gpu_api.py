@@ -1,0 +1,126 @@
+"""Drop-in surface: constructor kwargs, state-dict keys, add_class_prompt, optimizers, errors, eval cache."""
+import pytest
+import torch
+
+from helpers import build_cuda, build_oracle, ctx_grads, max_abs
+from oracle.tapclip_oracle import class_names, synthetic_images, synthetic_labels
+
+pytestmark = pytest.mark.gpu
+
+
+def _mini(mode="intended", dtype="fp32", C=5, P=4):
+    ow, om = build_oracle("mini-16", C, P, mode)
+    clip, model = build_cuda("mini-16", C, P, mode, dtype, ow)
+    return ow, om, clip, model
+
+
+def test_state_dict_keys_and_roundtrip():
+    ow, om, clip, model = _mini()
+    sd = model.state_dict()
+    for n in class_names(5):
+        assert f"prompt_learner.context_bank.{n}" in sd
+    assert "logit_scale" in sd and "clip.model.visual.conv1.weight" in sd and "clip.model.text_projection" in sd
+    assert set(k for k in sd if k.startswith("clip.model.")) == set("clip.model." + k for k in ow.model.state_dict())
+    names = [n for n, _ in model.named_parameters()]
+    assert sum("prompt_learner.context_bank" in n for n in names) == 5          # test_cross_domain2.py:13-15 relies on this
+    # legacy-key conversion path of test_cross_domain.py:46-61 -> load_state_dict(strict=False)
+    new_ctx = {f"prompt_learner.context_bank.{n}": torch.full((4, 256), float(i)) for i, n in enumerate(class_names(5))}
+    model.load_state_dict(new_ctx, strict=False)
+    flat = model.prompt_learner.flat_ctx()
+    assert torch.equal(flat[3], torch.full((4, 256), 3.0, device="cuda"))
+
+
+def test_add_class_prompt_after_construction_matches_fresh_model():
+    ow, om, clip, model = _mini(C=3)
+    torch.manual_seed(99)
+    for n in class_names(12)[3:]:
+        model.prompt_learner.add_class_prompt(n)              # test_cross_domain.py:65-67; grows the flat bank
+    model.prompt_learner.add_class_prompt(class_names(12)[0])  # existing -> no-op
+    assert model.prompt_learner.n_cls == 12
+    images = synthetic_images(2, 64).cuda()
+    model.eval()
+    with torch.no_grad():
+        l12 = model(images)["logits"]
+    assert l12.shape == (2, 12)
+    # oracle with the same 12 ctx vectors
+    from oracle.tapclip_oracle import OracleFullModel
+    om2 = OracleFullModel(class_names(12), ow, prompt_len=4)
+    with torch.no_grad():
+        for n in class_names(12):
+            om2.prompt_learner.context_bank[n].copy_(model.prompt_learner.context_bank[n].cpu())
+        ref = om2.forward_dedup(images.cpu())["logits"]
+    assert max_abs(l12, ref) < 1e-4
+
+
+def test_prompt_learner_forward_shape_and_errors():
+    import tapclip_b200 as tb
+    ow, om, clip, model = _mini()
+    assert model.prompt_learner().shape == (5, 4 + 77, 256)
+    assert max_abs(model.prompt_learner(), om.prompt_learner()) == 0.0
+    with pytest.raises(ValueError):
+        tb.PromptAdjustor(method="bogus")                      # prompt_adjustor.py:47
+    with pytest.raises(ValueError):
+        tb.CLIPWrapper("ViT-Z-99", None, "cuda")
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 3, 32, 32, device="cuda"))        # wrong image size
+    with pytest.raises((ValueError, RuntimeError)):
+        clip.engine.load_state_dict({"visual.conv1.weight": torch.zeros(3, 3, device="cuda")})
+
+
+def test_attribution_monitor_module():
+    import tapclip_b200 as tb
+    g = torch.Generator(device="cuda").manual_seed(0)
+    attn = torch.softmax(torch.randn(6, 20, 20, device="cuda", generator=g), -1)
+    ref = torch.softmax(attn[:, :5, 19], dim=-1)
+    assert max_abs(tb.AttributionMonitor(5)(attn), ref) < 1e-6
+    assert max_abs(tb.AttributionMonitor(5, normalize=False)(attn), attn[:, :5, 19]) < 1e-7
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_three_train_steps_track_the_oracle(fused):
+    """train.py:65-67,99-105: AdamW on prompt_learner.parameters(); losses and ctx follow the CPU oracle."""
+    import tapclip_b200 as tb
+    ow, om, clip, model = _mini(mode="intended", dtype="fp32")
+    images, labels = synthetic_images(4, 64), synthetic_labels(4, 5)
+    opt_ref = torch.optim.AdamW(om.prompt_learner.parameters(), lr=2e-3, weight_decay=0.01)
+    opt = tb.FusedAdamW(model, lr=2e-3, weight_decay=0.01) if fused else \
+        torch.optim.AdamW(model.prompt_learner.parameters(), lr=2e-3, weight_decay=0.01)
+    model.train(); om.train()
+    for step in range(3):
+        lr = om.forward_dedup(images, labels)["loss"]
+        opt_ref.zero_grad(); lr.backward(); opt_ref.step()
+        lc = model(images.cuda(), labels.cuda())["loss"]
+        opt.zero_grad(); lc.backward(); opt.step()
+        assert abs(lc.item() - lr.item()) < 2e-4, (step, lc.item(), lr.item())
+    ref_ctx = torch.stack([om.prompt_learner.context_bank[n].detach() for n in class_names(5)])
+    assert max_abs(model.prompt_learner.flat_ctx(), ref_ctx) < 2e-4
+
+
+def test_eval_text_feature_cache_and_argmax():
+    ow, om, clip, model = _mini(mode="intended", dtype="fp32")
+    images, labels = synthetic_images(4, 64).cuda(), synthetic_labels(4, 5).cuda()
+    model.eval()
+    with torch.no_grad():
+        n0 = clip.engine.launch_count
+        l1 = model(images)["logits"]
+        n1 = clip.engine.launch_count
+        l2 = model(images)["logits"]
+        n2 = clip.engine.launch_count
+    assert torch.equal(l1, l2) and (n2 - n1) < (n1 - n0)         # text side reused when ctx is unchanged
+    with torch.no_grad():
+        model.prompt_learner.context_bank[class_names(5)[0]].add_(1.0)
+        l3 = model(images)["logits"]
+    assert not torch.equal(l3, l1)                               # in-place ctx update invalidates the cache
+    pred, correct = clip.engine.argmax_count(l1, labels)
+    assert torch.equal(pred, l1.argmax(1)) and correct.item() == (l1.argmax(1) == labels).sum().item()
+
+
+def test_logits_only_backward_path():
+    """A caller that builds its own loss from outputs['logits'] (not outputs['loss']) still gets ctx gradients."""
+    ow, om, clip, model = _mini(mode="literal", dtype="fp32")
+    images, labels = synthetic_images(4, 64), synthetic_labels(4, 5)
+    model.train(); om.train()
+    (model(images.cuda())["logits"].logsumexp(1).sum()).backward()
+    (om.forward_dedup(images)["logits"].logsumexp(1).sum()).backward()
+    ref = torch.stack([om.prompt_learner.context_bank[n].grad for n in class_names(5)])
+    assert ((ctx_grads(model, 5) - ref).norm() / ref.norm()).item() < 2e-3

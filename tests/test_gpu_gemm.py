@@ -1,0 +1,100 @@
+"""K1 parity: the tcgen05/TMEM/TMA GEMM (and the fp32 SIMT GEMM) against torch matmul, through the C ABI."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(a, w, bias, dtype, epi, act=-1, block_n=0, out_init=None, want_pre=False):
+    from tapclip_b200 import _lib
+    lib = _lib.load()
+    M, K = a.shape
+    N = w.shape[0]
+    bf = dtype == "bf16"
+    if epi == _lib.EPI_ACT:
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16 if bf else torch.float32)
+    else:
+        out = out_init.clone() if out_init is not None else torch.empty(M, N, device="cuda", dtype=torch.float32)
+    pre = torch.empty_like(out) if want_pre else None
+    _lib.check(lib.tapclip_op_gemm(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), _lib.ptr(pre), M, N, K,
+                                   _lib.DTYPE[dtype], epi, act, block_n, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    return out, pre
+
+
+def _ref_act(x, act):
+    if act == 0:
+        return torch.nn.functional.gelu(x)
+    if act == 1:
+        return x * torch.sigmoid(1.702 * x)
+    return x
+
+
+SHAPES = [
+    (128, 256, 64), (128, 256, 768), (256, 768, 768), (1576, 2304, 768), (1576, 768, 3072),
+    (197 * 8, 3072, 768), (93 * 65, 1536, 512), (93 * 65, 512, 2048), (65, 512, 512), (8, 512, 768),
+    (300, 128, 128), (1000, 384, 640), (129, 264, 72),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("block_n", [0, 128, 256])
+def test_gemm_tc_f32_out(M, N, K, block_n):
+    from tapclip_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out, _ = _gemm(a, w, bias, "bf16", _lib.EPI_F32, block_n=block_n)
+    ref = a.float() @ w.float().t() + bias
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3, f"max abs err {err}"          # fp32 accumulation of exact bf16 products: order-of-summation noise only
+
+
+@pytest.mark.parametrize("M,N,K", [(1576, 768, 768), (93 * 65, 512, 2048), (200, 256, 128)])
+def test_gemm_tc_residual_add(M, N, K):
+    from tapclip_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    out, _ = _gemm(a, w, bias, "bf16", _lib.EPI_F32_ADD, out_init=x)
+    ref = x + a.float() @ w.float().t() + bias
+    assert (out - ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("act", [-1, 0, 1])
+@pytest.mark.parametrize("M,N,K", [(1576, 3072, 768), (93 * 65, 2048, 512), (130, 256, 64)])
+def test_gemm_tc_bf16_out_act(M, N, K, act):
+    from tapclip_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out, pre = _gemm(a, w, bias, "bf16", _lib.EPI_ACT, act=act, want_pre=(act >= 0))
+    z = a.float() @ w.float().t() + bias
+    ref = _ref_act(z, act)
+    tol = 2e-2                                            # one bf16 rounding of values up to ~4
+    assert (out.float() - ref).abs().max().item() < tol
+    if pre is not None:
+        assert (pre.float() - z).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 384, 128), (1576, 768, 768), (65, 512, 512), (77, 100, 36)])
+def test_gemm_simt_fp32(M, N, K):
+    from tapclip_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * K ** -0.5
+    bias = torch.randn(N, device="cuda", generator=g)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = (a.double() @ w.double().t() + bias.double()).float()
+    out, _ = _gemm(a, w, bias, "fp32", _lib.EPI_F32)
+    assert (out - ref).abs().max().item() < 2e-5
+    out, pre = _gemm(a, w, bias, "fp32", _lib.EPI_ACT, act=0, want_pre=True)
+    assert (out - torch.nn.functional.gelu(ref)).abs().max().item() < 2e-5
+    assert (pre - ref).abs().max().item() < 2e-5
+    x = torch.randn(M, N, device="cuda", generator=g)
+    out, _ = _gemm(a, w, bias, "fp32", _lib.EPI_F32_ADD, out_init=x)
+    assert (out - (x + ref)).abs().max().item() < 2e-5

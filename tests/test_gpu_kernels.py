@@ -1,0 +1,103 @@
+"""Per-kernel parity against plain torch fp32 (LayerNorm fwd/bwd, attention fwd/bwd + probe epilogue, K3)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from tapclip_b200 import _lib as L
+    return L, L.load()
+
+
+@pytest.mark.parametrize("rows,d", [(1576, 768), (6045, 512), (33, 128), (4, 1024)])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_layernorm_fwd_bwd(rows, d, dtype):
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(rows + d)
+    x = torch.randn(rows, d, device="cuda", generator=g) * 2 + 0.5
+    gamma = 1 + 0.1 * torch.randn(d, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(d, device="cuda", generator=g)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    out = torch.empty(rows, d, device="cuda", dtype=tdt)
+    xc = torch.empty_like(x)
+    L.check(lib.tapclip_op_layernorm(L.ptr(x), d, L.ptr(gamma), L.ptr(beta), L.ptr(out), L.DTYPE[dtype], L.ptr(xc), rows, d, L.stream_ptr()))
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (d,), gamma, beta, 1e-5)
+    tol = 3e-2 if dtype == "bf16" else 1e-5
+    assert (out.float() - ref).abs().max().item() < tol
+    assert torch.equal(xc, x)
+    dy = torch.randn(rows, d, device="cuda", generator=g)
+    ref.backward(dy)
+    acc0 = torch.randn(rows, d, device="cuda", generator=g)
+    acc = acc0.clone()
+    cast = torch.empty(rows, d, device="cuda", dtype=tdt)
+    L.check(lib.tapclip_op_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(gamma), L.ptr(acc), L.ptr(cast), L.DTYPE[dtype], rows, d, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (acc - (acc0 + xr.grad)).abs().max().item() < 2e-5
+    assert (cast.float() - acc).abs().max().item() < (5e-2 if dtype == "bf16" else 1e-7)
+
+
+def _ref_attention(qkv, S, N, H):
+    d = H * 64
+    q, k, v = qkv.float().view(S, N, 3, H, 64).permute(2, 0, 3, 1, 4)       # [S,H,N,64]
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(S * N, d)
+    return o, p
+
+
+@pytest.mark.parametrize("S,N,H", [(3, 197, 12), (5, 93, 8), (2, 17, 4), (2, 577, 2), (4, 82, 8), (1, 50, 12)])
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_attention_fwd_and_probes(S, N, H, dtype):
+    L, lib = _lib()
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(S * N + H)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    qkv = (torch.randn(S * N, 3 * d, device="cuda", generator=g) * 1.5).to(tdt)
+    ref_o, ref_p = _ref_attention(qkv, S, N, H)
+    tol_o, tol_p = (2e-2, 2e-3) if dtype == "bf16" else (2e-5, 2e-6)
+    # CLS-row probe
+    out = torch.empty(S * N, d, device="cuda", dtype=tdt)
+    rows = torch.zeros(S, H, N, device="cuda")
+    L.check(lib.tapclip_op_attention(L.ptr(qkv), L.ptr(out), L.DTYPE[dtype], S, N, H, L.PROBE_CLS_ROW, L.ptr(rows), 0, H * N, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (out.float() - ref_o).abs().max().item() < tol_o
+    assert (rows - ref_p[:, :, 0, :]).abs().max().item() < tol_p
+    assert (rows.sum(-1) - 1).abs().max().item() < 1e-3
+    # text-column probe
+    P = min(16, N - 1)
+    col = torch.zeros(S, H, P, device="cuda")
+    out2 = torch.empty_like(out)
+    L.check(lib.tapclip_op_attention(L.ptr(qkv), L.ptr(out2), L.DTYPE[dtype], S, N, H, L.PROBE_TEXT_COL, L.ptr(col), P, 0, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    assert (col - ref_p[:, :, :P, N - 1]).abs().max().item() < tol_p
+    # K3: head-mean + softmax over P (clip_wrapper.py:36 + attribution_monitor.py:29-32)
+    raw = torch.empty(S, P, device="cuda")
+    attr = torch.empty(S, P, device="cuda")
+    L.check(lib.tapclip_op_attribution(L.ptr(col), L.ptr(raw), L.ptr(attr), S, H, P, L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref_raw = ref_p[:, :, :P, N - 1].mean(1)
+    assert (raw - ref_raw).abs().max().item() < tol_p
+    assert (attr - torch.softmax(ref_raw, -1)).abs().max().item() < tol_p
+
+
+@pytest.mark.parametrize("S,N,H", [(5, 93, 8), (2, 82, 4), (3, 17, 2), (1, 128, 8)])
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+def test_attention_bwd(S, N, H, dtype):
+    L, lib = _lib()
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(N)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    qkv = torch.randn(S * N, 3 * d, device="cuda", generator=g).to(tdt)
+    do = torch.randn(S * N, d, device="cuda", generator=g).to(tdt)
+    dqkv = torch.empty_like(qkv)
+    L.check(lib.tapclip_op_attention_bwd(L.ptr(qkv), L.ptr(do), L.ptr(dqkv), L.DTYPE[dtype], S, N, H, L.stream_ptr()))
+    torch.cuda.synchronize()
+    x = qkv.float().clone().requires_grad_(True)
+    o, _ = _ref_attention(x, S, N, H)
+    o.backward(do.float())
+    tol = 3e-2 if dtype == "bf16" else 2e-5
+    assert (dqkv.float() - x.grad).abs().max().item() < tol * max(1.0, x.grad.abs().max().item())
