@@ -113,6 +113,12 @@ TAPCLIP_API int64_t tapclip_workspace_bytes(tapclip_handle h);
 /* Number of kernel launches issued by this handle since creation (bench.py `gpu_launches`). */
 TAPCLIP_API int64_t tapclip_launch_count(tapclip_handle h);
 
+/* Per-launch timing of the tensor-core kernels (GEMM, attention) with CUDA events on the launching stream.
+ * tapclip_profile(h, 1) starts recording, tapclip_profile(h, 0) stops; tapclip_profile_report synchronises the
+ * recorded events and returns a JSON summary (string owned by the handle, valid until the next call). */
+TAPCLIP_API int tapclip_profile(tapclip_handle h, int32_t enable);
+TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
+
 /* ---- single-kernel entry points (used by the per-kernel parity tests and micro-benchmarks) -------- */
 /* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias).  dtype BF16: A,W bf16, tcgen05 path; FP32: SIMT path.
  * epi: 0 = store activation type (+act, optional out_pre), 1 = store fp32, 2 = fp32 += .  block_n: 0|128|256 */

@@ -46,6 +46,8 @@ PROTOTYPES = {
     "tapclip_argmax_count": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "tapclip_workspace_bytes": (_i64, [_vp]),
     "tapclip_launch_count": (_i64, [_vp]),
+    "tapclip_profile": (C.c_int, [_vp, _i32]),
+    "tapclip_profile_report": (C.c_char_p, [_vp]),
     "tapclip_op_gemm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _vp]),
     "tapclip_op_layernorm": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
     "tapclip_op_layernorm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp]),

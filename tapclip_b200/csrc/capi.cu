@@ -117,6 +117,14 @@ TAPCLIP_API int tapclip_argmax_count(tapclip_handle h, const float* logits, cons
 TAPCLIP_API int64_t tapclip_workspace_bytes(tapclip_handle h) { return h ? h->impl.workspace_bytes() : -1; }
 TAPCLIP_API int64_t tapclip_launch_count(tapclip_handle h) { return h ? h->impl.launches : -1; }
 
+TAPCLIP_API int tapclip_profile(tapclip_handle h, int32_t enable) {
+    TC_API_BEGIN
+    NEED(h);
+    h->impl.profiling = enable != 0;
+    TC_API_END
+}
+TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h) { return h ? h->impl.profile_report() : "{}"; }
+
 // ---- single-kernel entry points ------------------------------------------------------------------------
 TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K,
                     int32_t dtype, int32_t epi, int32_t act, int32_t block_n, void* stream) {

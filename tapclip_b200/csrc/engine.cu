@@ -212,14 +212,82 @@ std::string Engine::missing_weights() const {
     return os.str();
 }
 
+// ---- per-launch profiling (CUDA events on the launching stream) -----------------------------------------
+void Engine::prof_begin(ProfRec& r, cudaStream_t st) {
+    TC_CUDA(cudaEventCreate(&r.a));
+    TC_CUDA(cudaEventCreate(&r.b));
+    TC_CUDA(cudaEventRecord(r.a, st));
+}
+void Engine::prof_end(ProfRec& r, cudaStream_t st) {
+    TC_CUDA(cudaEventRecord(r.b, st));
+    prof.push_back(r);
+}
+const char* Engine::profile_report() {
+    struct Agg { int64_t n = 0; double ms = 0, flops = 0; };
+    std::map<std::string, Agg> kinds;
+    std::map<std::string, Agg> shapes;
+    static const char* kind_name[] = {"gemm", "attention_fwd", "attention_bwd"};
+    for (ProfRec& r : prof) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+        Agg& k = kinds[kind_name[r.kind]];
+        k.n++; k.ms += ms; k.flops += r.flops;
+        char key[96];
+        snprintf(key, sizeof(key), "%s M=%lld N=%lld K=%lld epi=%d", kind_name[r.kind], (long long)r.M, (long long)r.N, (long long)r.K, r.epi);
+        Agg& s = shapes[key];
+        s.n++; s.ms += ms; s.flops += r.flops;
+    }
+    prof.clear();
+    std::ostringstream os;
+    os << "{";
+    bool first = true;
+    for (auto& kv : kinds) {
+        os << (first ? "" : ", ") << "\"" << kv.first << "\": {\"launches\": " << kv.second.n << ", \"ms\": " << kv.second.ms
+           << ", \"flops\": " << kv.second.flops << "}";
+        first = false;
+    }
+    os << (first ? "" : ", ") << "\"shapes\": {";
+    first = true;
+    for (auto& kv : shapes) {
+        os << (first ? "" : ", ") << "\"" << kv.first << "\": {\"launches\": " << kv.second.n << ", \"ms\": " << kv.second.ms
+           << ", \"flops\": " << kv.second.flops << "}";
+        first = false;
+    }
+    os << "}}";
+    prof_report = os.str();
+    return prof_report.c_str();
+}
+
 // ---- primitive wrappers ------------------------------------------------------------------------------
 void Engine::gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K,
                   int epi, int act, cudaStream_t st) {
     GemmArgs g;
     g.a = a; g.w = w; g.bias = bias; g.out = out; g.out_pre = out_pre;
     g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act;
+    ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, epi};
+    if (profiling) prof_begin(r, st);
     if (bf) gemm_tc(g, st);
     else gemm_simt_f32(g, st);
+    if (profiling) prof_end(r, st);
+    ++launches;
+}
+
+void Engine::attn_fwd(const void* qkv, void* out, int S, int N, int H, const AttnProbe& probe, cudaStream_t st) {
+    ProfRec r{nullptr, nullptr, 4.0 * (double)S * H * (double)N * N * 64.0, 1, S, N, H, probe.mode};
+    if (profiling) prof_begin(r, st);
+    attention_fwd(qkv, out, bf, S, N, H, probe, st);
+    if (profiling) prof_end(r, st);
+    ++launches;
+}
+
+void Engine::attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st) {
+    ProfRec r{nullptr, nullptr, 10.0 * (double)S * H * (double)N * N * 64.0, 2, S, N, H, 0};
+    if (profiling) prof_begin(r, st);
+    attention_bwd(qkv, d_out, dqkv, bf, S, N, H, st);
+    if (profiling) prof_end(r, st);
     ++launches;
 }
 
@@ -239,7 +307,7 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
     }
     layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, bf, sx0, M, d, st); ++launches;
     gemm(ln.p, b.w_qkv, b.b_qkv, sqkv, nullptr, M, 3 * d, d, EPI_BF16, ACT_NONE, st);
-    attention_fwd(sqkv, attn.p, bf, S, N, H, probe, st); ++launches;
+    attn_fwd(sqkv, attn.p, S, N, H, probe, st);
     if (probs_only) return;
     gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, st);
     layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, bf, sx1, M, d, st); ++launches;
@@ -379,7 +447,7 @@ void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream
         layernorm_bwd((const float*)b_dln.p, x1, b.ln2_g, (float*)b_dx.p, b_dxc.p, bf, M, D, st); ++launches;
         // attention branch
         gemm(b_dxc.p, b.wt_o, nullptr, b_dattn.p, nullptr, M, D, D, EPI_BF16, ACT_NONE, st);
-        attention_bwd(qkv, b_dattn.p, b_dqkv.p, bf, C, T, H, st); ++launches;
+        attn_bwd(qkv, b_dattn.p, b_dqkv.p, C, T, H, st);
         gemm(b_dqkv.p, b.wt_qkv, nullptr, b_dln.p, nullptr, M, D, 3 * D, EPI_F32, ACT_NONE, st);
         layernorm_bwd((const float*)b_dln.p, x0, b.ln1_g, (float*)b_dx.p, b_dxc.p, bf, M, D, st); ++launches;
     }

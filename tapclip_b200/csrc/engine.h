@@ -45,6 +45,15 @@ struct Engine {
     DevBuf s_rows, s_cls;
     struct { bool valid = false; int C = 0, P = 0, T = 0, PA = 1; bool has_attr = false; } saved;
 
+    // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline numbers)
+    struct ProfRec { cudaEvent_t a, b; double flops; int kind; int64_t M, N, K; int epi; };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::string prof_report;
+    void prof_begin(ProfRec& r, cudaStream_t st);
+    void prof_end(ProfRec& r, cudaStream_t st);
+    const char* profile_report();
+
     explicit Engine(const tapclip_config& c);
     ~Engine();
     std::vector<DevBuf*> all_bufs();
@@ -56,6 +65,8 @@ struct Engine {
 
     void gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int epi,
               int act, cudaStream_t st);
+    void attn_fwd(const void* qkv, void* out, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
+    void attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st);
     void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf,
                        const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st);
     void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, cudaStream_t st);

@@ -129,6 +129,13 @@ class Engine:
                                                  _lib.ptr(correct), _lib.stream_ptr()))
         return pred, correct
 
+    def profile(self, enable: bool):
+        _lib.check(self.lib.tapclip_profile(self._h, 1 if enable else 0))
+
+    def profile_report(self) -> dict:
+        import json
+        return json.loads(self.lib.tapclip_profile_report(self._h).decode())
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.tapclip_launch_count(self._h))

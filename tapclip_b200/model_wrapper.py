@@ -30,11 +30,10 @@ class _TapClipFunction(torch.autograd.Function):
     """images, labels, ctx bank, token bank -> logits (+ loss); backward -> ctx / logit_scale gradients."""
 
     @staticmethod
-    def forward(ctx, model, images, labels, logit_scale, *ctx_params):
+    def forward(ctx, model, images, labels, need_grad, logit_scale, *ctx_params):
         eng = model.clip.engine
         pl = model.prompt_learner
         mode = model.clip.attribution
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in ctx_params)
         shard = model._sharding()
         n_cls, P = pl.n_cls, pl.prompt_len
         lo, hi = shard.bounds(n_cls)
@@ -70,7 +69,7 @@ class _TapClipFunction(torch.autograd.Function):
             dl = dlogits_ce * g_loss
         if g_logits is not None:
             dl = g_logits.contiguous() if dl is None else dl + g_logits
-        n_in = 4 + n_cls
+        n_in = 5 + n_cls
         if dl is None:
             return (None,) * n_in
         d_text, d_scale = eng.logits_backward(dl.contiguous(), logits, img_norm, logit_scale)
@@ -83,7 +82,7 @@ class _TapClipFunction(torch.autograd.Function):
             dctx_local = eng.text_backward(d_local, hi - lo, P)                    # row A13
             dctx = all_gather_rows(dctx_local.view(hi - lo, -1), shard, n_cls).view(n_cls, P, -1)
             grads = list(dctx.unbind(0))
-        return (None, None, None, d_scale.reshape(logit_scale.shape) if logit_scale.requires_grad else None, *grads)
+        return (None, None, None, None, d_scale.reshape(logit_scale.shape) if logit_scale.requires_grad else None, *grads)
 
 
 class FullModel(nn.Module):
@@ -133,7 +132,9 @@ class FullModel(nn.Module):
         pl = self.prompt_learner
         params = [pl.context_bank[k] for k in pl.context_bank.keys()]          # model_wrapper.py:47 (insertion order)
         images = images.contiguous().float()
-        logits, loss = _TapClipFunction.apply(self, images, labels, self.logit_scale, *params)
+        # grad mode is off inside autograd.Function.forward, so decide here whether activations must be kept
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        logits, loss = _TapClipFunction.apply(self, images, labels, need_grad, self.logit_scale, *params)
         outputs = {"logits": logits}                                           # model_wrapper.py:88
         if labels is not None:                                                 # model_wrapper.py:90-93
             outputs.update({"loss": loss, "loss_cls": loss})
