@@ -8,7 +8,8 @@
 //  * attn_fwd_mma_kernel   bf16, mma.sync m16n8k16 tensor-core path, flash-style online softmax over
 //                          32-key steps, K/V/Q staged in XOR-swizzled smem by cp.async.
 //  * attn_fwd_simt_kernel  fp32 parity mode (one warp per query row).
-//  * attn_bwd_kernel       dQ,dK,dV for the text tower (N <= 128), probabilities recomputed in smem.
+//  * attn_bwd_mma_kernel   bf16 dQ,dK,dV for the text tower (N <= 128) on mma.sync, probabilities recomputed.
+//  * attn_bwd_kernel       fp32 parity-mode backward (SIMT, shared memory).
 #include "kernels.h"
 
 namespace tapclip {
@@ -343,6 +344,208 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bf16 tensor-core backward (text tower: N <= 128).  One CTA per (sequence, head), one warp per 16-row block.
+//   phase 1 (warp owns 16 query rows):  S = Q K^T, P = softmax(scale*S) (whole row in registers),
+//            dP = dO V^T, D = rowsum(P o dP), dS = P o (dP - D) * scale, dQ = dS K; P and dS -> smem (bf16)
+//   phase 2 (warp owns 16 key rows):    dV = P^T dO, dK = dS^T Q   (A operands via ldmatrix.trans on P / dS)
+// ------------------------------------------------------------------------------------------------
+template <int NB16>
+__global__ void __launch_bounds__(NB16 * 32, 1)
+attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out, bf16* __restrict__ dqkv, int N, int H,
+                    float scale) {
+    constexpr int NP = NB16 * 16;               // padded sequence length
+    constexpr int NB8 = NB16 * 2;               // 8-wide key blocks
+    constexpr int PLD = NP * 2 + 16;            // P / dS row pitch in bytes (odd multiple of 16 B: conflict-free ldmatrix)
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* Qs = smem;
+    uint8_t* Ks = Qs + NP * 128;
+    uint8_t* Vs = Ks + NP * 128;
+    uint8_t* Os = Vs + NP * 128;                // dO
+    uint8_t* Ps = Os + NP * 128;
+    uint8_t* Ss = Ps + NP * PLD;                // dS
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x / H, h = blockIdx.x % H;
+    const int d = H * DH;
+    const bf16* base = qkv + (int64_t)s * N * 3 * d + h * DH;
+    const bf16* dobase = d_out + (int64_t)s * N * d + h * DH;
+    for (int idx = threadIdx.x; idx < NP * 8; idx += NB16 * 32) {
+        const int row = idx >> 3, ch = idx & 7;
+        const bool ok = row < N;
+        const bf16* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
+        const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
+        cp_async_16(smem_u32(Qs + off), src, ok);
+        cp_async_16(smem_u32(Ks + off), src + d, ok);
+        cp_async_16(smem_u32(Vs + off), src + 2 * d, ok);
+        cp_async_16(smem_u32(Os + off), dobase + (int64_t)(ok ? row : 0) * d + ch * 8, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int g = lane >> 2, tq = lane & 3, mat = lane >> 3, l7 = lane & 7;
+    const int r0 = warp * 16;
+    bf16* dbase = dqkv + (int64_t)s * N * 3 * d + h * DH;
+    {
+        // ---------------- phase 1 ----------------
+        uint32_t af[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int row = r0 + (mat & 1) * 8 + l7, ch = ks * 2 + (mat >> 1);
+            ldmatrix_x4(af[ks], smem_u32(Qs + row * 128 + ((ch ^ (row & 7)) << 4)));
+        }
+        float sc[NB8][4];
+#pragma unroll
+        for (int i = 0; i < NB8; ++i) { sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int nbp = 0; nbp < NB16; ++nbp) {
+                const int key = (nbp * 2 + (mat >> 1)) * 8 + l7, ch = ks * 2 + (mat & 1);
+                uint32_t b[4];
+                ldmatrix_x4(b, smem_u32(Ks + key * 128 + ((ch ^ (key & 7)) << 4)));
+                mma_bf16_16816(sc[nbp * 2], af[ks], b[0], b[1]);
+                mma_bf16_16816(sc[nbp * 2 + 1], af[ks], b[2], b[3]);
+            }
+        }
+        // softmax over the full row (rows g and g+8 of this warp's block)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int key = nb * 8 + tq * 2 + e;
+                float v0 = sc[nb][e] * scale, v1 = sc[nb][e + 2] * scale;
+                if (key >= N) { v0 = -INFINITY; v1 = -INFINITY; }
+                sc[nb][e] = v0; sc[nb][e + 2] = v1;
+                mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb) {
+            sc[nb][0] = __expf(sc[nb][0] - mx0); sc[nb][1] = __expf(sc[nb][1] - mx0);
+            sc[nb][2] = __expf(sc[nb][2] - mx1); sc[nb][3] = __expf(sc[nb][3] - mx1);
+            l0 += sc[nb][0] + sc[nb][1]; l1 += sc[nb][2] + sc[nb][3];
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb) { sc[nb][0] *= i0; sc[nb][1] *= i0; sc[nb][2] *= i1; sc[nb][3] *= i1; }
+        // dP = dO V^T
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int row = r0 + (mat & 1) * 8 + l7, ch = ks * 2 + (mat >> 1);
+            ldmatrix_x4(af[ks], smem_u32(Os + row * 128 + ((ch ^ (row & 7)) << 4)));
+        }
+        float dp[NB8][4];
+#pragma unroll
+        for (int i = 0; i < NB8; ++i) { dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int nbp = 0; nbp < NB16; ++nbp) {
+                const int key = (nbp * 2 + (mat >> 1)) * 8 + l7, ch = ks * 2 + (mat & 1);
+                uint32_t b[4];
+                ldmatrix_x4(b, smem_u32(Vs + key * 128 + ((ch ^ (key & 7)) << 4)));
+                mma_bf16_16816(dp[nbp * 2], af[ks], b[0], b[1]);
+                mma_bf16_16816(dp[nbp * 2 + 1], af[ks], b[2], b[3]);
+            }
+        }
+        float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb) {
+            D0 += sc[nb][0] * dp[nb][0] + sc[nb][1] * dp[nb][1];
+            D1 += sc[nb][2] * dp[nb][2] + sc[nb][3] * dp[nb][3];
+        }
+        D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+        D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+        // P, dS -> smem (bf16) and dS -> A fragments for dQ = dS K
+        uint32_t da[NB16][4];
+#pragma unroll
+        for (int nb = 0; nb < NB8; ++nb) {
+            const float s0 = sc[nb][0] * (dp[nb][0] - D0) * scale, s1 = sc[nb][1] * (dp[nb][1] - D0) * scale;
+            const float s2 = sc[nb][2] * (dp[nb][2] - D1) * scale, s3 = sc[nb][3] * (dp[nb][3] - D1) * scale;
+            const uint32_t plo = pack_bf16x2(sc[nb][0], sc[nb][1]), phi = pack_bf16x2(sc[nb][2], sc[nb][3]);
+            const uint32_t slo = pack_bf16x2(s0, s1), shi = pack_bf16x2(s2, s3);
+            const uint32_t coff = (nb * 8 + tq * 2) * 2;
+            *reinterpret_cast<uint32_t*>(Ps + (r0 + g) * PLD + coff) = plo;
+            *reinterpret_cast<uint32_t*>(Ps + (r0 + g + 8) * PLD + coff) = phi;
+            *reinterpret_cast<uint32_t*>(Ss + (r0 + g) * PLD + coff) = slo;
+            *reinterpret_cast<uint32_t*>(Ss + (r0 + g + 8) * PLD + coff) = shi;
+            da[nb >> 1][(nb & 1) * 2 + 0] = slo;
+            da[nb >> 1][(nb & 1) * 2 + 1] = shi;
+        }
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+        for (int ks2 = 0; ks2 < NB16; ++ks2) {
+#pragma unroll
+            for (int dbp = 0; dbp < 4; ++dbp) {
+                const int key = ks2 * 16 + (mat & 1) * 8 + l7, ch = dbp * 2 + (mat >> 1);
+                uint32_t b[4];
+                ldmatrix_x4_trans(b, smem_u32(Ks + key * 128 + ((ch ^ (key & 7)) << 4)));
+                mma_bf16_16816(o[dbp * 2], da[ks2], b[0], b[1]);
+                mma_bf16_16816(o[dbp * 2 + 1], da[ks2], b[2], b[3]);
+            }
+        }
+#pragma unroll
+        for (int db = 0; db < 8; ++db) {
+            if (r0 + g < N) *reinterpret_cast<uint32_t*>(dbase + (int64_t)(r0 + g) * 3 * d + db * 8 + tq * 2) = pack_bf16x2(o[db][0], o[db][1]);
+            if (r0 + g + 8 < N) *reinterpret_cast<uint32_t*>(dbase + (int64_t)(r0 + g + 8) * 3 * d + db * 8 + tq * 2) = pack_bf16x2(o[db][2], o[db][3]);
+        }
+    }
+    __syncthreads();
+    // ---------------- phase 2: this warp's 16 KEY rows j0..j0+15 ----------------
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+        const uint8_t* Am = which == 0 ? Ps : Ss;       // [i][j] ; A[m=j][k=i] via ldmatrix.trans
+        const uint8_t* Bm = which == 0 ? Os : Qs;       // dO (for dV) or Q (for dK), B[k=i][n=dim] via ldmatrix.trans
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < NB16; ++ks) {
+            uint32_t a[4];
+            {
+                const int i = ks * 16 + (mat >> 1) * 8 + l7, j = r0 + (mat & 1) * 8;
+                ldmatrix_x4_trans(a, smem_u32(Am + i * PLD + j * 2));
+            }
+#pragma unroll
+            for (int dbp = 0; dbp < 4; ++dbp) {
+                const int i = ks * 16 + (mat & 1) * 8 + l7, ch = dbp * 2 + (mat >> 1);
+                uint32_t b[4];
+                ldmatrix_x4_trans(b, smem_u32(Bm + i * 128 + ((ch ^ (i & 7)) << 4)));
+                mma_bf16_16816(o[dbp * 2], a, b[0], b[1]);
+                mma_bf16_16816(o[dbp * 2 + 1], a, b[2], b[3]);
+            }
+        }
+        const int coloff = which == 0 ? 2 * d : d;      // dV or dK column block of dqkv
+#pragma unroll
+        for (int db = 0; db < 8; ++db) {
+            if (r0 + g < N) *reinterpret_cast<uint32_t*>(dbase + (int64_t)(r0 + g) * 3 * d + coloff + db * 8 + tq * 2) = pack_bf16x2(o[db][0], o[db][1]);
+            if (r0 + g + 8 < N) *reinterpret_cast<uint32_t*>(dbase + (int64_t)(r0 + g + 8) * 3 * d + coloff + db * 8 + tq * 2) = pack_bf16x2(o[db][2], o[db][3]);
+        }
+    }
+}
+
+template <int NB16>
+void launch_attn_bwd_mma(const bf16* qkv, const bf16* d_out, bf16* dqkv, int S, int N, int H, cudaStream_t stream) {
+    constexpr int NP = NB16 * 16;
+    const size_t smem = (size_t)4 * NP * 128 + (size_t)2 * NP * (NP * 2 + 16);
+    static bool configured = false;
+    if (!configured) {
+        TC_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<NB16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    attn_bwd_mma_kernel<NB16><<<S * H, NB16 * 32, smem, stream>>>(qkv, d_out, dqkv, N, H, 0.125f);
+}
+
 }  // namespace
 
 void attention_fwd(const void* qkv, void* out, bool is_bf16, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream) {
@@ -379,10 +582,19 @@ void attention_bwd(const void* qkv, const void* d_out, void* dqkv, bool is_bf16,
     if (S == 0) return;
     TC_CHECK(N <= 128, "attention backward supports sequence length <= 128 (got %d)", N);
     const size_t smem = ((size_t)4 * N * LDH + (size_t)N * (N + 1)) * sizeof(float);
-    static size_t conf_bf16 = 0, conf_f32 = 0;
+    static size_t conf_f32 = 0;
     if (is_bf16) {
-        if (smem > conf_bf16) { TC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf_bf16 = smem; }
-        attn_bwd_kernel<bf16><<<S * H, 256, smem, stream>>>((const bf16*)qkv, (const bf16*)d_out, (bf16*)dqkv, N, H, 0.125f);
+        const bf16* q = (const bf16*)qkv; const bf16* g = (const bf16*)d_out; bf16* o = (bf16*)dqkv;
+        switch ((N + 15) / 16) {
+            case 1: launch_attn_bwd_mma<1>(q, g, o, S, N, H, stream); break;
+            case 2: launch_attn_bwd_mma<2>(q, g, o, S, N, H, stream); break;
+            case 3: launch_attn_bwd_mma<3>(q, g, o, S, N, H, stream); break;
+            case 4: launch_attn_bwd_mma<4>(q, g, o, S, N, H, stream); break;
+            case 5: launch_attn_bwd_mma<5>(q, g, o, S, N, H, stream); break;
+            case 6: launch_attn_bwd_mma<6>(q, g, o, S, N, H, stream); break;
+            case 7: launch_attn_bwd_mma<7>(q, g, o, S, N, H, stream); break;
+            default: launch_attn_bwd_mma<8>(q, g, o, S, N, H, stream); break;
+        }
     } else {
         if (smem > conf_f32) { TC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf_f32 = smem; }
         attn_bwd_kernel<float><<<S * H, 256, smem, stream>>>((const float*)qkv, (const float*)d_out, (float*)dqkv, N, H, 0.125f);

@@ -85,6 +85,32 @@ template <int ACT> __device__ __forceinline__ float act_bwd(float x) {
     } else return 1.0f;
 }
 
+// Fast forms for bf16/fp16 epilogues (result is rounded to 8/11 significand bits anyway):
+//   quick_gelu: x*sigmoid(1.702x) = h + h*tanh(0.851x), h = x/2     -> one MUFU (tanh.approx, rel err 2^-11)
+//   gelu_erf  : Abramowitz-Stegun 7.1.26 erf (abs err 1.5e-7)       -> two MUFU (rcp, ex2)
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int ACT> __device__ __forceinline__ float act_fwd_fast(float x) {
+    if constexpr (ACT == ACT_QUICK_GELU) {
+        const float h = 0.5f * x;
+        return fmaf(h, tanh_approx(0.851f * x), h);
+    } else if constexpr (ACT == ACT_GELU_ERF) {
+        const float z = fabsf(x) * 0.70710678118654752f;
+        const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+        float p = fmaf(t, 1.061405429f, -1.453152027f);
+        p = fmaf(p, t, 1.421413741f);
+        p = fmaf(p, t, -0.284496736f);
+        p = fmaf(p, t, 0.254829592f);
+        p *= t;
+        const float e = 1.0f - p * exp2f(-1.4426950408889634f * z * z);       // erf(|x|/sqrt2)
+        const float h = 0.5f * x;
+        return fmaf(h, copysignf(e, x), h);
+    } else return x;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -184,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 *reinterpret_cast<uint4*>(stage_buf + row_off + (((uint32_t)j ^ sw) << 4)) = p;
                             }
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) v[j] = act_fwd<ACT>(v[j]);
+                            for (int j = 0; j < 64; ++j) v[j] = act_fwd_fast<ACT>(v[j]);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 uint4 p;
@@ -204,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             __syncwarp();
                             uint8_t* sb = stage_buf + buf * EPI_BUF_BYTES;
 #pragma unroll
-                            for (int j = 0; j < 64; ++j) v[j] = act_fwd<ACT>(v[j]);
+                            for (int j = 0; j < 64; ++j) v[j] = act_fwd_fast<ACT>(v[j]);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 uint4 p;

@@ -30,7 +30,8 @@ def main(path, step_index=3):
     def short(n):
         n = re.sub(r"^void ", "", n)
         n = n.replace("tapclip::<unnamed>::", "")
-        return re.sub(r"\(.*", "", n)[:80]
+        n = n[: n.rindex(">(") + 1] if ">(" in n else re.sub(r"\(.*", "", n)
+        return n[:90]
 
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, v in step:
