@@ -179,7 +179,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local_rank)
     cfg = get_model_config(model_name)
 
-    clip = tb.CLIPWrapper(model_name, None, "cuda", seed=0, attribution="intended", dtype="bf16")
+    clip = tb.CLIPWrapper(model_name, None, "cuda", seed=0, attribution="intended", dtype=args.dtype)
     torch.manual_seed(4)
     model = tb.FullModel([f"class_{i:03d}" for i in range(C)], clip, prompt_len=P, cache_text_features=False)
     opt = tb.FusedAdamW(model, lr=2e-3, weight_decay=0.01) if train else None
@@ -271,7 +271,8 @@ def run_ours(args, wl):
     line = {
         "metric": "images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "steps_per_s": args.steps / (ms_resident / 1e3),
+        "dtype": "bf16" if args.dtype == "bf16" else "bf16 (image tower + all gradients) / fp16 (text-tower forward operands); fp32 accumulate + residual",
+        "data": "synthetic", "steps_per_s": args.steps / (ms_resident / 1e3),
         "config": {"workload": desc, "model": model_name, "batch_per_gpu": B, "global_batch": imgs_per_step, "n_cls": C,
                    "prompt_len": P, "attribution": "intended", "optimizer": "FusedAdamW(lr=2e-3, wd=0.01)" if train else None,
                    "parallelism": f"dp{world} images + class-sharded text" if world > 1 else "single GPU",
@@ -314,6 +315,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train_c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="mixed", choices=["mixed", "bf16"],
+                    help="'mixed' (default, meets the 1e-2 logit bar) or 'bf16' (bf16 operands everywhere)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

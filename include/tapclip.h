@@ -32,7 +32,14 @@ extern "C" {
 typedef struct tapclip_engine* tapclip_handle;
 
 enum { TAPCLIP_ACT_GELU_ERF = 0, TAPCLIP_ACT_QUICK_GELU = 1 };
-enum { TAPCLIP_DTYPE_FP32 = 0, TAPCLIP_DTYPE_BF16 = 1 };        /* compute type of GEMM/attention operands */
+/* Engine precision (tapclip_config.dtype).  Residual streams, LayerNorm, softmax, L2-norm, logits and the loss are
+ * always fp32; the setting picks the tensor-core OPERAND type:
+ *   FP32  : fp32 SIMT kernels everywhere (parity mode, logits within 1e-4 of the reference);
+ *   BF16  : bf16 operands everywhere;
+ *   MIXED : bf16 operands in the image tower and in the backward pass, fp16 operands in the text-tower forward
+ *           (same tcgen05 kind::f16 rate and bytes; needed for the 1e-2 logit bar — DESIGN.md "Precision").
+ * For the single-kernel tapclip_op_* entry points the same integers name the element type: 0 fp32, 1 bf16, 2 fp16. */
+enum { TAPCLIP_DTYPE_FP32 = 0, TAPCLIP_DTYPE_BF16 = 1, TAPCLIP_DTYPE_MIXED = 2, TAPCLIP_DTYPE_FP16 = 2 };
 enum { TAPCLIP_ATTR_LITERAL = 0, TAPCLIP_ATTR_INTENDED = 1 };  /* SURVEY.md 8a "mode definitions" */
 
 typedef struct {
@@ -120,7 +127,7 @@ TAPCLIP_API int tapclip_profile(tapclip_handle h, int32_t enable);
 TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
 
 /* ---- single-kernel entry points (used by the per-kernel parity tests and micro-benchmarks) -------- */
-/* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias).  dtype BF16: A,W bf16, tcgen05 path; FP32: SIMT path.
+/* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias).  dtype BF16/FP16: A,W (and epi-0 out) 16-bit, tcgen05 path; FP32: SIMT path.
  * epi: 0 = store activation type (+act, optional out_pre), 1 = store fp32, 2 = fp32 += .  block_n: 0|128|256 */
 TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N,
                     int64_t K, int32_t dtype, int32_t epi, int32_t act, int32_t block_n, void* stream);

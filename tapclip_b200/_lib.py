@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtapclip.so")
 
 ACT = {"gelu_erf": 0, "quick_gelu": 1}
-DTYPE = {"fp32": 0, "bf16": 1}
+DTYPE = {"fp32": 0, "bf16": 1, "mixed": 2, "fp16": 2}     # engine precision / element type (include/tapclip.h)
 ATTR_MODE = {"literal": 0, "intended": 1}
 EPI_ACT, EPI_F32, EPI_F32_ADD = 0, 1, 2
 PROBE_NONE, PROBE_TEXT_COL, PROBE_CLS_ROW = 0, 1, 2

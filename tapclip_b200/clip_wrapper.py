@@ -147,12 +147,14 @@ class CLIPWrapper(nn.Module):
       state_dict   open_clip-named weights instead of ``pretrained_path``
       seed         random-init seed when neither a path nor a state_dict is given (synthetic weights)
       attribution  'literal' | 'intended' (see module docstring)
-      dtype        'bf16' (tcgen05 tensor cores) | 'fp32' (SIMT parity mode, logits within 1e-4)
+      dtype        'mixed' (default: tcgen05 tensor cores, bf16 operands in the image tower and the backward pass,
+                   fp16 operands in the text-tower forward — meets the 1e-2 logit bar) | 'bf16' (bf16 operands
+                   everywhere) | 'fp32' (SIMT parity mode, logits within 1e-4)
       tokenizer    any ``str -> LongTensor[1,77]`` callable (e.g. open_clip's); default: SyntheticTokenizer
     """
 
     def __init__(self, model_name="ViT-B-32", pretrained_path=None, device="cuda", *, state_dict=None, seed=0,
-                 attribution="literal", dtype="bf16", tokenizer=None):
+                 attribution="literal", dtype="mixed", tokenizer=None):
         super().__init__()
         if attribution not in ("literal", "intended"):
             raise ValueError(f"Unknown attribution mode: {attribution}")

@@ -11,6 +11,7 @@
 //  * attn_bwd_mma_kernel   bf16 dQ,dK,dV for the text tower (N <= 128) on mma.sync, probabilities recomputed.
 //  * attn_bwd_kernel       fp32 parity-mode backward (SIMT, shared memory).
 #include "kernels.h"
+#include <type_traits>
 
 namespace tapclip {
 namespace {
@@ -21,8 +22,9 @@ constexpr int KC = 32;
 // ------------------------------------------------------------------------------------------------
 // bf16 tensor-core forward
 // ------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
-attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N, int H, int npad, float scale_log2,
+attn_fwd_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, int npad, float scale_log2,
                     int probe_mode, float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int nwarps = blockDim.x >> 5;
@@ -35,7 +37,7 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N,
     uint8_t* Ks = Qs + qrows * 128;
     uint8_t* Vs = Ks + npad * 128;
 
-    const bf16* base = qkv + (int64_t)s * N * 3 * d + h * DH;
+    const T* base = qkv + (int64_t)s * N * 3 * d + h * DH;
     for (int idx = threadIdx.x; idx < qrows * 8; idx += blockDim.x) {
         const int row = idx >> 3, ch = idx & 7, grow = q0 + row;
         const bool ok = grow < N;
@@ -44,7 +46,7 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N,
     for (int idx = threadIdx.x; idx < npad * 8; idx += blockDim.x) {
         const int row = idx >> 3, ch = idx & 7;
         const bool ok = row < N;
-        const bf16* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
+        const T* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
         const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
         cp_async_16(smem_u32(Ks + off), src + d, ok);
         cp_async_16(smem_u32(Vs + off), src + 2 * d, ok);
@@ -83,8 +85,8 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N,
                 const int key = kc + (nbp * 2 + (mat >> 1)) * 8 + l7, ch = ks * 2 + (mat & 1);
                 uint32_t b[4];
                 ldmatrix_x4(b, smem_u32(Ks + key * 128 + ((ch ^ (key & 7)) << 4)));
-                mma_bf16_16816(sc[nbp * 2], qf[ks], b[0], b[1]);
-                mma_bf16_16816(sc[nbp * 2 + 1], qf[ks], b[2], b[3]);
+                mma_16816<T>(sc[nbp * 2], qf[ks], b[0], b[1]);
+                mma_16816<T>(sc[nbp * 2 + 1], qf[ks], b[2], b[3]);
             }
         }
         float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -115,8 +117,8 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N,
             const float p0 = exp2f(sc[nb][0] - mn0), p1 = exp2f(sc[nb][1] - mn0);
             const float p2 = exp2f(sc[nb][2] - mn1), p3 = exp2f(sc[nb][3] - mn1);
             l0 += p0 + p1; l1 += p2 + p3;
-            pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-            pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+            pa[nb >> 1][(nb & 1) * 2 + 0] = pack2<T>(p0, p1);
+            pa[nb >> 1][(nb & 1) * 2 + 1] = pack2<T>(p2, p3);
         }
 #pragma unroll
         for (int ks2 = 0; ks2 < 2; ++ks2) {
@@ -125,8 +127,8 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N,
                 const int key = kc + ks2 * 16 + (mat & 1) * 8 + l7, ch = dbp * 2 + (mat >> 1);
                 uint32_t b[4];
                 ldmatrix_x4_trans(b, smem_u32(Vs + key * 128 + ((ch ^ (key & 7)) << 4)));
-                mma_bf16_16816(o[dbp * 2], pa[ks2], b[0], b[1]);
-                mma_bf16_16816(o[dbp * 2 + 1], pa[ks2], b[2], b[3]);
+                mma_16816<T>(o[dbp * 2], pa[ks2], b[0], b[1]);
+                mma_16816<T>(o[dbp * 2 + 1], pa[ks2], b[2], b[3]);
             }
         }
     }
@@ -158,8 +160,8 @@ attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int N,
     uint8_t* Ws = Qs + warp * 16 * 128;
 #pragma unroll
     for (int db = 0; db < 8; ++db) {
-        *reinterpret_cast<uint32_t*>(Ws + g * 128 + ((db ^ (g & 7)) << 4) + tq * 4) = pack_bf16x2(o[db][0] * inv0, o[db][1] * inv0);
-        *reinterpret_cast<uint32_t*>(Ws + (g + 8) * 128 + ((db ^ ((g + 8) & 7)) << 4) + tq * 4) = pack_bf16x2(o[db][2] * inv1, o[db][3] * inv1);
+        *reinterpret_cast<uint32_t*>(Ws + g * 128 + ((db ^ (g & 7)) << 4) + tq * 4) = pack2<T>(o[db][0] * inv0, o[db][1] * inv0);
+        *reinterpret_cast<uint32_t*>(Ws + (g + 8) * 128 + ((db ^ ((g + 8) & 7)) << 4) + tq * 4) = pack2<T>(o[db][2] * inv1, o[db][3] * inv1);
     }
     __syncwarp();
 #pragma unroll
@@ -351,9 +353,9 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __res
 //            dP = dO V^T, D = rowsum(P o dP), dS = P o (dP - D) * scale, dQ = dS K; P and dS -> smem (bf16)
 //   phase 2 (warp owns 16 key rows):    dV = P^T dO, dK = dS^T Q   (A operands via ldmatrix.trans on P / dS)
 // ------------------------------------------------------------------------------------------------
-template <int NB16>
+template <int NB16, typename TQ>
 __global__ void __launch_bounds__(NB16 * 32, 1)
-attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out, bf16* __restrict__ dqkv, int N, int H,
+attn_bwd_mma_kernel(const TQ* __restrict__ qkv, const bf16* __restrict__ d_out, bf16* __restrict__ dqkv, int N, int H,
                     float scale) {
     constexpr int NP = NB16 * 16;               // padded sequence length
     constexpr int NB8 = NB16 * 2;               // 8-wide key blocks
@@ -368,16 +370,35 @@ attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x / H, h = blockIdx.x % H;
     const int d = H * DH;
-    const bf16* base = qkv + (int64_t)s * N * 3 * d + h * DH;
+    const TQ* base = qkv + (int64_t)s * N * 3 * d + h * DH;
     const bf16* dobase = d_out + (int64_t)s * N * d + h * DH;
     for (int idx = threadIdx.x; idx < NP * 8; idx += NB16 * 32) {
         const int row = idx >> 3, ch = idx & 7;
         const bool ok = row < N;
-        const bf16* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
+        const TQ* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
         const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
-        cp_async_16(smem_u32(Qs + off), src, ok);
-        cp_async_16(smem_u32(Ks + off), src + d, ok);
-        cp_async_16(smem_u32(Vs + off), src + 2 * d, ok);
+        if constexpr (sizeof(TQ) == 2 && std::is_same<TQ, bf16>::value) {
+            cp_async_16(smem_u32(Qs + off), src, ok);
+            cp_async_16(smem_u32(Ks + off), src + d, ok);
+            cp_async_16(smem_u32(Vs + off), src + 2 * d, ok);
+        } else {
+            // saved activations are fp16 (mixed mode): gradients are bf16, so Q/K/V are converted once here
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) raw = *reinterpret_cast<const uint4*>(src + part * d);
+                const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+                uint4 cv;
+                uint32_t* cp = reinterpret_cast<uint32_t*>(&cv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(hp[e]);
+                    cp[e] = pack_bf16x2(f.x, f.y);
+                }
+                uint8_t* dst = part == 0 ? Qs : (part == 1 ? Ks : Vs);
+                *reinterpret_cast<uint4*>(dst + off) = cv;
+            }
+        }
         cp_async_16(smem_u32(Os + off), dobase + (int64_t)(ok ? row : 0) * d + ch * 8, ok);
     }
     cp_async_commit();
@@ -534,41 +555,57 @@ attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_out
     }
 }
 
-template <int NB16>
-void launch_attn_bwd_mma(const bf16* qkv, const bf16* d_out, bf16* dqkv, int S, int N, int H, cudaStream_t stream) {
+template <int NB16, typename TQ>
+void launch_attn_bwd_mma(const TQ* qkv, const bf16* d_out, bf16* dqkv, int S, int N, int H, cudaStream_t stream) {
     constexpr int NP = NB16 * 16;
     const size_t smem = (size_t)4 * NP * 128 + (size_t)2 * NP * (NP * 2 + 16);
     static bool configured = false;
     if (!configured) {
-        TC_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<NB16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TC_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<NB16, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    attn_bwd_mma_kernel<NB16><<<S * H, NB16 * 32, smem, stream>>>(qkv, d_out, dqkv, N, H, 0.125f);
+    attn_bwd_mma_kernel<NB16, TQ><<<S * H, NB16 * 32, smem, stream>>>(qkv, d_out, dqkv, N, H, 0.125f);
+}
+
+template <typename TQ>
+void dispatch_attn_bwd_mma(const TQ* q, const bf16* g, bf16* o, int S, int N, int H, cudaStream_t stream) {
+    switch ((N + 15) / 16) {
+        case 1: launch_attn_bwd_mma<1, TQ>(q, g, o, S, N, H, stream); break;
+        case 2: launch_attn_bwd_mma<2, TQ>(q, g, o, S, N, H, stream); break;
+        case 3: launch_attn_bwd_mma<3, TQ>(q, g, o, S, N, H, stream); break;
+        case 4: launch_attn_bwd_mma<4, TQ>(q, g, o, S, N, H, stream); break;
+        case 5: launch_attn_bwd_mma<5, TQ>(q, g, o, S, N, H, stream); break;
+        case 6: launch_attn_bwd_mma<6, TQ>(q, g, o, S, N, H, stream); break;
+        case 7: launch_attn_bwd_mma<7, TQ>(q, g, o, S, N, H, stream); break;
+        default: launch_attn_bwd_mma<8, TQ>(q, g, o, S, N, H, stream); break;
+    }
 }
 
 }  // namespace
 
-void attention_fwd(const void* qkv, void* out, bool is_bf16, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream) {
+void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream) {
     if (S == 0) return;
     TC_CHECK(N >= 1 && H >= 1, "bad attention shape");
     if (probe.mode == PROBE_TEXT_COL) TC_CHECK(probe.out && probe.P >= 1 && probe.P <= N, "bad text probe");
     if (probe.mode == PROBE_CLS_ROW) TC_CHECK(probe.out && probe.seq_stride >= (int64_t)H * N, "bad CLS probe");
-    if (is_bf16) {
+    if (dt == DT_BF16 || dt == DT_F16) {
         const int npad = (int)round_up(N, KC);
         const int nrb = (int)ceil_div(N, 16);
         int nwarps = nrb <= 8 ? nrb : (int)ceil_div(nrb, ceil_div(nrb, 8));
         const int nz = (int)ceil_div(nrb, nwarps);
         const size_t smem = (size_t)(nwarps * 16 + 2 * npad) * 128;
         TC_CHECK(smem <= 227 * 1024, "sequence length %d too long for the attention kernel", N);
-        static size_t configured = 0;
-        if (smem > configured) {
-            TC_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+        static size_t configured[2] = {0, 0};
+        const int which = dt == DT_F16 ? 1 : 0;
+        if (smem > configured[which]) {
+            if (which) TC_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else TC_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[which] = smem;
         }
         dim3 grid((unsigned)(S * H), (unsigned)nz);
-        attn_fwd_mma_kernel<<<grid, nwarps * 32, smem, stream>>>((const bf16*)qkv, (bf16*)out, N, H, npad,
-                                                                 0.125f * 1.4426950408889634f, probe.mode, probe.out, probe.P,
-                                                                 probe.seq_stride);
+        const float sl2 = 0.125f * 1.4426950408889634f;
+        if (which) attn_fwd_mma_kernel<f16><<<grid, nwarps * 32, smem, stream>>>((const f16*)qkv, (f16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        else attn_fwd_mma_kernel<bf16><<<grid, nwarps * 32, smem, stream>>>((const bf16*)qkv, (bf16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
     } else {
         TC_CHECK(N <= KMAX * 32, "sequence length %d too long for the fp32 attention kernel", N);
         dim3 grid((unsigned)ceil_div(N, 4), (unsigned)(S * H));
@@ -578,24 +615,17 @@ void attention_fwd(const void* qkv, void* out, bool is_bf16, int S, int N, int H
     TC_LAUNCH_CHECK();
 }
 
-void attention_bwd(const void* qkv, const void* d_out, void* dqkv, bool is_bf16, int S, int N, int H, cudaStream_t stream) {
+void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, int grad_dt, int S, int N, int H, cudaStream_t stream) {
     if (S == 0) return;
     TC_CHECK(N <= 128, "attention backward supports sequence length <= 128 (got %d)", N);
-    const size_t smem = ((size_t)4 * N * LDH + (size_t)N * (N + 1)) * sizeof(float);
-    static size_t conf_f32 = 0;
-    if (is_bf16) {
-        const bf16* q = (const bf16*)qkv; const bf16* g = (const bf16*)d_out; bf16* o = (bf16*)dqkv;
-        switch ((N + 15) / 16) {
-            case 1: launch_attn_bwd_mma<1>(q, g, o, S, N, H, stream); break;
-            case 2: launch_attn_bwd_mma<2>(q, g, o, S, N, H, stream); break;
-            case 3: launch_attn_bwd_mma<3>(q, g, o, S, N, H, stream); break;
-            case 4: launch_attn_bwd_mma<4>(q, g, o, S, N, H, stream); break;
-            case 5: launch_attn_bwd_mma<5>(q, g, o, S, N, H, stream); break;
-            case 6: launch_attn_bwd_mma<6>(q, g, o, S, N, H, stream); break;
-            case 7: launch_attn_bwd_mma<7>(q, g, o, S, N, H, stream); break;
-            default: launch_attn_bwd_mma<8>(q, g, o, S, N, H, stream); break;
-        }
+    if (grad_dt == DT_BF16) {
+        if (qkv_dt == DT_BF16) dispatch_attn_bwd_mma<bf16>((const bf16*)qkv, (const bf16*)d_out, (bf16*)dqkv, S, N, H, stream);
+        else if (qkv_dt == DT_F16) dispatch_attn_bwd_mma<f16>((const f16*)qkv, (const bf16*)d_out, (bf16*)dqkv, S, N, H, stream);
+        else TC_CHECK(false, "unsupported saved-activation dtype %d", qkv_dt);
     } else {
+        TC_CHECK(grad_dt == DT_F32 && qkv_dt == DT_F32, "unsupported dtype combination for attention backward");
+        const size_t smem = ((size_t)4 * N * LDH + (size_t)N * (N + 1)) * sizeof(float);
+        static size_t conf_f32 = 0;
         if (smem > conf_f32) { TC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf_f32 = smem; }
         attn_bwd_kernel<float><<<S * H, 256, smem, stream>>>((const float*)qkv, (const float*)d_out, (float*)dqkv, N, H, 0.125f);
     }

@@ -131,8 +131,8 @@ TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias,
     TC_API_BEGIN
     GemmArgs g;
     g.a = a; g.w = w; g.bias = bias; g.out = out; g.out_pre = out_pre;
-    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.block_n = block_n;
-    if (dtype == DT_BF16) gemm_tc(g, S(stream));
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.block_n = block_n; g.dt = dtype;
+    if (dtype != DT_F32) gemm_tc(g, S(stream));
     else gemm_simt_f32(g, S(stream));
     TC_API_END
 }
@@ -140,14 +140,14 @@ TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias,
 TAPCLIP_API int tapclip_op_layernorm(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out, int32_t out_dtype,
                          float* x_copy, int64_t rows, int32_t d, void* stream) {
     TC_API_BEGIN
-    layernorm_fwd(x, x_row_stride, gamma, beta, out, out_dtype == DT_BF16, x_copy, rows, d, S(stream));
+    layernorm_fwd(x, x_row_stride, gamma, beta, out, out_dtype, x_copy, rows, d, S(stream));
     TC_API_END
 }
 
 TAPCLIP_API int tapclip_op_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast, int32_t cast_dtype,
                              int64_t rows, int32_t d, void* stream) {
     TC_API_BEGIN
-    layernorm_bwd(dy, x, gamma, dx_acc, dx_cast, cast_dtype == DT_BF16, rows, d, S(stream));
+    layernorm_bwd(dy, x, gamma, dx_acc, dx_cast, cast_dtype, rows, d, S(stream));
     TC_API_END
 }
 
@@ -156,14 +156,15 @@ TAPCLIP_API int tapclip_op_attention(const void* qkv, void* out, int32_t dtype, 
     TC_API_BEGIN
     AttnProbe p;
     p.mode = probe_mode; p.out = probe_out; p.P = probe_P; p.seq_stride = probe_seq_stride;
-    attention_fwd(qkv, out, dtype == DT_BF16, S_, N, H, p, S(stream));
+    attention_fwd(qkv, out, dtype, S_, N, H, p, S(stream));
     TC_API_END
 }
 
 TAPCLIP_API int tapclip_op_attention_bwd(const void* qkv, const void* d_out, void* dqkv, int32_t dtype, int32_t S_, int32_t N, int32_t H,
                              void* stream) {
     TC_API_BEGIN
-    attention_bwd(qkv, d_out, dqkv, dtype == DT_BF16, S_, N, H, S(stream));
+    // dtype = type of the saved qkv; gradients are fp32 in fp32 mode and bf16 otherwise
+    attention_bwd(qkv, dtype, d_out, dqkv, dtype == DT_F32 ? DT_F32 : DT_BF16, S_, N, H, S(stream));
     TC_API_END
 }
 
@@ -175,7 +176,7 @@ TAPCLIP_API int tapclip_op_attribution(const float* probe, float* raw, float* at
 
 TAPCLIP_API int tapclip_op_cast(const float* src, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
     TC_API_BEGIN
-    cast_f32(src, dst, dst_dtype == DT_BF16, n, S(stream));
+    cast_f32(src, dst, dst_dtype, n, S(stream));
     TC_API_END
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -14,6 +15,7 @@
 namespace tapclip {
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
 
 // ----------------------------------------------------------------------------------------------
 // error plumbing: every C-ABI export returns int (0 = ok) and leaves a thread-local message
@@ -49,7 +51,10 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 enum Act : int { ACT_NONE = -1, ACT_GELU_ERF = 0, ACT_QUICK_GELU = 1 };
-enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+// element types of activations / GEMM operands.  As an engine-level setting DT_F16 means "mixed": bf16 image tower
+// and gradients, fp16 text-tower forward (see DESIGN.md "Precision").
+enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
+static inline int dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 
 // ----------------------------------------------------------------------------------------------
 // device helpers
@@ -59,14 +64,24 @@ enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<f16>(f16 v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ f16 from_f32<f16>(float v) { return __float2half_rn(v); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<bf16>(float lo, float hi) { return pack_bf16x2(lo, hi); }
+template <> __device__ __forceinline__ uint32_t pack2<f16>(float lo, float hi) { return pack_f16x2(lo, hi); }
 
 // activation and its derivative; erf form matches torch.nn.GELU(), quick form x*sigmoid(1.702x)
 template <int ACT> __device__ __forceinline__ float act_fwd(float x) {
@@ -261,6 +276,15 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <typename T> __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma_16816<bf16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { mma_bf16_16816(d, a, b0, b1); }
+template <> __device__ __forceinline__ void mma_16816<f16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) { mma_f16_16816(d, a, b0, b1); }
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, bool pred) {
     int sz = pred ? 16 : 0;   // src-size 0 => zero-fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(sz) : "memory");

@@ -144,10 +144,10 @@ __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, 
         store_val<T>(dst + i, src[i]);
 }
 
-template <typename T, int ACT>
-__global__ void act_bwd_kernel(T* __restrict__ dh, const T* __restrict__ h_pre, int64_t n) {
+template <typename T, typename TH, int ACT>
+__global__ void act_bwd_kernel(T* __restrict__ dh, const TH* __restrict__ h_pre, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dh[i] = from_f32<T>(to_f32<T>(dh[i]) * act_bwd<ACT>(to_f32<T>(h_pre[i])));
+        dh[i] = from_f32<T>(to_f32<T>(dh[i]) * act_bwd<ACT>(to_f32<TH>(h_pre[i])));
 }
 
 // models/model_wrapper.py:79,83 for all (b, c) at once: logits = exp(logit_scale) * I_hat . T_hat^T.  One warp per pair.
@@ -263,12 +263,13 @@ inline unsigned grid_for(int64_t n, int threads = 256) { return (unsigned)std::m
 
 }  // namespace
 
-void patchify(const float* images, void* out, bool out_is_bf16, int B, int R, int p, int kpad, cudaStream_t stream) {
+void patchify(const float* images, void* out, int out_dt, int B, int R, int p, int kpad, cudaStream_t stream) {
     TC_CHECK(R % p == 0, "image size %d not divisible by patch %d", R, p);
     const int g = R / p, kdim = 3 * p * p;
     const int64_t total = (int64_t)B * g * g * kpad;
     if (total == 0) return;
-    if (out_is_bf16) patchify_kernel<bf16><<<grid_for(total), 256, 0, stream>>>(images, (bf16*)out, B, R, p, g, kdim, kpad);
+    if (out_dt == DT_BF16) patchify_kernel<bf16><<<grid_for(total), 256, 0, stream>>>(images, (bf16*)out, B, R, p, g, kdim, kpad);
+    else if (out_dt == DT_F16) patchify_kernel<f16><<<grid_for(total), 256, 0, stream>>>(images, (f16*)out, B, R, p, g, kdim, kpad);
     else patchify_kernel<float><<<grid_for(total), 256, 0, stream>>>(images, (float*)out, B, R, p, g, kdim, kpad);
     TC_LAUNCH_CHECK();
 }
@@ -303,39 +304,45 @@ void attribution_reduce(const float* probe, float* raw, float* attr, int C, int 
     TC_LAUNCH_CHECK();
 }
 
-void gather_rows(const float* x, void* out, bool out_is_bf16, int64_t rows, int64_t row_stride, int64_t row_offset, int d,
+void gather_rows(const float* x, void* out, int out_dt, int64_t rows, int64_t row_stride, int64_t row_offset, int d,
                  cudaStream_t stream) {
     if (rows == 0) return;
-    if (out_is_bf16) gather_rows_kernel<bf16><<<grid_for(rows * d), 256, 0, stream>>>(x, (bf16*)out, rows, row_stride, row_offset, d);
+    if (out_dt == DT_BF16) gather_rows_kernel<bf16><<<grid_for(rows * d), 256, 0, stream>>>(x, (bf16*)out, rows, row_stride, row_offset, d);
+    else if (out_dt == DT_F16) gather_rows_kernel<f16><<<grid_for(rows * d), 256, 0, stream>>>(x, (f16*)out, rows, row_stride, row_offset, d);
     else gather_rows_kernel<float><<<grid_for(rows * d), 256, 0, stream>>>(x, (float*)out, rows, row_stride, row_offset, d);
     TC_LAUNCH_CHECK();
 }
 
-void scatter_rows(const float* src, float* dst, void* dst_cast, bool cast_is_bf16, int64_t rows, int64_t row_stride,
+void scatter_rows(const float* src, float* dst, void* dst_cast, int cast_dt, int64_t rows, int64_t row_stride,
                   int64_t row_offset, int d, cudaStream_t stream) {
     if (rows == 0) return;
-    if (cast_is_bf16) scatter_rows_kernel<bf16><<<grid_for(rows * d), 256, 0, stream>>>(src, dst, (bf16*)dst_cast, rows, row_stride, row_offset, d);
+    TC_CHECK(cast_dt != DT_F16, "gradients are never fp16");
+    if (cast_dt == DT_BF16) scatter_rows_kernel<bf16><<<grid_for(rows * d), 256, 0, stream>>>(src, dst, (bf16*)dst_cast, rows, row_stride, row_offset, d);
     else scatter_rows_kernel<float><<<grid_for(rows * d), 256, 0, stream>>>(src, dst, (float*)dst_cast, rows, row_stride, row_offset, d);
     TC_LAUNCH_CHECK();
 }
 
-void cast_f32(const float* src, void* dst, bool dst_is_bf16, int64_t n, cudaStream_t stream) {
+void cast_f32(const float* src, void* dst, int dst_dt, int64_t n, cudaStream_t stream) {
     if (n == 0) return;
-    if (dst_is_bf16) cast_kernel<bf16><<<grid_for(n), 256, 0, stream>>>(src, (bf16*)dst, n);
+    if (dst_dt == DT_BF16) cast_kernel<bf16><<<grid_for(n), 256, 0, stream>>>(src, (bf16*)dst, n);
+    else if (dst_dt == DT_F16) cast_kernel<f16><<<grid_for(n), 256, 0, stream>>>(src, (f16*)dst, n);
     else cast_kernel<float><<<grid_for(n), 256, 0, stream>>>(src, (float*)dst, n);
     TC_LAUNCH_CHECK();
 }
 
-void act_bwd_inplace(void* dh, const void* h_pre, bool is_bf16, int act, int64_t n, cudaStream_t stream) {
+void act_bwd_inplace(void* dh, int dh_dt, const void* h_pre, int h_dt, int act, int64_t n, cudaStream_t stream) {
     if (n == 0) return;
     const unsigned grid = grid_for(n);
-    if (is_bf16) {
-        if (act == ACT_GELU_ERF) act_bwd_kernel<bf16, ACT_GELU_ERF><<<grid, 256, 0, stream>>>((bf16*)dh, (const bf16*)h_pre, n);
-        else act_bwd_kernel<bf16, ACT_QUICK_GELU><<<grid, 256, 0, stream>>>((bf16*)dh, (const bf16*)h_pre, n);
-    } else {
-        if (act == ACT_GELU_ERF) act_bwd_kernel<float, ACT_GELU_ERF><<<grid, 256, 0, stream>>>((float*)dh, (const float*)h_pre, n);
-        else act_bwd_kernel<float, ACT_QUICK_GELU><<<grid, 256, 0, stream>>>((float*)dh, (const float*)h_pre, n);
-    }
+#define TC_ACT_BWD(T, TH)                                                                                             \
+    do {                                                                                                              \
+        if (act == ACT_GELU_ERF) act_bwd_kernel<T, TH, ACT_GELU_ERF><<<grid, 256, 0, stream>>>((T*)dh, (const TH*)h_pre, n); \
+        else act_bwd_kernel<T, TH, ACT_QUICK_GELU><<<grid, 256, 0, stream>>>((T*)dh, (const TH*)h_pre, n);             \
+    } while (0)
+    if (dh_dt == DT_F32 && h_dt == DT_F32) TC_ACT_BWD(float, float);
+    else if (dh_dt == DT_BF16 && h_dt == DT_BF16) TC_ACT_BWD(bf16, bf16);
+    else if (dh_dt == DT_BF16 && h_dt == DT_F16) TC_ACT_BWD(bf16, f16);
+    else TC_CHECK(false, "unsupported dtype combination for act_bwd (%d, %d)", dh_dt, h_dt);
+#undef TC_ACT_BWD
     TC_LAUNCH_CHECK();
 }
 

@@ -54,7 +54,7 @@ void DevBuf::release() {
 }
 
 Engine::Engine(const tapclip_config& c) : cfg(c) {
-    TC_CHECK(c.dtype == DT_F32 || c.dtype == DT_BF16, "dtype must be 0 (fp32) or 1 (bf16)");
+    TC_CHECK(c.dtype == DT_F32 || c.dtype == DT_BF16 || c.dtype == DT_F16, "dtype must be 0 (fp32), 1 (bf16) or 2 (mixed bf16/fp16)");
     TC_CHECK(c.act == ACT_GELU_ERF || c.act == ACT_QUICK_GELU, "act must be 0 (gelu_erf) or 1 (quick_gelu)");
     TC_CHECK(c.image_size > 0 && c.patch_size > 0 && c.image_size % c.patch_size == 0, "image_size %% patch_size != 0");
     TC_CHECK(c.vision_width == c.vision_heads * 64 && c.text_width == c.text_heads * 64,
@@ -68,8 +68,10 @@ Engine::Engine(const tapclip_config& c) : cfg(c) {
     cudaDeviceProp prop;
     TC_CUDA(cudaGetDeviceProperties(&prop, dev));
     TC_CHECK(prop.major == 10, "libtapclip needs an sm_100 (B200) device, found sm_%d%d; there is no fallback path", prop.major, prop.minor);
-    bf = (c.dtype == DT_BF16);
-    esz = bf ? 2 : 4;
+    vdt = (c.dtype == DT_F32) ? DT_F32 : DT_BF16;
+    tdt = (c.dtype == DT_F32) ? DT_F32 : (c.dtype == DT_F16 ? DT_F16 : DT_BF16);
+    gdt = vdt;
+    esz = dtype_size(vdt);
     grid = c.image_size / c.patch_size;
     n_tok = grid * grid + 1;
     kpatch = 3 * c.patch_size * c.patch_size;
@@ -97,10 +99,9 @@ int64_t Engine::workspace_bytes() {
 }
 
 // ---- weights ---------------------------------------------------------------------------------------
-void* Engine::store(const std::string& key, const float* src, int R, int C, int dst_ld, bool transpose, bool as_act, cudaStream_t st) {
-    const bool to_bf16 = as_act && bf;
+void* Engine::store(const std::string& key, const float* src, int R, int C, int dst_ld, bool transpose, int dt, cudaStream_t st) {
     const int rows = transpose ? C : R;
-    const size_t bytes = (size_t)rows * dst_ld * (to_bf16 ? 2 : 4);
+    const size_t bytes = (size_t)rows * dst_ld * dtype_size(dt);
     void* dst = nullptr;
     auto it = weights.find(key);
     if (it != weights.end()) { cudaFree(it->second); weights.erase(it); }
@@ -109,7 +110,8 @@ void* Engine::store(const std::string& key, const float* src, int R, int C, int 
     TC_CUDA(cudaMemsetAsync(dst, 0, bytes, st));
     const int64_t total = (int64_t)R * C;
     const unsigned g = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
-    if (to_bf16) convert_weight_kernel<bf16><<<g, 256, 0, st>>>(src, (bf16*)dst, R, C, dst_ld, transpose ? 1 : 0);
+    if (dt == DT_BF16) convert_weight_kernel<bf16><<<g, 256, 0, st>>>(src, (bf16*)dst, R, C, dst_ld, transpose ? 1 : 0);
+    else if (dt == DT_F16) convert_weight_kernel<f16><<<g, 256, 0, st>>>(src, (f16*)dst, R, C, dst_ld, transpose ? 1 : 0);
     else convert_weight_kernel<float><<<g, 256, 0, st>>>(src, (float*)dst, R, C, dst_ld, transpose ? 1 : 0);
     TC_LAUNCH_CHECK();
     ++launches;
@@ -140,20 +142,20 @@ void Engine::load_weight(const std::string& name, const float* data, int ndim, c
         return;
     if (name == "visual.conv1.weight") {
         if (!shape_is(ndim, shape, {dv, 3, cfg.patch_size, cfg.patch_size})) bad_shape();
-        w_patch = store(name, data, dv, kpatch, kpatch_pad, false, true, st);
+        w_patch = store(name, data, dv, kpatch, kpatch_pad, false, vdt, st);
         return;
     }
-    if (name == "visual.class_embedding") { if (!shape_is(ndim, shape, {dv})) bad_shape(); cls_emb = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
-    if (name == "visual.positional_embedding") { if (!shape_is(ndim, shape, {n_tok, dv})) bad_shape(); pos_emb = (float*)store(name, data, n_tok, dv, dv, false, false, st); return; }
-    if (name == "visual.ln_pre.weight") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_pre_g = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
-    if (name == "visual.ln_pre.bias") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_pre_b = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
-    if (name == "visual.ln_post.weight") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_post_g = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
-    if (name == "visual.ln_post.bias") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_post_b = (float*)store(name, data, 1, dv, dv, false, false, st); return; }
-    if (name == "visual.proj") { if (!shape_is(ndim, shape, {dv, E})) bad_shape(); w_vproj = store(name, data, dv, E, dv, true, true, st); return; }
+    if (name == "visual.class_embedding") { if (!shape_is(ndim, shape, {dv})) bad_shape(); cls_emb = (float*)store(name, data, 1, dv, dv, false, DT_F32, st); return; }
+    if (name == "visual.positional_embedding") { if (!shape_is(ndim, shape, {n_tok, dv})) bad_shape(); pos_emb = (float*)store(name, data, n_tok, dv, dv, false, DT_F32, st); return; }
+    if (name == "visual.ln_pre.weight") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_pre_g = (float*)store(name, data, 1, dv, dv, false, DT_F32, st); return; }
+    if (name == "visual.ln_pre.bias") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_pre_b = (float*)store(name, data, 1, dv, dv, false, DT_F32, st); return; }
+    if (name == "visual.ln_post.weight") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_post_g = (float*)store(name, data, 1, dv, dv, false, DT_F32, st); return; }
+    if (name == "visual.ln_post.bias") { if (!shape_is(ndim, shape, {dv})) bad_shape(); ln_post_b = (float*)store(name, data, 1, dv, dv, false, DT_F32, st); return; }
+    if (name == "visual.proj") { if (!shape_is(ndim, shape, {dv, E})) bad_shape(); w_vproj = store(name, data, dv, E, dv, true, vdt, st); return; }
     if (name == "text_projection") {
         if (!shape_is(ndim, shape, {dt, E})) bad_shape();
-        w_tproj = store(name, data, dt, E, dt, true, true, st);                 // [E, D] forward operand
-        wt_tproj = store(name + "#T", data, dt, E, E, false, true, st);         // [D, E] dgrad operand
+        w_tproj = store(name, data, dt, E, dt, true, tdt, st);                  // [E, D] forward operand
+        wt_tproj = store(name + "#T", data, dt, E, E, false, gdt, st);          // [D, E] dgrad operand
         return;
     }
     // transformer blocks
@@ -170,11 +172,11 @@ void Engine::load_weight(const std::string& name, const float* data, int ndim, c
     BlockWeights& b = blocks[layer];
     const int d = is_vis ? dv : dt;
     const bool need_t = is_txt;          // dgrad copies only for the text tower (the image tower gets no gradient)
-    auto vec = [&](float*& slot, int n) { if (!shape_is(ndim, shape, {n})) bad_shape(); slot = (float*)store(name, data, 1, n, n, false, false, st); };
+    auto vec = [&](float*& slot, int n) { if (!shape_is(ndim, shape, {n})) bad_shape(); slot = (float*)store(name, data, 1, n, n, false, DT_F32, st); };
     auto mat = [&](void*& w, void*& wt, int N, int K) {
         if (!shape_is(ndim, shape, {N, K})) bad_shape();
-        w = store(name, data, N, K, K, false, true, st);
-        if (need_t) wt = store(name + "#T", data, N, K, N, true, true, st);     // [K, N]
+        w = store(name, data, N, K, K, false, is_vis ? vdt : tdt, st);
+        if (need_t) wt = store(name + "#T", data, N, K, N, true, gdt, st);      // [K, N], gradient type
     };
     if (leaf == "ln_1.weight") vec(b.ln1_g, d);
     else if (leaf == "ln_1.bias") vec(b.ln1_b, d);
@@ -263,22 +265,22 @@ const char* Engine::profile_report() {
 
 // ---- primitive wrappers ------------------------------------------------------------------------------
 void Engine::gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K,
-                  int epi, int act, cudaStream_t st) {
+                  int epi, int act, int dt, cudaStream_t st) {
     GemmArgs g;
     g.a = a; g.w = w; g.bias = bias; g.out = out; g.out_pre = out_pre;
-    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.dt = dt;
     ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, epi};
     if (profiling) prof_begin(r, st);
-    if (bf) gemm_tc(g, st);
+    if (dt != DT_F32) gemm_tc(g, st);
     else gemm_simt_f32(g, st);
     if (profiling) prof_end(r, st);
     ++launches;
 }
 
-void Engine::attn_fwd(const void* qkv, void* out, int S, int N, int H, const AttnProbe& probe, cudaStream_t st) {
+void Engine::attn_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t st) {
     ProfRec r{nullptr, nullptr, 4.0 * (double)S * H * (double)N * N * 64.0, 1, S, N, H, probe.mode};
     if (profiling) prof_begin(r, st);
-    attention_fwd(qkv, out, bf, S, N, H, probe, st);
+    attention_fwd(qkv, out, dt, S, N, H, probe, st);
     if (profiling) prof_end(r, st);
     ++launches;
 }
@@ -286,7 +288,7 @@ void Engine::attn_fwd(const void* qkv, void* out, int S, int N, int H, const Att
 void Engine::attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st) {
     ProfRec r{nullptr, nullptr, 10.0 * (double)S * H * (double)N * N * 64.0, 2, S, N, H, 0};
     if (profiling) prof_begin(r, st);
-    attention_bwd(qkv, d_out, dqkv, bf, S, N, H, st);
+    attention_bwd(qkv, tdt, d_out, dqkv, gdt, S, N, H, st);
     if (profiling) prof_end(r, st);
     ++launches;
 }
@@ -295,7 +297,7 @@ void Engine::attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int
 //   probe      : attention probe for this layer (or PROBE_NONE)
 //   stop_after_attention_probs : attribution pass, last block: only the probabilities are needed
 //   save       : keep x copies / qkv / h_pre for the backward pass (slot = layer)
-void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
+void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
                            DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st) {
     const int64_t M = (int64_t)S * N;
     float* sx0 = nullptr; float* sx1 = nullptr; void* sqkv = qkv.p; void* shpre = nullptr;
@@ -305,14 +307,14 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
         sqkv = (uint8_t*)t_save_qkv.p + (int64_t)save_slot * M * 3 * d * esz;
         shpre = (uint8_t*)t_save_h.p + (int64_t)save_slot * M * 4 * d * esz;
     }
-    layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, bf, sx0, M, d, st); ++launches;
-    gemm(ln.p, b.w_qkv, b.b_qkv, sqkv, nullptr, M, 3 * d, d, EPI_BF16, ACT_NONE, st);
-    attn_fwd(sqkv, attn.p, S, N, H, probe, st);
+    layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, dt, sx0, M, d, st); ++launches;
+    gemm(ln.p, b.w_qkv, b.b_qkv, sqkv, nullptr, M, 3 * d, d, EPI_BF16, ACT_NONE, dt, st);
+    attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
     if (probs_only) return;
-    gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, st);
-    layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, bf, sx1, M, d, st); ++launches;
-    gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, M, 4 * d, d, EPI_BF16, cfg.act, st);
-    gemm(hbuf.p, b.w_proj, b.b_proj, x, nullptr, M, d, 4 * d, EPI_F32_ADD, ACT_NONE, st);
+    gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, dt, st);
+    layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, dt, sx1, M, d, st); ++launches;
+    gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, M, 4 * d, d, EPI_BF16, cfg.act, dt, st);
+    gemm(hbuf.p, b.w_proj, b.b_proj, x, nullptr, M, d, 4 * d, EPI_F32_ADD, ACT_NONE, dt, st);
 }
 
 // ---- image tower (row A4) ---------------------------------------------------------------------------
@@ -332,10 +334,10 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
     v_h.ensure(M * 4 * d * esz);
     v_pooled.ensure((int64_t)B * d * esz);
 
-    patchify(images, v_patches.p, bf, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
-    gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, st);
+    patchify(images, v_patches.p, vdt, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
+    gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, vdt, st);
     assemble_tokens((const float*)v_patch_out.p, cls_emb, pos_emb, (float*)v_x.p, B, N, d, st); ++launches;
-    layernorm_fwd((const float*)v_x.p, d, ln_pre_g, ln_pre_b, v_x.p, false, nullptr, M, d, st); ++launches;
+    layernorm_fwd((const float*)v_x.p, d, ln_pre_g, ln_pre_b, v_x.p, DT_F32, nullptr, M, d, st); ++launches;
     for (int l = 0; l < L; ++l) {
         AttnProbe probe;
         if (out_cls_rows) {
@@ -343,10 +345,10 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
             probe.out = out_cls_rows + (int64_t)l * H * N;
             probe.seq_stride = (int64_t)L * H * N;
         }
-        block_forward(vis[l], (float*)v_x.p, B, N, d, H, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st);
+        block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st);
     }
-    layernorm_fwd((const float*)v_x.p, (int64_t)N * d, ln_post_g, ln_post_b, v_pooled.p, bf, nullptr, B, d, st); ++launches;
-    gemm(v_pooled.p, w_vproj, nullptr, out_feat, nullptr, B, E, d, EPI_F32, ACT_NONE, st);
+    layernorm_fwd((const float*)v_x.p, (int64_t)N * d, ln_post_g, ln_post_b, v_pooled.p, vdt, nullptr, B, d, st); ++launches;
+    gemm(v_pooled.p, w_vproj, nullptr, out_feat, nullptr, B, E, d, EPI_F32, ACT_NONE, vdt, st);
 }
 
 // ---- text side (rows A2, A6-A10) ----------------------------------------------------------------------
@@ -389,7 +391,7 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
             AttnProbe probe;
             const bool last = (l == L - 1);
             if (last) { probe.mode = PROBE_TEXT_COL; probe.out = (float*)t_probe.p; probe.P = P; }
-            block_forward(txt[l], x, C, T, D, H, t_ln, t_qkv, t_attn, t_h, probe, last, -1, st);
+            block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, probe, last, -1, st);
         }
         attribution_reduce((const float*)t_probe.p, (float*)t_attr_raw.p, (float*)t_attr.p, C, H, P, st); ++launches;
         attr = (const float*)t_attr.p;
@@ -404,10 +406,10 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
     splice_prompts(ctx, tok, attr, PA, x, C, P, Lc, D, st); ++launches;
     for (int l = 0; l < L; ++l) {
         AttnProbe none;
-        block_forward(txt[l], x, C, T, D, H, t_ln, t_qkv, t_attn, t_h, none, false, save ? l : -1, st);
+        block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, none, false, save ? l : -1, st);
     }
-    gather_rows(x, t_pooled.p, bf, C, T, T - 1, D, st); ++launches;
-    gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, st);
+    gather_rows(x, t_pooled.p, tdt, C, T, T - 1, D, st); ++launches;
+    gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, tdt, st);
     l2norm_fwd((const float*)t_feat.p, (float*)t_tfeat.p, (float*)t_inv_norm.p, C, E, st); ++launches;
     if (out_text_feat) TC_CUDA(cudaMemcpyAsync(out_text_feat, t_tfeat.p, (size_t)C * E * 4, cudaMemcpyDeviceToDevice, st));
     if (save) { saved.valid = true; saved.C = C; saved.P = P; saved.T = T; saved.PA = PA; saved.has_attr = (mode == 1); }
@@ -429,11 +431,11 @@ void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream
     b_dfeatc.ensure((int64_t)C * E * esz);
     b_dpool.ensure((int64_t)C * D * 4);
     // L2-norm and projection backward (model_wrapper.py:74-75), then scatter into the last position (:73)
-    l2norm_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, (float*)b_dfeat.p, b_dfeatc.p, bf, C, E, st); ++launches;
-    gemm(b_dfeatc.p, wt_tproj, nullptr, b_dpool.p, nullptr, C, D, E, EPI_F32, ACT_NONE, st);
+    l2norm_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, (float*)b_dfeat.p, b_dfeatc.p, gdt, C, E, st); ++launches;
+    gemm(b_dfeatc.p, wt_tproj, nullptr, b_dpool.p, nullptr, C, D, E, EPI_F32, ACT_NONE, gdt, st);
     TC_CUDA(cudaMemsetAsync(b_dx.p, 0, (size_t)M * D * 4, st));
     TC_CUDA(cudaMemsetAsync(b_dxc.p, 0, (size_t)M * D * esz, st));
-    scatter_rows((const float*)b_dpool.p, (float*)b_dx.p, b_dxc.p, bf, C, T, T - 1, D, st); ++launches;
+    scatter_rows((const float*)b_dpool.p, (float*)b_dx.p, b_dxc.p, gdt, C, T, T - 1, D, st); ++launches;
     for (int l = L - 1; l >= 0; --l) {
         const BlockWeights& b = txt[l];
         const float* x0 = (const float*)t_save_x.p + (int64_t)(2 * l) * M * D;
@@ -441,15 +443,15 @@ void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream
         const void* qkv = (const uint8_t*)t_save_qkv.p + (int64_t)l * M * 3 * D * esz;
         const void* hpre = (const uint8_t*)t_save_h.p + (int64_t)l * M * 4 * D * esz;
         // MLP branch
-        gemm(b_dxc.p, b.wt_proj, nullptr, b_dh.p, nullptr, M, 4 * D, D, EPI_BF16, ACT_NONE, st);
-        act_bwd_inplace(b_dh.p, hpre, bf, cfg.act, M * 4 * D, st); ++launches;
-        gemm(b_dh.p, b.wt_fc, nullptr, b_dln.p, nullptr, M, D, 4 * D, EPI_F32, ACT_NONE, st);
-        layernorm_bwd((const float*)b_dln.p, x1, b.ln2_g, (float*)b_dx.p, b_dxc.p, bf, M, D, st); ++launches;
+        gemm(b_dxc.p, b.wt_proj, nullptr, b_dh.p, nullptr, M, 4 * D, D, EPI_BF16, ACT_NONE, gdt, st);
+        act_bwd_inplace(b_dh.p, gdt, hpre, tdt, cfg.act, M * 4 * D, st); ++launches;
+        gemm(b_dh.p, b.wt_fc, nullptr, b_dln.p, nullptr, M, D, 4 * D, EPI_F32, ACT_NONE, gdt, st);
+        layernorm_bwd((const float*)b_dln.p, x1, b.ln2_g, (float*)b_dx.p, b_dxc.p, gdt, M, D, st); ++launches;
         // attention branch
-        gemm(b_dxc.p, b.wt_o, nullptr, b_dattn.p, nullptr, M, D, D, EPI_BF16, ACT_NONE, st);
+        gemm(b_dxc.p, b.wt_o, nullptr, b_dattn.p, nullptr, M, D, D, EPI_BF16, ACT_NONE, gdt, st);
         attn_bwd(qkv, b_dattn.p, b_dqkv.p, C, T, H, st);
-        gemm(b_dqkv.p, b.wt_qkv, nullptr, b_dln.p, nullptr, M, D, 3 * D, EPI_F32, ACT_NONE, st);
-        layernorm_bwd((const float*)b_dln.p, x0, b.ln1_g, (float*)b_dx.p, b_dxc.p, bf, M, D, st); ++launches;
+        gemm(b_dqkv.p, b.wt_qkv, nullptr, b_dln.p, nullptr, M, D, 3 * D, EPI_F32, ACT_NONE, gdt, st);
+        layernorm_bwd((const float*)b_dln.p, x0, b.ln1_g, (float*)b_dx.p, b_dxc.p, gdt, M, D, st); ++launches;
     }
     splice_bwd((const float*)b_dx.p, saved.has_attr ? (const float*)t_attr.p : nullptr, saved.PA, out_dctx, C, P, T, D, st); ++launches;
 }

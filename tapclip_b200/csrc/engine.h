@@ -26,8 +26,10 @@ struct BlockWeights {
 
 struct Engine {
     tapclip_config cfg;
-    bool bf = true;             // activation / GEMM operand type is bf16 (else fp32)
-    int esz = 2;                // bytes per activation element
+    int vdt = DT_BF16;          // activation / operand type of the image tower
+    int tdt = DT_BF16;          // ... of the text-tower forward (fp16 in mixed mode: see DESIGN.md "Precision")
+    int gdt = DT_BF16;          // ... of the backward pass (gradients are never fp16)
+    int esz = 2;                // bytes per activation element (same for all three)
     int grid = 0, n_tok = 0, kpatch = 0, kpatch_pad = 0;
     int64_t launches = 0;
 
@@ -59,16 +61,16 @@ struct Engine {
     std::vector<DevBuf*> all_bufs();
     int64_t workspace_bytes();
 
-    void* store(const std::string& key, const float* src, int R, int C, int dst_ld, bool transpose, bool as_act, cudaStream_t st);
+    void* store(const std::string& key, const float* src, int R, int C, int dst_ld, bool transpose, int dt, cudaStream_t st);
     void load_weight(const std::string& name, const float* data, int ndim, const int64_t* shape, cudaStream_t st);
     std::string missing_weights() const;
 
     void gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int epi,
-              int act, cudaStream_t st);
-    void attn_fwd(const void* qkv, void* out, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
+              int act, int dt, cudaStream_t st);
+    void attn_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
     void attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st);
-    void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf,
-                       const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st);
+    void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
+                       DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st);
     void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, cudaStream_t st);
     void text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
                       float* out_text_feat, cudaStream_t st);

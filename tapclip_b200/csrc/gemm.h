@@ -22,9 +22,10 @@ struct GemmArgs {
     int epi = EPI_F32;
     int act = ACT_NONE;
     int block_n = 0;           // 0 = choose; 128 or 256 force a tile width (tcgen05 path only)
+    int dt = DT_BF16;          // tcgen05 path: 16-bit type of A, W and of the EPI_BF16 output (DT_BF16 or DT_F16)
 };
 
-// tcgen05/TMEM/TMA path: A and W bf16; out bf16 (EPI_BF16) or f32
+// tcgen05/TMEM/TMA path: A and W bf16 (or fp16, g.dt); out = same 16-bit type (EPI_BF16) or f32
 void gemm_tc(const GemmArgs& g, cudaStream_t stream);
 
 // fp32 SIMT path for the fp32 parity mode: A, W, out all f32; EPI_BF16 means "store in the activation

@@ -11,6 +11,7 @@
 // Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  M/N/K tails are handled by TMA zero-fill on loads and clipping on stores.
 #include "gemm.h"
+#include <type_traits>
 
 namespace tapclip {
 
@@ -42,18 +43,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
     return d;
 }
-// UMMA instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M=128, N=BLOCK_N
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) /*C=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(n >> 3) << 17) |
+// UMMA instruction descriptor: (bf16|fp16) x same -> fp32, both operands K-major, M=128, N=BLOCK_N
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool f16) {
+    const uint32_t fmt = f16 ? 0u : 1u;             // F16F32Format: 0 = F16, 1 = BF16
+    return (1u << 4) /*C=f32*/ | (fmt << 7) /*A*/ | (fmt << 10) /*B*/ | ((uint32_t)(n >> 3) << 17) |
            ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE>
+template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
                const float* __restrict__ bias, int M, int N, int K) {
     using C = Cfg<BLOCK_N>;
+    using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
@@ -105,7 +108,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BLOCK_N);
+            constexpr uint32_t idesc = make_idesc(BLOCK_N, F16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -179,8 +182,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 uint4 p;
-                                p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                                p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                                p.x = pack2<T16>(v[8 * j + 0], v[8 * j + 1]); p.y = pack2<T16>(v[8 * j + 2], v[8 * j + 3]);
+                                p.z = pack2<T16>(v[8 * j + 4], v[8 * j + 5]); p.w = pack2<T16>(v[8 * j + 6], v[8 * j + 7]);
                                 *reinterpret_cast<uint4*>(stage_buf + row_off + (((uint32_t)j ^ sw) << 4)) = p;
                             }
 #pragma unroll
@@ -188,8 +191,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 uint4 p;
-                                p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                                p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                                p.x = pack2<T16>(v[8 * j + 0], v[8 * j + 1]); p.y = pack2<T16>(v[8 * j + 2], v[8 * j + 3]);
+                                p.z = pack2<T16>(v[8 * j + 4], v[8 * j + 5]); p.w = pack2<T16>(v[8 * j + 6], v[8 * j + 7]);
                                 *reinterpret_cast<uint4*>(stage_buf + EPI_BUF_BYTES + row_off + (((uint32_t)j ^ sw) << 4)) = p;
                             }
                             fence_proxy_async_smem();
@@ -208,8 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 uint4 p;
-                                p.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]); p.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                                p.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); p.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                                p.x = pack2<T16>(v[8 * j + 0], v[8 * j + 1]); p.y = pack2<T16>(v[8 * j + 2], v[8 * j + 3]);
+                                p.z = pack2<T16>(v[8 * j + 4], v[8 * j + 5]); p.w = pack2<T16>(v[8 * j + 6], v[8 * j + 7]);
                                 *reinterpret_cast<uint4*>(sb + row_off + (((uint32_t)j ^ sw) << 4)) = p;
                             }
                             fence_proxy_async_smem();
@@ -314,10 +317,11 @@ CUtensorMap make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, i
 
 int g_num_sms = 0;
 
-template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE>
+template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16>
 void launch(const GemmArgs& g, cudaStream_t stream) {
     using C = Cfg<BLOCK_N>;
-    auto kern = gemm_tc_kernel<BLOCK_N, EPI, ACT, STORE_PRE>;
+    auto kern = gemm_tc_kernel<BLOCK_N, EPI, ACT, STORE_PRE, F16>;
+    constexpr CUtensorMapDataType DT16 = F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     static bool configured = false;
     if (!configured) {
         TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -328,30 +332,30 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
         TC_CUDA(cudaGetDevice(&dev));
         TC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    CUtensorMap ta = make_tmap(g.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K);
-    CUtensorMap tb = make_tmap(g.w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, g.K, g.ldw, BLOCK_N, BLOCK_K);
+    CUtensorMap ta = make_tmap(g.a, DT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K);
+    CUtensorMap tb = make_tmap(g.w, DT16, 2, g.N, g.K, g.ldw, BLOCK_N, BLOCK_K);
     CUtensorMap tc, tc2;
-    if (EPI == EPI_BF16) tc = make_tmap(g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, 64);
+    if (EPI == EPI_BF16) tc = make_tmap(g.out, DT16, 2, g.M, g.N, g.ldo, 32, 64);
     else tc = make_tmap(g.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldo, 32, 32);
     tc2 = tc;
-    if (STORE_PRE) tc2 = make_tmap(g.out_pre, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, 64);
+    if (STORE_PRE) tc2 = make_tmap(g.out_pre, DT16, 2, g.M, g.N, g.ldo, 32, 64);
     const int64_t tiles = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, BLOCK_N);
     const int grid = (int)std::min<int64_t>(tiles, g_num_sms);
     kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, g.bias, (int)g.M, (int)g.N, (int)g.K);
     TC_LAUNCH_CHECK();
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool F16>
 void dispatch(const GemmArgs& g, cudaStream_t stream) {
-    if (g.epi == EPI_F32) return launch<BLOCK_N, EPI_F32, ACT_NONE, false>(g, stream);
-    if (g.epi == EPI_F32_ADD) return launch<BLOCK_N, EPI_F32_ADD, ACT_NONE, false>(g, stream);
+    if (g.epi == EPI_F32) return launch<BLOCK_N, EPI_F32, ACT_NONE, false, F16>(g, stream);
+    if (g.epi == EPI_F32_ADD) return launch<BLOCK_N, EPI_F32_ADD, ACT_NONE, false, F16>(g, stream);
     TC_CHECK(g.epi == EPI_BF16, "unknown epilogue %d", g.epi);
     const bool pre = g.out_pre != nullptr;
-    if (g.act == ACT_NONE) { TC_CHECK(!pre, "out_pre needs an activation"); return launch<BLOCK_N, EPI_BF16, ACT_NONE, false>(g, stream); }
-    if (g.act == ACT_GELU_ERF) return pre ? launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, true>(g, stream)
-                                          : launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, false>(g, stream);
-    if (g.act == ACT_QUICK_GELU) return pre ? launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, true>(g, stream)
-                                            : launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, false>(g, stream);
+    if (g.act == ACT_NONE) { TC_CHECK(!pre, "out_pre needs an activation"); return launch<BLOCK_N, EPI_BF16, ACT_NONE, false, F16>(g, stream); }
+    if (g.act == ACT_GELU_ERF) return pre ? launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, true, F16>(g, stream)
+                                          : launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, false, F16>(g, stream);
+    if (g.act == ACT_QUICK_GELU) return pre ? launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, true, F16>(g, stream)
+                                            : launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, false, F16>(g, stream);
     TC_CHECK(false, "unknown activation %d", g.act);
 }
 
@@ -367,8 +371,9 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
         const int64_t tiles256 = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, 256);
         bn = (g.N % 256 == 0 && tiles256 >= 2 * g_num_sms) ? 256 : 128;
     }
-    if (bn == 256) dispatch<256>(g, stream);
-    else dispatch<128>(g, stream);
+    TC_CHECK(g.dt == DT_BF16 || g.dt == DT_F16, "tcgen05 GEMM operands must be bf16 or fp16");
+    if (g.dt == DT_F16) { if (bn == 256) dispatch<256, true>(g, stream); else dispatch<128, true>(g, stream); }
+    else { if (bn == 256) dispatch<256, false>(g, stream); else dispatch<128, false>(g, stream); }
 }
 
 }  // namespace tapclip

@@ -7,18 +7,18 @@ namespace tapclip {
 // ---- norm.cu ---------------------------------------------------------------------------------------
 // LayerNorm over the last dim (eps 1e-5, torch semantics): out[r,:] = (x[r,:]-mean)*rstd*gamma+beta.
 // x rows are `x_row_stride` floats apart (lets ln_post read only the CLS rows); out is dense [rows,d].
-// out_is_bf16 selects the activation type.  x_copy (optional, dense fp32) receives the unnormalised row
+// out_dt (DType) selects the activation type.  x_copy (optional, dense fp32) receives the unnormalised row
 // (saved for the backward pass).  In-place fp32 (out == x) is allowed.
 void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out,
-                   bool out_is_bf16, float* x_copy, int64_t rows, int d, cudaStream_t stream);
+                   int out_dt, float* x_copy, int64_t rows, int d, cudaStream_t stream);
 // dx_acc[r,:] += LN'(dy[r,:]; x[r,:], gamma)  (mean/rstd recomputed from x);  dx_cast (optional, activation
 // type) receives the updated dx_acc row cast to the activation type.
 void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast,
-                   bool cast_is_bf16, int64_t rows, int d, cudaStream_t stream);
+                   int cast_dt, int64_t rows, int d, cudaStream_t stream);
 // out[r,:] = x[r,:] / ||x[r,:]||_2 ; inv_norm[r] (optional) = 1/||x||
 void l2norm_fwd(const float* x, float* out, float* inv_norm, int64_t rows, int d, cudaStream_t stream);
 // dx = (g - xhat * <xhat, g>) * inv_norm ; optional cast copy in the activation type
-void l2norm_bwd(const float* g, const float* xhat, const float* inv_norm, float* dx, void* dx_cast, bool cast_is_bf16,
+void l2norm_bwd(const float* g, const float* xhat, const float* inv_norm, float* dx, void* dx_cast, int cast_dt,
                 int64_t rows, int d, cudaStream_t stream);
 
 // ---- attention.cu ----------------------------------------------------------------------------------
@@ -31,17 +31,18 @@ struct AttnProbe {
     int64_t seq_stride = 0;
 };
 // qkv [S*N, 3*H*64] (packed in_proj output, activation type) -> out [S*N, H*64]; softmax(QK^T/8)V, no mask.
-// bf16: mma.sync tensor-core flash kernel; fp32: SIMT kernel.  Probabilities asked for by `probe` are
+// bf16 / fp16: mma.sync tensor-core flash kernel; fp32: SIMT kernel.  Probabilities asked for by `probe` are
 // emitted from the softmax registers; the N x N map is never written.
-void attention_fwd(const void* qkv, void* out, bool is_bf16, int S, int N, int H, const AttnProbe& probe,
+void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe,
                    cudaStream_t stream);
 // dqkv [S*N, 3*H*64] from d_out [S*N, H*64] and the saved qkv (probabilities recomputed). N <= 128.
-void attention_bwd(const void* qkv, const void* d_out, void* dqkv, bool is_bf16, int S, int N, int H,
+// qkv may be fp16 (mixed mode) while gradients are bf16; fp32 mode: everything fp32.
+void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, int grad_dt, int S, int N, int H,
                    cudaStream_t stream);
 
 // ---- elementwise.cu --------------------------------------------------------------------------------
 // images [B,3,R,R] fp32 NCHW -> patches [B*g*g, kpad] (k = c*p*p + py*p + px, zero padded to kpad)
-void patchify(const float* images, void* out, bool out_is_bf16, int B, int R, int p, int kpad, cudaStream_t stream);
+void patchify(const float* images, void* out, int out_dt, int B, int R, int p, int kpad, cudaStream_t stream);
 // x[b,0,:] = cls + pos[0];  x[b,1+i,:] = patch_out[b*g2+i,:] + pos[1+i]
 void assemble_tokens(const float* patch_out, const float* cls, const float* pos, float* x, int B, int n_tokens, int d,
                      cudaStream_t stream);
@@ -54,14 +55,14 @@ void splice_bwd(const float* dx, const float* attr, int attr_p, float* dctx, int
 // raw[c,p] = mean_h probe[c,h,p];  attr[c,:] = softmax_p(raw[c,:])      (K3)
 void attribution_reduce(const float* probe, float* raw, float* attr, int C, int H, int P, cudaStream_t stream);
 // out[r,:] = cast(x[(r*row_stride + row_offset),:])
-void gather_rows(const float* x, void* out, bool out_is_bf16, int64_t rows, int64_t row_stride, int64_t row_offset, int d,
+void gather_rows(const float* x, void* out, int out_dt, int64_t rows, int64_t row_stride, int64_t row_offset, int d,
                  cudaStream_t stream);
 // dst[(r*row_stride+row_offset),:] = src[r,:] (dst fp32 pre-zeroed) + optional cast copy into dst_cast
-void scatter_rows(const float* src, float* dst, void* dst_cast, bool cast_is_bf16, int64_t rows, int64_t row_stride,
+void scatter_rows(const float* src, float* dst, void* dst_cast, int cast_dt, int64_t rows, int64_t row_stride,
                   int64_t row_offset, int d, cudaStream_t stream);
-void cast_f32(const float* src, void* dst, bool dst_is_bf16, int64_t n, cudaStream_t stream);
+void cast_f32(const float* src, void* dst, int dst_dt, int64_t n, cudaStream_t stream);
 // dh = dh * act'(h_pre)   (activation type, in place)
-void act_bwd_inplace(void* dh, const void* h_pre, bool is_bf16, int act, int64_t n, cudaStream_t stream);
+void act_bwd_inplace(void* dh, int dh_dt, const void* h_pre, int h_dt, int act, int64_t n, cudaStream_t stream);
 // logits[b,c] = exp(*logit_scale) * <img[b,:], txt[c,:]>
 void cosine_logits(const float* img, const float* txt, const float* logit_scale, float* logits, int B, int C, int E,
                    cudaStream_t stream);

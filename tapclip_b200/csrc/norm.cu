@@ -18,6 +18,12 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
     u.y = pack_bf16x2(v.z, v.w);
     *reinterpret_cast<uint2*>(p) = u;
 }
+template <> __device__ __forceinline__ void store4<f16>(f16* p, float4 v) {
+    uint2 u;
+    u.x = pack_f16x2(v.x, v.y);
+    u.y = pack_f16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -170,22 +176,24 @@ void check_d(int d) { TC_CHECK(d % 128 == 0 && d >= 128 && d <= 128 * MAXV, "row
 
 }  // namespace
 
-void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out, bool out_is_bf16,
+void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out, int out_dt,
                    float* x_copy, int64_t rows, int d, cudaStream_t stream) {
     check_d(d);
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (out_is_bf16) layernorm_fwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (bf16*)out, x_copy, rows, d);
+    if (out_dt == DT_BF16) layernorm_fwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (bf16*)out, x_copy, rows, d);
+    else if (out_dt == DT_F16) layernorm_fwd_kernel<f16><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (f16*)out, x_copy, rows, d);
     else layernorm_fwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (float*)out, x_copy, rows, d);
     TC_LAUNCH_CHECK();
 }
 
-void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast, bool cast_is_bf16,
+void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast, int cast_dt,
                    int64_t rows, int d, cudaStream_t stream) {
     check_d(d);
+    TC_CHECK(cast_dt != DT_F16, "gradients are never fp16");
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (cast_is_bf16) layernorm_bwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d);
+    if (cast_dt == DT_BF16) layernorm_bwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d);
     else layernorm_bwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(dy, x, gamma, dx_acc, (float*)dx_cast, rows, d);
     TC_LAUNCH_CHECK();
 }
@@ -197,12 +205,13 @@ void l2norm_fwd(const float* x, float* out, float* inv_norm, int64_t rows, int d
     TC_LAUNCH_CHECK();
 }
 
-void l2norm_bwd(const float* g, const float* xhat, const float* inv_norm, float* dx, void* dx_cast, bool cast_is_bf16,
+void l2norm_bwd(const float* g, const float* xhat, const float* inv_norm, float* dx, void* dx_cast, int cast_dt,
                 int64_t rows, int d, cudaStream_t stream) {
     check_d(d);
+    TC_CHECK(cast_dt != DT_F16, "gradients are never fp16");
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (cast_is_bf16) l2norm_bwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(g, xhat, inv_norm, dx, (bf16*)dx_cast, rows, d);
+    if (cast_dt == DT_BF16) l2norm_bwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(g, xhat, inv_norm, dx, (bf16*)dx_cast, rows, d);
     else l2norm_bwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(g, xhat, inv_norm, dx, (float*)dx_cast, rows, d);
     TC_LAUNCH_CHECK();
 }

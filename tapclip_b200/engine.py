@@ -15,11 +15,11 @@ def _check_cuda_f32(t: torch.Tensor, name: str):
 
 
 class Engine:
-    """One engine per device.  ``dtype``: 'bf16' (tcgen05 tensor-core path) or 'fp32' (SIMT parity mode)."""
+    """One engine per device.  ``dtype``: 'mixed' | 'bf16' (tcgen05 tensor-core paths) or 'fp32' (SIMT parity mode)."""
 
-    def __init__(self, cfg: ModelConfig, dtype: str = "bf16", device="cuda"):
-        if dtype not in _lib.DTYPE:
-            raise ValueError(f"dtype must be one of {sorted(_lib.DTYPE)}, got {dtype!r}")
+    def __init__(self, cfg: ModelConfig, dtype: str = "mixed", device="cuda"):
+        if dtype not in ("fp32", "bf16", "mixed"):
+            raise ValueError(f"dtype must be 'mixed', 'bf16' or 'fp32', got {dtype!r}")
         if not torch.cuda.is_available():
             raise _lib.TapclipError("tapclip_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.lib = _lib.load()

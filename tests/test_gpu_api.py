@@ -8,7 +8,7 @@ from oracle.tapclip_oracle import class_names, synthetic_images, synthetic_label
 pytestmark = pytest.mark.gpu
 
 
-def _mini(mode="intended", dtype="fp32", C=5, P=4):
+def _mini(mode="intended", dtype="fp32", C=5, P=4):   # fp32 parity mode: the API tests compare against the oracle tightly
     ow, om = build_oracle("mini-16", C, P, mode)
     clip, model = build_cuda("mini-16", C, P, mode, dtype, ow)
     return ow, om, clip, model

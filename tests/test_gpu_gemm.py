@@ -10,9 +10,8 @@ def _gemm(a, w, bias, dtype, epi, act=-1, block_n=0, out_init=None, want_pre=Fal
     lib = _lib.load()
     M, K = a.shape
     N = w.shape[0]
-    bf = dtype == "bf16"
     if epi == _lib.EPI_ACT:
-        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16 if bf else torch.float32)
+        out = torch.empty(M, N, device="cuda", dtype={"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[dtype])
     else:
         out = out_init.clone() if out_init is not None else torch.empty(M, N, device="cuda", dtype=torch.float32)
     pre = torch.empty_like(out) if want_pre else None
@@ -79,6 +78,27 @@ def test_gemm_tc_bf16_out_act(M, N, K, act):
     assert (out.float() - ref).abs().max().item() < tol
     if pre is not None:
         assert (pre.float() - z).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("act", [-1, 1])
+@pytest.mark.parametrize("M,N,K", [(93 * 65, 2048, 512), (93 * 65, 512, 2048), (65, 512, 512), (130, 256, 64)])
+def test_gemm_tc_fp16_operands(M, N, K, act):
+    """Mixed mode: text-tower forward GEMMs take fp16 operands (same tcgen05 kind::f16 instruction, a/b format = F16)."""
+    from tapclip_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(9)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    z = a.float() @ w.float().t() + bias
+    out, _ = _gemm(a, w, bias, "fp16", _lib.EPI_F32)
+    assert (out - z).abs().max().item() < 2e-3
+    x = torch.randn(M, N, device="cuda", generator=g)
+    out, _ = _gemm(a, w, bias, "fp16", _lib.EPI_F32_ADD, out_init=x)
+    assert (out - (x + z)).abs().max().item() < 2e-3
+    out, pre = _gemm(a, w, bias, "fp16", _lib.EPI_ACT, act=act, want_pre=(act >= 0))
+    assert out.dtype == torch.float16 and (out.float() - _ref_act(z, act)).abs().max().item() < 4e-3
+    if pre is not None:
+        assert (pre.float() - z).abs().max().item() < 4e-3
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 384, 128), (1576, 768, 768), (65, 512, 512), (77, 100, 36)])
