@@ -192,8 +192,6 @@ def run_ours(args, wl):
     host_labels = [torch.randint(0, C, (B,), generator=g).pin_memory() for _ in range(n_ring)]
     dev_images = [t.to(dev) for t in host_images]
     dev_labels = [t.to(dev) for t in host_labels]
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-    logit_host = torch.zeros(B, C, dtype=torch.float32).pin_memory()
 
     def step(images, labels):
         if train:
@@ -227,12 +225,46 @@ def run_ours(args, wl):
     def resident(i):
         step(dev_images[i % n_ring], dev_labels[i % n_ring])
 
+    # End-to-end: every step moves its own inputs host->device (pinned memory) and its result device->host.
+    # As in a DataLoader(pin_memory=True) + non_blocking loop, the copy of batch i+1 is issued on a copy stream while
+    # step i computes; the step's result is copied to pinned memory asynchronously and consumed one step later.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{"im": torch.empty_like(dev_images[0]), "lb": torch.empty_like(dev_labels[0]), "ready": torch.cuda.Event(),
+              "free": torch.cuda.Event()} for _ in range(2)]
+    res_host = [(torch.zeros((), dtype=torch.float32) if train else torch.zeros(B, C, dtype=torch.float32)).pin_memory() for _ in range(2)]
+    res_done = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"primed": -1, "checksum": 0.0}
+
+    def prefetch(i):
+        s = slots[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(s["free"])
+            s["im"].copy_(host_images[i % n_ring], non_blocking=True)
+            s["lb"].copy_(host_labels[i % n_ring], non_blocking=True)
+            s["ready"].record(copy_stream)
+        e2e_state["primed"] = i
+
     def end_to_end(i):
-        im = host_images[i % n_ring].to(dev, non_blocking=True)
-        lb = host_labels[i % n_ring].to(dev, non_blocking=True)
-        res = step(im, lb)
-        (loss_host if train else logit_host).copy_(res.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if e2e_state["primed"] < i:
+            prefetch(i)
+        prefetch(i + 1)
+        s = slots[i % 2]
+        main = torch.cuda.current_stream()
+        main.wait_event(s["ready"])
+        res = step(s["im"], s["lb"])
+        s["free"].record(main)
+        res_host[i % 2].copy_(res.detach(), non_blocking=True)
+        res_done[i % 2].record(main)
+        if i > 0:
+            res_done[(i - 1) % 2].synchronize()                       # consume the previous step's result on the host
+            e2e_state["checksum"] += float(res_host[(i - 1) % 2].sum())
+
+    def e2e_flush(n):
+        res_done[(n - 1) % 2].synchronize()
+        e2e_state["checksum"] += float(res_host[(n - 1) % 2].sum())
+        e2e_state["primed"] = -1
+        for s in slots:
+            s["free"] = torch.cuda.Event()
 
     for i in range(args.warmup):
         resident(i)
@@ -242,16 +274,25 @@ def run_ours(args, wl):
     n0 = clip.engine.launch_count
     ms_resident = timed(args.steps, resident)
     launches = clip.engine.launch_count - n0
-    for i in range(min(args.warmup, 2)):
+    for i in range(3):
         end_to_end(i)
-    ms_e2e = timed(args.steps, end_to_end)
+    e2e_flush(3)
+
+    def e2e_loop(i):
+        end_to_end(i)
+        if i == args.steps - 1:
+            e2e_flush(args.steps)
+    ms_e2e = timed(args.steps, e2e_loop)
     clocks = sampler.stop() if rank == 0 else None
 
-    # per-launch CUDA-event timing of the tensor-core kernels over the same K steps (roofline numbers)
+    # per-launch CUDA-event timing of the tensor-core kernels over the same K steps (roofline numbers); the towers run
+    # back to back on one stream here so that each kernel's events time that kernel alone
+    model.overlap_towers = False
     clip.engine.profile(True)
-    timed(args.steps, resident)
+    ms_serial = timed(args.steps, resident)
     clip.engine.profile(False)
     prof = clip.engine.profile_report()
+    model.overlap_towers = True
 
     if rank != 0:
         if world > 1:
@@ -288,7 +329,8 @@ def run_ours(args, wl):
             "frac": (gemm_tflops / peaks["bf16_sustained"]) if gemm_tflops else None, "traffic": None,
             "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
             "gemm_launches_per_step": gemm["launches"] / args.steps, "gemm_ms_per_step": gemm["ms"] / args.steps,
-            "gemm_share_of_step": gemm["ms"] / ms_resident if ms_resident else None,
+            "gemm_share_of_step": gemm["ms"] / ms_serial if ms_serial else None,
+            "ms_per_step_single_stream_profiled": ms_serial / args.steps,
             "attention_fwd_ms_per_step": prof.get("attention_fwd", {}).get("ms", 0.0) / args.steps,
             "attention_bwd_ms_per_step": prof.get("attention_bwd", {}).get("ms", 0.0) / args.steps,
             "step_algorithmic_tflop_per_gpu": flops_step / 1e12,

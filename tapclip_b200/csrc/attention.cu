@@ -71,7 +71,8 @@ attn_fwd_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H
 #pragma unroll
     for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
     float ps0 = 0.f, ps1 = 0.f;             // probed (scaled, log2-domain) score of key N-1 for rows g / g+8
-    const bool cls_probe = (probe_mode == PROBE_CLS_ROW) && r0 == 0 && g == 0;
+    const bool cls_any = (probe_mode == PROBE_CLS_ROW) && r0 == 0;            // warp-uniform
+    const bool cls_probe = cls_any && g == 0;
     float* cls_out = probe_out ? probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N : nullptr;
 
     for (int kc = 0; kc < npad; kc += KC) {
@@ -90,17 +91,27 @@ attn_fwd_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H
             }
         }
         float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (kc + KC < N && !cls_any) {
+            // interior chunk (warp-uniform): no masking, no probe bookkeeping
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) {
+            for (int nb = 0; nb < 4; ++nb) {
+                sc[nb][0] *= scale_log2; sc[nb][1] *= scale_log2; sc[nb][2] *= scale_log2; sc[nb][3] *= scale_log2;
+                mx0 = fmaxf(mx0, fmaxf(sc[nb][0], sc[nb][1]));
+                mx1 = fmaxf(mx1, fmaxf(sc[nb][2], sc[nb][3]));
+            }
+        } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int key = kc + nb * 8 + tq * 2 + e;
-                float v0 = sc[nb][e] * scale_log2, v1 = sc[nb][e + 2] * scale_log2;
-                if (key >= N) { v0 = -INFINITY; v1 = -INFINITY; }
-                if (key == N - 1) { ps0 = v0; ps1 = v1; }
-                if (cls_probe && key < N) cls_out[key] = v0;
-                sc[nb][e] = v0; sc[nb][e + 2] = v1;
-                mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+            for (int nb = 0; nb < 4; ++nb) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int key = kc + nb * 8 + tq * 2 + e;
+                    float v0 = sc[nb][e] * scale_log2, v1 = sc[nb][e + 2] * scale_log2;
+                    if (key >= N) { v0 = -INFINITY; v1 = -INFINITY; }
+                    if (key == N - 1) { ps0 = v0; ps1 = v1; }
+                    if (cls_probe && key < N) cls_out[key] = v0;
+                    sc[nb][e] = v0; sc[nb][e + 2] = v1;
+                    mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+                }
             }
         }
         mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));

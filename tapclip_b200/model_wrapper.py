@@ -38,8 +38,22 @@ class _TapClipFunction(torch.autograd.Function):
         n_cls, P = pl.n_cls, pl.prompt_len
         lo, hi = shard.bounds(n_cls)
 
-        img_feat = eng.encode_image(images)                                       # row A4
-        text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad)   # rows A6-A10 on this rank's classes
+        # The two towers are independent until the logit contraction: the (small, launch-bound) text passes run on a
+        # side stream and fill the image tower's kernel tails; joined before the logits.
+        side = model._side_stream(images.device)
+        if side is not None:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad)   # rows A6-A10, this rank's classes
+            img_feat = eng.encode_image(images)                                   # row A4
+            main.wait_stream(side)
+            for t in (text_local, attr_local, raw_local):
+                if t is not None:
+                    t.record_stream(main)
+        else:
+            img_feat = eng.encode_image(images)
+            text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad)
         text_feat = all_gather_rows(text_local, shard, n_cls)                     # [C, E]
         if labels is not None:
             b_total = shard.global_batch(images.shape[0])
@@ -89,7 +103,8 @@ class FullModel(nn.Module):
     """models/model_wrapper.py:12-100."""
 
     def __init__(self, class_names, clip_wrapper, prompt_len=5, attr_lambda=1.0, stab_lambda=0.1,
-                 adjustor_method="scale", class_specific=False, *, distributed=None, cache_text_features=True):
+                 adjustor_method="scale", class_specific=False, *, distributed=None, cache_text_features=True,
+                 overlap_towers=True):
         super().__init__()
         self.clip = clip_wrapper
         self.class_names = class_names
@@ -106,10 +121,20 @@ class FullModel(nn.Module):
         self.cache_text_features = cache_text_features
         self._text_cache = None
         self.last_attribution = None
+        self.overlap_towers = overlap_towers
+        self._side = None
 
     @property
     def prompt_len(self):
         return self.prompt_learner.prompt_len
+
+    def _side_stream(self, device):
+        """Side stream for the text tower (None = run both towers on the caller's stream)."""
+        if not self.overlap_towers or device.type != "cuda":
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
 
     def _sharding(self) -> ClassSharding:
         return ClassSharding.current(self.distributed)
