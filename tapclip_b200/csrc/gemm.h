@@ -21,7 +21,7 @@ struct GemmArgs {
     int64_t lda = 0, ldw = 0, ldo = 0;
     int epi = EPI_F32;
     int act = ACT_NONE;
-    int block_n = 0;           // 0 = choose; 128 or 256 force a tile width (tcgen05 path only)
+    int block_n = 0;           // 0 = choose; 128 / 256 = 128 x block_n single-CTA tiles; 512 = 2-CTA pairs, 256 x 256 tiles
     int dt = DT_BF16;          // tcgen05 path: 16-bit type of A, W and of the EPI_BF16 output (DT_BF16 or DT_F16)
 };
 

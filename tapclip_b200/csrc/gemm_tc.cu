@@ -4,14 +4,23 @@
 // reference's third-party model (SURVEY.md 2.3 rows k2,k5,k8,k10 + patch-embed + the two projections).
 //
 // Structure (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer: 128B-swizzled A (128x64) and W (BLOCK_N x 64) tiles into a 4-stage smem ring
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, fp32 accumulate)
-//   warps 2..5  epilogue: tcgen05.ld TMEM -> registers -> bias / activation -> swizzled smem -> TMA store
-//               (or TMA reduce-add for the fp32 residual stream)
+//   warp 0      TMA producer: 128B-swizzled A (128x64) and W tiles into a 4..6-stage smem ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulate in TMEM)
+//   warps 2..5  epilogue: tcgen05.ld TMEM -> registers -> bias / activation -> swizzled smem transpose -> coalesced
+//               16-byte global stores (red.global.add.v4.f32 for the fp32 residual stream)
 // Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  M/N/K tails are handled by TMA zero-fill on loads and clipping on stores.
+//
+// Two tile shapes:
+//   CTA2 = false  cta_group::1, UMMA 128 x BLOCK_N x 16, one CTA per tile (48 KB of operands per k-block).
+//   CTA2 = true   cta_group::2, UMMA 256 x BLOCK_N x 16 issued by the leader of a 2-CTA cluster: each CTA holds its
+//                 own 128 rows of A and HALF of the W tile (32 KB per k-block -> 1.5x fewer L2->SM bytes per flop,
+//                 6 stages in flight).  The mainloop of the 1-CTA shape is L2-feed-bound (ncu: 64-73 % tensor pipe).
 #include "gemm.h"
 #include <type_traits>
+#include <cstdlib>
+#include <map>
+#include <tuple>
 
 namespace tapclip {
 
@@ -25,12 +34,13 @@ constexpr int STAGE_A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int EPI_BUF_BYTES = 32 * 128;             // 32 rows x 128 B, one TMA-store box
 constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES;    // 4 warps x 2 buffers
 
-template <int BLOCK_N> struct Cfg {
-    static constexpr int STAGE_B_BYTES = BLOCK_N * BLOCK_K * 2;
+template <int BLOCK_N, bool CTA2> struct Cfg {
+    static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;          // rows of W this CTA stages per k-block
+    static constexpr int STAGE_B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;            // 4 (48 KB), 6 (32 KB), 8 (24 KB)
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/ + 1024 /*align slack*/;
 };
 
 // UMMA shared-memory descriptor: K-major operand, 128B swizzle, 8-row groups 1024 B apart
@@ -44,18 +54,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 // UMMA instruction descriptor: (bf16|fp16) x same -> fp32, both operands K-major, M=128, N=BLOCK_N
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool f16) {
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool f16) {
     const uint32_t fmt = f16 ? 0u : 1u;             // F16F32Format: 0 = F16, 1 = BF16
     return (1u << 4) /*C=f32*/ | (fmt << 7) /*A*/ | (fmt << 10) /*B*/ | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(BLOCK_M >> 4) << 24);
+           ((uint32_t)(m >> 4) << 24);
 }
 
-template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16>
+template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2,
-               const float* __restrict__ bias, int M, int N, int K) {
-    using C = Cfg<BLOCK_N>;
+               void* __restrict__ out, void* __restrict__ out_pre, int ldo,
+               const float* __restrict__ bias, int M, int N, int K, int dbg) {
+    using C = Cfg<BLOCK_N, CTA2>;
     using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -68,25 +78,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* tmem_full = bars + 2 * C::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* bias_s = reinterpret_cast<float*>(smem_epi + EPI_BYTES + 256);      // bias of the current tile, shared by the 4 epilogue warps
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+    // work decomposition: a "unit" is one CTA (CTA2 = false) or one 2-CTA cluster owning 256 rows (CTA2 = true)
+    constexpr int UNIT_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+    const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int num_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int m_tiles = (M + UNIT_M - 1) / UNIT_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        tma_prefetch_desc(&tmap_c);
-        if (STORE_PRE) tma_prefetch_desc(&tmap_c2);
         for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 8 : 4); }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
-    if (warp == 1) tmem_alloc(tmem_base_slot, C::TMEM_COLS);
+    if (warp == 1) {
+        if constexpr (CTA2) tmem_alloc_2sm(tmem_base_slot, C::TMEM_COLS);
+        else tmem_alloc(tmem_base_slot, C::TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();        // the peer's barriers must be initialised before any remote arrive
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -94,24 +112,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ================================ TMA producer ================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                const int m0 = (tile / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M;
+                const int n0 = (tile % n_tiles) * BLOCK_N + (int)cta_rank * (CTA2 ? C::B_ROWS : 0);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-                    tma_load_2d(smem_a + stage * STAGE_A_BYTES, &tmap_a, kb * BLOCK_K, m0, &full_bar[stage]);
-                    tma_load_2d(smem_b + stage * C::STAGE_B_BYTES, &tmap_b, kb * BLOCK_K, n0, &full_bar[stage]);
+                    if constexpr (CTA2) {
+                        // both CTAs' loads complete on the LEADER's full barrier, which expects the pair's bytes
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                        const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+                        tma_load_2d_2sm(smem_a + stage * STAGE_A_BYTES, &tmap_a, kb * BLOCK_K, m0, fb);
+                        tma_load_2d_2sm(smem_b + stage * C::STAGE_B_BYTES, &tmap_b, kb * BLOCK_K, n0, fb);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        tma_load_2d(smem_a + stage * STAGE_A_BYTES, &tmap_a, kb * BLOCK_K, m0, &full_bar[stage]);
+                        tma_load_2d(smem_b + stage * C::STAGE_B_BYTES, &tmap_b, kb * BLOCK_K, n0, &full_bar[stage]);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BLOCK_N, F16);
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc(UNIT_M, BLOCK_N, F16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -123,159 +150,145 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 32 B (= 16 bf16) inside the 128B swizzle row: +2 in the >>4 address field
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (CTA2) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);          // frees this smem stage once the MMAs retire
+                    // frees this smem stage (in both CTAs of a pair) once the MMAs retire
+                    if constexpr (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);                // accumulator ready for the epilogue
+                // accumulator ready for the epilogue warps (of both CTAs)
+                if constexpr (CTA2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
         // ================================ epilogue warps ==============================
+        // TMEM -> registers (one accumulator row per thread) -> bias/activation -> XOR-swizzled smem transpose ->
+        // coalesced 16-byte global stores (each store instruction covers 4 rows x 128 B).  Stores are fire-and-forget:
+        // nothing in this loop waits on the memory system except the tcgen05.ld itself.
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int ew = warp - 2;
-        uint8_t* stage_buf = smem_epi + ew * 2 * EPI_BUF_BYTES;
+        const uint32_t stage_u32 = smem_u32(smem_epi + ew * 2 * EPI_BUF_BYTES);
         const uint32_t row_off = (uint32_t)lane * 128u;
         const uint32_t sw = (uint32_t)(lane & 7);
+        const int rd_row = lane >> 3, rd_ch = lane & 7;      // read-back mapping: 8 lanes cover one 128-byte row
         int acc = 0; uint32_t acc_phase = 0;
         int buf = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
+            const int m0 = (tile / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            if (bias != nullptr) {
+                // stage this tile's bias in smem while the MMAs of the tile are still running (a global load per
+                // chunk inside the epilogue loop exposed its full latency: ncu long_scoreboard on the bias FADDs)
+                asm volatile("bar.sync 1, 128;" ::: "memory");               // everyone is done with the previous tile's bias
+                const int et = (int)threadIdx.x - 64;
+                if (et < BLOCK_N / 4) {
+                    const int col = n0 + et * 4;
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (col < N) b = __ldg(reinterpret_cast<const float4*>(bias + col));
+                    *reinterpret_cast<float4*>(bias_s + et * 4) = b;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
             const int row0 = m0 + q * 32;
-
-            if constexpr (EPI == EPI_BF16) {
-                constexpr int CH = 64;                       // 64 bf16 columns = 128 B per row per store box
+            constexpr int CH = (EPI == EPI_BF16) ? 64 : 32;  // columns per 128-byte staging row
+            constexpr int OUT_ESZ = (EPI == EPI_BF16) ? 2 : 4;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N / CH; ++c) {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld_32x32(taddr + c * CH, r0);
-                    tmem_ld_32x32(taddr + c * CH + 32, r1);
-                    tmem_ld_wait();
-                    if (c == BLOCK_N / CH - 1) {             // all TMEM reads of this tile are done
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                    }
-                    const int col0 = n0 + c * CH;
-                    float v[64];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
-                    if (bias != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 64; j += 4) {
-                            if (col0 + j < N) {
-                                float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                            }
-                        }
-                    }
-                    if (row0 < M && col0 < N) {
-                        if constexpr (STORE_PRE) {
-                            // both staging buffers per chunk: [0] pre-activation, [1] activated
-                            if (lane == 0) tma_store_wait_read<0>();
-                            __syncwarp();
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                uint4 p;
-                                p.x = pack2<T16>(v[8 * j + 0], v[8 * j + 1]); p.y = pack2<T16>(v[8 * j + 2], v[8 * j + 3]);
-                                p.z = pack2<T16>(v[8 * j + 4], v[8 * j + 5]); p.w = pack2<T16>(v[8 * j + 6], v[8 * j + 7]);
-                                *reinterpret_cast<uint4*>(stage_buf + row_off + (((uint32_t)j ^ sw) << 4)) = p;
-                            }
-#pragma unroll
-                            for (int j = 0; j < 64; ++j) v[j] = act_fwd_fast<ACT>(v[j]);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                uint4 p;
-                                p.x = pack2<T16>(v[8 * j + 0], v[8 * j + 1]); p.y = pack2<T16>(v[8 * j + 2], v[8 * j + 3]);
-                                p.z = pack2<T16>(v[8 * j + 4], v[8 * j + 5]); p.w = pack2<T16>(v[8 * j + 6], v[8 * j + 7]);
-                                *reinterpret_cast<uint4*>(stage_buf + EPI_BUF_BYTES + row_off + (((uint32_t)j ^ sw) << 4)) = p;
-                            }
-                            fence_proxy_async_smem();
-                            __syncwarp();
-                            if (lane == 0) {
-                                tma_store_2d(&tmap_c2, stage_buf, col0, row0);
-                                tma_store_2d(&tmap_c, stage_buf + EPI_BUF_BYTES, col0, row0);
-                                tma_store_commit();
-                            }
-                        } else {
-                            if (lane == 0) tma_store_wait_read<1>();     // buffer used two chunks ago is free
-                            __syncwarp();
-                            uint8_t* sb = stage_buf + buf * EPI_BUF_BYTES;
-#pragma unroll
-                            for (int j = 0; j < 64; ++j) v[j] = act_fwd_fast<ACT>(v[j]);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                uint4 p;
-                                p.x = pack2<T16>(v[8 * j + 0], v[8 * j + 1]); p.y = pack2<T16>(v[8 * j + 2], v[8 * j + 3]);
-                                p.z = pack2<T16>(v[8 * j + 4], v[8 * j + 5]); p.w = pack2<T16>(v[8 * j + 6], v[8 * j + 7]);
-                                *reinterpret_cast<uint4*>(sb + row_off + (((uint32_t)j ^ sw) << 4)) = p;
-                            }
-                            fence_proxy_async_smem();
-                            __syncwarp();
-                            if (lane == 0) { tma_store_2d(&tmap_c, sb, col0, row0); tma_store_commit(); }
-                            buf ^= 1;
-                        }
-                    }
-                }
-            } else {
-                constexpr int CH = 32;                       // 32 fp32 columns = 128 B per row per store box
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N / CH; ++c) {
+            for (int c = 0; c < BLOCK_N / CH; ++c) {
+                float v[CH];
+                {
                     uint32_t r0[32];
                     tmem_ld_32x32(taddr + c * CH, r0);
-                    tmem_ld_wait();
-                    if (c == BLOCK_N / CH - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    if constexpr (CH == 64) {
+                        uint32_t r1[32];
+                        tmem_ld_32x32(taddr + c * CH + 32, r1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+                    } else {
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
                     }
-                    const int col0 = n0 + c * CH;
-                    float v[32];
+                }
+                if (c == BLOCK_N / CH - 1) {                 // all TMEM reads of this tile are done
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0)); else mbar_arrive(&tmem_empty[acc]); }
+                }
+                const int col0 = n0 + c * CH;
+                if (bias != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-                    if (bias != nullptr) {
+                    for (int j = 0; j < CH; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c * CH + j);   // smem broadcast
+                        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                    }
+                }
+                if (row0 >= M || col0 >= N || dbg == 2) continue;
+                constexpr int NPASS = (EPI == EPI_BF16 && STORE_PRE) ? 2 : 1;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (col0 + j < N) {
-                                float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-                                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                for (int pass = 0; pass < NPASS; ++pass) {
+                    const bool is_pre = STORE_PRE && pass == 0;       // first pass of STORE_PRE writes the pre-activation copy
+                    if (!is_pre) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) v[j] = act_fwd_fast<ACT>(v[j]);
+                    }
+                    const uint32_t sb = stage_u32 + buf * EPI_BUF_BYTES;
+                    buf ^= 1;
+                    // registers -> swizzled staging (conflict-free 16-byte shared stores)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t p0, p1, p2, p3;
+                        if constexpr (EPI == EPI_BF16) {
+                            p0 = pack2<T16>(v[8 * j + 0], v[8 * j + 1]); p1 = pack2<T16>(v[8 * j + 2], v[8 * j + 3]);
+                            p2 = pack2<T16>(v[8 * j + 4], v[8 * j + 5]); p3 = pack2<T16>(v[8 * j + 6], v[8 * j + 7]);
+                        } else {
+                            p0 = __float_as_uint(v[4 * j]); p1 = __float_as_uint(v[4 * j + 1]);
+                            p2 = __float_as_uint(v[4 * j + 2]); p3 = __float_as_uint(v[4 * j + 3]);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + row_off + (((uint32_t)j ^ sw) << 4)),
+                                     "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+                    }
+                    __syncwarp();
+                    // staging -> global: lane (rd_row, rd_ch) moves 16 bytes; 8 lanes = one full 128-byte row segment
+                    uint8_t* gbase = reinterpret_cast<uint8_t*>(is_pre ? out_pre : out);
+                    const int gcol = col0 + rd_ch * (16 / OUT_ESZ);
+                    if (dbg != 1) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + rd_row;
+                            uint32_t x0, x1, x2, x3;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                                         : "r"(sb + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
+                            if (row0 + r < M && gcol < N) {
+                                uint8_t* gp = gbase + ((int64_t)(row0 + r) * ldo + gcol) * OUT_ESZ;
+                                if constexpr (EPI == EPI_F32_ADD) {
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "f"(__uint_as_float(x0)),
+                                                 "f"(__uint_as_float(x1)), "f"(__uint_as_float(x2)), "f"(__uint_as_float(x3)) : "memory");
+                                } else {
+                                    *reinterpret_cast<uint4*>(gp) = make_uint4(x0, x1, x2, x3);
+                                }
                             }
                         }
                     }
-                    if (row0 < M && col0 < N) {
-                        if (lane == 0) tma_store_wait_read<1>();
-                        __syncwarp();
-                        uint8_t* sb = stage_buf + buf * EPI_BUF_BYTES;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 p = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            *reinterpret_cast<float4*>(sb + row_off + (((uint32_t)j ^ sw) << 4)) = p;
-                        }
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            if constexpr (EPI == EPI_F32_ADD) tma_reduce_add_2d(&tmap_c, sb, col0, row0);
-                            else tma_store_2d(&tmap_c, sb, col0, row0);
-                            tma_store_commit();
-                        }
-                        buf ^= 1;
-                    }
+                    // the other staging buffer is used next; this one is re-used two passes later, after a __syncwarp
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();        // neither CTA may exit (or free TMEM) while its peer can still reach it
+    else __syncthreads();
     tc_fence_after();
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (warp == 1) {
+        if constexpr (CTA2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+        else tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -298,8 +311,30 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols]; 128B swizzle
-CUtensorMap make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
-                      int box_rows, int box_cols) {
+CUtensorMap encode_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+                        int box_rows, int box_cols);
+
+// cuTensorMapEncodeTiled costs a few microseconds on the host; the engine's operands live in stable buffers, so the
+// encoded maps are cached by (pointer, geometry).  Single-threaded per handle/process by contract (include/tapclip.h).
+struct TmapKey {
+    const void* ptr; int dt; int64_t rows, cols, ld; int box_rows, box_cols;
+    bool operator<(const TmapKey& o) const {
+        return std::tie(ptr, dt, rows, cols, ld, box_rows, box_cols) < std::tie(o.ptr, o.dt, o.rows, o.cols, o.ld, o.box_rows, o.box_cols);
+    }
+};
+std::map<TmapKey, CUtensorMap> g_tmap_cache;
+
+const CUtensorMap& make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+                             int box_rows, int box_cols) {
+    const TmapKey key{ptr, (int)dt, rows, cols, ld, box_rows, box_cols};
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) return it->second;
+    if (g_tmap_cache.size() > 4096) g_tmap_cache.clear();
+    return g_tmap_cache.emplace(key, encode_tmap(ptr, dt, elem_bytes, rows, cols, ld, box_rows, box_cols)).first->second;
+}
+
+CUtensorMap encode_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+                        int box_rows, int box_cols) {
     TC_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned");
     TC_CHECK((ld * elem_bytes) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld=%lld)", (long long)ld);
     TC_CHECK(box_cols * elem_bytes == 128, "box inner extent must be 128 bytes");
@@ -316,11 +351,13 @@ CUtensorMap make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, i
 }
 
 int g_num_sms = 0;
+// TAPCLIP_GEMM_DEBUG (measurement only; results are WRONG when set): 1 = skip the epilogue's TMA stores, 2 = skip the epilogue body
+int g_debug = getenv("TAPCLIP_GEMM_DEBUG") ? atoi(getenv("TAPCLIP_GEMM_DEBUG")) : 0;
 
-template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16>
+template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16, bool CTA2>
 void launch(const GemmArgs& g, cudaStream_t stream) {
-    using C = Cfg<BLOCK_N>;
-    auto kern = gemm_tc_kernel<BLOCK_N, EPI, ACT, STORE_PRE, F16>;
+    using C = Cfg<BLOCK_N, CTA2>;
+    auto kern = gemm_tc_kernel<BLOCK_N, EPI, ACT, STORE_PRE, F16, CTA2>;
     constexpr CUtensorMapDataType DT16 = F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     static bool configured = false;
     if (!configured) {
@@ -332,30 +369,43 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
         TC_CUDA(cudaGetDevice(&dev));
         TC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    CUtensorMap ta = make_tmap(g.a, DT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K);
-    CUtensorMap tb = make_tmap(g.w, DT16, 2, g.N, g.K, g.ldw, BLOCK_N, BLOCK_K);
-    CUtensorMap tc, tc2;
-    if (EPI == EPI_BF16) tc = make_tmap(g.out, DT16, 2, g.M, g.N, g.ldo, 32, 64);
-    else tc = make_tmap(g.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldo, 32, 32);
-    tc2 = tc;
-    if (STORE_PRE) tc2 = make_tmap(g.out_pre, DT16, 2, g.M, g.N, g.ldo, 32, 64);
-    const int64_t tiles = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, BLOCK_N);
-    const int grid = (int)std::min<int64_t>(tiles, g_num_sms);
-    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, g.bias, (int)g.M, (int)g.N, (int)g.K);
+    const CUtensorMap& ta = make_tmap(g.a, DT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K);
+    const CUtensorMap& tb = make_tmap(g.w, DT16, 2, g.N, g.K, g.ldw, C::B_ROWS, BLOCK_K);
+    const int out_esz = (EPI == EPI_BF16) ? 2 : 4;
+    TC_CHECK((reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && (g.ldo * out_esz) % 16 == 0, "GEMM output must be 16-byte aligned with a 16-byte row pitch");
+    if (STORE_PRE) TC_CHECK((reinterpret_cast<uintptr_t>(g.out_pre) & 15) == 0, "GEMM pre-activation output must be 16-byte aligned");
+    if (CTA2) {
+        const int64_t tiles = ceil_div(g.M, 2 * BLOCK_M) * ceil_div(g.N, BLOCK_N);
+        const int clusters = (int)std::min<int64_t>(tiles, g_num_sms / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = C::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        TC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug));
+    } else {
+        const int64_t tiles = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, BLOCK_N);
+        const int grid = (int)std::min<int64_t>(tiles, g_num_sms);
+        kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug);
+    }
     TC_LAUNCH_CHECK();
 }
 
-template <int BLOCK_N, bool F16>
+template <int BLOCK_N, bool F16, bool CTA2>
 void dispatch(const GemmArgs& g, cudaStream_t stream) {
-    if (g.epi == EPI_F32) return launch<BLOCK_N, EPI_F32, ACT_NONE, false, F16>(g, stream);
-    if (g.epi == EPI_F32_ADD) return launch<BLOCK_N, EPI_F32_ADD, ACT_NONE, false, F16>(g, stream);
+    if (g.epi == EPI_F32) return launch<BLOCK_N, EPI_F32, ACT_NONE, false, F16, CTA2>(g, stream);
+    if (g.epi == EPI_F32_ADD) return launch<BLOCK_N, EPI_F32_ADD, ACT_NONE, false, F16, CTA2>(g, stream);
     TC_CHECK(g.epi == EPI_BF16, "unknown epilogue %d", g.epi);
     const bool pre = g.out_pre != nullptr;
-    if (g.act == ACT_NONE) { TC_CHECK(!pre, "out_pre needs an activation"); return launch<BLOCK_N, EPI_BF16, ACT_NONE, false, F16>(g, stream); }
-    if (g.act == ACT_GELU_ERF) return pre ? launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, true, F16>(g, stream)
-                                          : launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, false, F16>(g, stream);
-    if (g.act == ACT_QUICK_GELU) return pre ? launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, true, F16>(g, stream)
-                                            : launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, false, F16>(g, stream);
+    if (g.act == ACT_NONE) { TC_CHECK(!pre, "out_pre needs an activation"); return launch<BLOCK_N, EPI_BF16, ACT_NONE, false, F16, CTA2>(g, stream); }
+    if (g.act == ACT_GELU_ERF) return pre ? launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, true, F16, CTA2>(g, stream)
+                                          : launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, false, F16, CTA2>(g, stream);
+    if (g.act == ACT_QUICK_GELU) return pre ? launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, true, F16, CTA2>(g, stream)
+                                            : launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, false, F16, CTA2>(g, stream);
     TC_CHECK(false, "unknown activation %d", g.act);
 }
 
@@ -364,16 +414,19 @@ void dispatch(const GemmArgs& g, cudaStream_t stream) {
 void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     TC_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "empty GEMM %lldx%lldx%lld", (long long)g.M, (long long)g.N, (long long)g.K);
     TC_CHECK(g.K % 8 == 0 && g.N % 8 == 0, "tcgen05 GEMM needs K%%8==0 and N%%8==0 (K=%lld N=%lld)", (long long)g.K, (long long)g.N);
+    TC_CHECK(g.dt == DT_BF16 || g.dt == DT_F16, "tcgen05 GEMM operands must be bf16 or fp16");
+    // block_n: 0 = choose; 128 / 256 = one CTA per 128 x block_n tile; 512 = 2-CTA pairs on 256 x 256 tiles
     int bn = g.block_n;
     if (bn == 0) {
-        // wide tiles when they already fill the machine, narrow ones otherwise
-        if (g_num_sms == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
-        const int64_t tiles256 = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, 256);
-        bn = (g.N % 256 == 0 && tiles256 >= 2 * g_num_sms) ? 256 : 128;
+        // Measured (tools/gemm_bench.py, B200): 128x256 single-CTA tiles are within 3 % of the 2-CTA 256x256 tiles on the
+        // image-tower shapes (both ~0.95 of cuBLAS: the mainloop is not L2-feed-bound) and 10-15 % faster on the small
+        // text-tower shapes, where a 2-CTA pair halves the number of schedulable units.
+        bn = (g.N % 256 == 0) ? 256 : 128;
     }
-    TC_CHECK(g.dt == DT_BF16 || g.dt == DT_F16, "tcgen05 GEMM operands must be bf16 or fp16");
-    if (g.dt == DT_F16) { if (bn == 256) dispatch<256, true>(g, stream); else dispatch<128, true>(g, stream); }
-    else { if (bn == 256) dispatch<256, false>(g, stream); else dispatch<128, false>(g, stream); }
+    const bool f16 = g.dt == DT_F16;
+    if (bn == 512) { if (f16) dispatch<256, true, true>(g, stream); else dispatch<256, false, true>(g, stream); }
+    else if (bn == 256) { if (f16) dispatch<256, true, false>(g, stream); else dispatch<256, false, false>(g, stream); }
+    else { if (f16) dispatch<128, true, false>(g, stream); else dispatch<128, false, false>(g, stream); }
 }
 
 }  // namespace tapclip

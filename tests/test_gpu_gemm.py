@@ -37,7 +37,7 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
-@pytest.mark.parametrize("block_n", [0, 128, 256])
+@pytest.mark.parametrize("block_n", [0, 128, 256, 512])    # 512 = 2-CTA pairs (cta_group::2), 256x256 tiles
 def test_gemm_tc_f32_out(M, N, K, block_n):
     from tapclip_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
@@ -51,27 +51,29 @@ def test_gemm_tc_f32_out(M, N, K, block_n):
 
 
 @pytest.mark.parametrize("M,N,K", [(1576, 768, 768), (93 * 65, 512, 2048), (200, 256, 128)])
-def test_gemm_tc_residual_add(M, N, K):
+@pytest.mark.parametrize("block_n", [0, 256, 512])
+def test_gemm_tc_residual_add(M, N, K, block_n):
     from tapclip_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(11)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
     bias = torch.randn(N, device="cuda", generator=g)
     x = torch.randn(M, N, device="cuda", generator=g)
-    out, _ = _gemm(a, w, bias, "bf16", _lib.EPI_F32_ADD, out_init=x)
+    out, _ = _gemm(a, w, bias, "bf16", _lib.EPI_F32_ADD, out_init=x, block_n=block_n)
     ref = x + a.float() @ w.float().t() + bias
     assert (out - ref).abs().max().item() < 2e-3
 
 
 @pytest.mark.parametrize("act", [-1, 0, 1])
 @pytest.mark.parametrize("M,N,K", [(1576, 3072, 768), (93 * 65, 2048, 512), (130, 256, 64)])
-def test_gemm_tc_bf16_out_act(M, N, K, act):
+@pytest.mark.parametrize("block_n", [0, 256])
+def test_gemm_tc_bf16_out_act(M, N, K, act, block_n):
     from tapclip_b200 import _lib
     g = torch.Generator(device="cuda").manual_seed(5)
     a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
     bias = torch.randn(N, device="cuda", generator=g)
-    out, pre = _gemm(a, w, bias, "bf16", _lib.EPI_ACT, act=act, want_pre=(act >= 0))
+    out, pre = _gemm(a, w, bias, "bf16", _lib.EPI_ACT, act=act, want_pre=(act >= 0), block_n=block_n)
     z = a.float() @ w.float().t() + bias
     ref = _ref_act(z, act)
     tol = 2e-2                                            # one bf16 rounding of values up to ~4

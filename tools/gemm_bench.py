@@ -19,19 +19,36 @@ SHAPES = [  # (tag, M, N, K, epi, act)
 
 
 def bench(fn, reps):
+    """GPU time per launch from a CUDA-graph replay of `reps` back-to-back launches (no host launch cost inside)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3   # us
 
 
-print(f"{'shape':10s} {'M':>6s} {'N':>5s} {'K':>5s} epi |  bn=0 us  TF/s | bn=128 us TF/s | bn=256 us TF/s | cuBLAS us TF/s")
+def host_cost(fn, reps):
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    dt = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    return dt / reps * 1e6
+
+
+print(f"{'shape':10s} {'M':>6s} {'N':>5s} {'K':>5s} epi |  auto us  TF/s | bn=128 us TF/s | bn=256 us TF/s | 2cta256 us TF/s | cuBLAS us TF/s")
 for tag, M, N, K, epi, act in SHAPES:
     a = torch.randn(M, K, device="cuda").bfloat16()
     w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
@@ -39,12 +56,14 @@ for tag, M, N, K, epi, act in SHAPES:
     out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16 if epi == 0 else torch.float32)
     fl = 2.0 * M * N * K
     cols = []
-    for bn in (0, 128, 256):
+    for bn in (0, 128, 256, 512):
         def run():
             _lib.check(lib.tapclip_op_gemm(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), None, M, N, K, 1, epi, act, bn,
                                            _lib.stream_ptr()))
         us = bench(run, reps)
         cols.append(f"{us:8.1f} {fl / us / 1e6:6.0f}")
+        if bn == 0:
+            hc = host_cost(run, reps)
     us = bench(lambda: torch.matmul(a, w.t()), reps)
     cols.append(f"{us:8.1f} {fl / us / 1e6:6.0f}")
-    print(f"{tag:10s} {M:6d} {N:5d} {K:5d} {epi:3d} | " + " | ".join(cols))
+    print(f"{tag:10s} {M:6d} {N:5d} {K:5d} {epi:3d} | " + " | ".join(cols) + f" | host enqueue {hc:5.1f} us")

@@ -36,15 +36,15 @@ def report(tag, out, ref):
         print(f"   out[{m},{n}]={out[m, n].item():.5g} ref={ref[m, n].item():.5g}")
 
 
-for block_n in (128, 256):
-    for (M, N, K) in [(128, block_n, 64), (128, block_n, 128), (128, block_n, 512), (256, 2 * block_n, 64), (1000, 768, 768)]:
+for block_n in (128, 256, 512):
+    for (M, N, K) in [(128, min(block_n, 256), 64), (256, min(block_n, 256), 128), (128, min(block_n, 256), 512), (256, 2 * min(block_n, 256), 64), (1000, 768, 768)]:
         g = torch.Generator(device="cuda").manual_seed(1)
         a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
         w = torch.randn(N, K, device="cuda", generator=g).bfloat16()
         ref = a.float() @ w.float().t()
         report(f"bn={block_n} rand  M={M} N={N} K={K} f32", run(a, w, None, 1, block_n), ref)
     # one-hot A: out[m, n] = w[n, m % K]  -> exposes K-offset / swizzle mistakes exactly
-    M, N, K = 128, block_n, 64
+    M, N, K = 256, min(block_n, 256), 64
     a = torch.zeros(M, K, device="cuda"); a[torch.arange(M), torch.arange(M) % K] = 1
     w = torch.arange(N * K, device="cuda", dtype=torch.float32).reshape(N, K) % 251
     report(f"bn={block_n} onehot f32", run(a.bfloat16(), w.bfloat16(), None, 1, block_n), a @ w.t())
