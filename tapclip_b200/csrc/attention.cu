@@ -12,6 +12,7 @@
 //  * attn_bwd_kernel       fp32 parity-mode backward (SIMT, shared memory).
 #include "kernels.h"
 #include <type_traits>
+#include <cstdlib>
 
 namespace tapclip {
 namespace {
@@ -599,6 +600,12 @@ void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, cons
     TC_CHECK(N >= 1 && H >= 1, "bad attention shape");
     if (probe.mode == PROBE_TEXT_COL) TC_CHECK(probe.out && probe.P >= 1 && probe.P <= N, "bad text probe");
     if (probe.mode == PROBE_CLS_ROW) TC_CHECK(probe.out && probe.seq_stride >= (int64_t)H * N, "bad CLS probe");
+    static const int impl = getenv("TAPCLIP_ATTN_IMPL") ? atoi(getenv("TAPCLIP_ATTN_IMPL")) : 0;   // 0 auto, 1 mma.sync, 2 tcgen05
+    // auto: the persistent tcgen05 kernel for N <= 208 (ViT-B/16, ViT-B/32, text tower); the mma.sync flash kernel otherwise
+    if (impl == 2 || (impl == 0 && attention_fwd_tc_supported(dt, N) && N <= 208)) {
+        attention_fwd_tc(qkv, out, dt, S, N, H, probe, stream);
+        return;
+    }
     if (dt == DT_BF16 || dt == DT_F16) {
         const int npad = (int)round_up(N, KC);
         const int nrb = (int)ceil_div(N, 16);

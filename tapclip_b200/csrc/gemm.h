@@ -25,6 +25,11 @@ struct GemmArgs {
     int dt = DT_BF16;          // tcgen05 path: 16-bit type of A, W and of the EPI_BF16 output (DT_BF16 or DT_F16)
 };
 
+// Cached TMA descriptor of a 2-D row-major tensor [rows, cols] (leading dimension ld, elements of elem_bytes), 128B-swizzled
+// boxes of box_rows x box_cols (box_cols * elem_bytes must be 128).  Shared by the GEMM and the tcgen05 attention kernel.
+const CUtensorMap& make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+                             int box_rows, int box_cols);
+
 // tcgen05/TMEM/TMA path: A and W bf16 (or fp16, g.dt); out = same 16-bit type (EPI_BF16) or f32
 void gemm_tc(const GemmArgs& g, cudaStream_t stream);
 

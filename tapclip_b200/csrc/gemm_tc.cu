@@ -294,6 +294,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+}  // namespace
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -338,6 +340,7 @@ CUtensorMap encode_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes,
     TC_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned");
     TC_CHECK((ld * elem_bytes) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld=%lld)", (long long)ld);
     TC_CHECK(box_cols * elem_bytes == 128, "box inner extent must be 128 bytes");
+    TC_CHECK(box_rows >= 1 && box_rows <= 256, "TMA box rows must be in [1, 256]");
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)(ld * elem_bytes)};
@@ -349,6 +352,8 @@ CUtensorMap encode_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes,
     TC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
     return m;
 }
+
+namespace {
 
 int g_num_sms = 0;
 // TAPCLIP_GEMM_DEBUG (measurement only; results are WRONG when set): 1 = skip the epilogue's TMA stores, 2 = skip the epilogue body

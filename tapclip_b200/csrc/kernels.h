@@ -35,6 +35,9 @@ struct AttnProbe {
 // emitted from the softmax registers; the N x N map is never written.
 void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe,
                    cudaStream_t stream);
+// tcgen05 version of attention_fwd for 16-bit inputs and N <= 256 (attention_tc.cu); same contract
+bool attention_fwd_tc_supported(int dt, int N);
+void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream);
 // dqkv [S*N, 3*H*64] from d_out [S*N, H*64] and the saved qkv (probabilities recomputed). N <= 128.
 // qkv may be fp16 (mixed mode) while gradients are bf16; fp32 mode: everything fp32.
 void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, int grad_dt, int S, int N, int H,
