@@ -27,6 +27,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 attn_fwd_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, int npad, float scale_log2,
                     int probe_mode, float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride) {
+    pdl_wait_and_trigger();
     extern __shared__ __align__(128) uint8_t smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,6 +196,7 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, float scale, int probe_mode,
                      float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride) {
+    pdl_wait_and_trigger();
     __shared__ float qs[4][DH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.y / H, h = blockIdx.y % H;
@@ -271,6 +273,7 @@ constexpr int LDH = DH + 1;
 template <typename T>
 __global__ void __launch_bounds__(256)
 attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __restrict__ dqkv, int N, int H, float scale) {
+    pdl_wait_and_trigger();
     extern __shared__ __align__(16) float sm[];
     float* Q = sm;
     float* K = Q + N * LDH;
@@ -369,6 +372,7 @@ template <int NB16, typename TQ>
 __global__ void __launch_bounds__(NB16 * 32, 1)
 attn_bwd_mma_kernel(const TQ* __restrict__ qkv, const bf16* __restrict__ d_out, bf16* __restrict__ dqkv, int N, int H,
                     float scale) {
+    pdl_wait_and_trigger();
     constexpr int NP = NB16 * 16;               // padded sequence length
     constexpr int NB8 = NB16 * 2;               // 8-wide key blocks
     constexpr int PLD = NP * 2 + 16;            // P / dS row pitch in bytes (odd multiple of 16 B: conflict-free ldmatrix)
@@ -576,7 +580,7 @@ void launch_attn_bwd_mma(const TQ* qkv, const bf16* d_out, bf16* dqkv, int S, in
         TC_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<NB16, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    attn_bwd_mma_kernel<NB16, TQ><<<S * H, NB16 * 32, smem, stream>>>(qkv, d_out, dqkv, N, H, 0.125f);
+    launch_pdl(attn_bwd_mma_kernel<NB16, TQ>, S * H, NB16 * 32, smem, stream, qkv, d_out, dqkv, N, H, 0.125f);
 }
 
 template <typename TQ>
@@ -622,12 +626,12 @@ void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, cons
         }
         dim3 grid((unsigned)(S * H), (unsigned)nz);
         const float sl2 = 0.125f * 1.4426950408889634f;
-        if (which) attn_fwd_mma_kernel<f16><<<grid, nwarps * 32, smem, stream>>>((const f16*)qkv, (f16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
-        else attn_fwd_mma_kernel<bf16><<<grid, nwarps * 32, smem, stream>>>((const bf16*)qkv, (bf16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        if (which) launch_pdl(attn_fwd_mma_kernel<f16>, grid, nwarps * 32, smem, stream, (const f16*)qkv, (f16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        else launch_pdl(attn_fwd_mma_kernel<bf16>, grid, nwarps * 32, smem, stream, (const bf16*)qkv, (bf16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
     } else {
         TC_CHECK(N <= KMAX * 32, "sequence length %d too long for the fp32 attention kernel", N);
         dim3 grid((unsigned)ceil_div(N, 4), (unsigned)(S * H));
-        attn_fwd_simt_kernel<float><<<grid, 128, 0, stream>>>((const float*)qkv, (float*)out, N, H, 0.125f, probe.mode, probe.out,
+        launch_pdl(attn_fwd_simt_kernel<float>, grid, 128, 0, stream, (const float*)qkv, (float*)out, N, H, 0.125f, probe.mode, probe.out,
                                                               probe.P, probe.seq_stride);
     }
     TC_LAUNCH_CHECK();
@@ -645,7 +649,7 @@ void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, i
         const size_t smem = ((size_t)4 * N * LDH + (size_t)N * (N + 1)) * sizeof(float);
         static size_t conf_f32 = 0;
         if (smem > conf_f32) { TC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf_f32 = smem; }
-        attn_bwd_kernel<float><<<S * H, 256, smem, stream>>>((const float*)qkv, (const float*)d_out, (float*)dqkv, N, H, 0.125f);
+        launch_pdl(attn_bwd_kernel<float>, S * H, 256, smem, stream, (const float*)qkv, (const float*)d_out, (float*)dqkv, N, H, 0.125f);
     }
     TC_LAUNCH_CHECK();
 }

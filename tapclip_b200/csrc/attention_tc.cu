@@ -209,6 +209,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -295,6 +297,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // ---- loader: keeps up to three items of Q/K/V in flight ----
@@ -407,8 +411,8 @@ void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         if (num_sms == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
         const int n_items = S * H * nqt;
         const unsigned grid2 = (unsigned)std::min(n_items, num_sms);
-        if (f16) attn_fwd_tc2_kernel<true><<<grid2, ATTN2_THREADS, smem2, stream>>>(tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
-        else attn_fwd_tc2_kernel<false><<<grid2, ATTN2_THREADS, smem2, stream>>>(tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        if (f16) launch_pdl(attn_fwd_tc2_kernel<true>, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        else launch_pdl(attn_fwd_tc2_kernel<false>, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
         TC_LAUNCH_CHECK();
         return;
     }
@@ -420,8 +424,8 @@ void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         conf[f16] = smem;
     }
     const unsigned grid = (unsigned)((int64_t)S * H * nqt);
-    if (f16) attn_fwd_tc_kernel<true><<<grid, ATTN_THREADS, smem, stream>>>(tq, tkv, out, N, H, nkp, nqt, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
-    else attn_fwd_tc_kernel<false><<<grid, ATTN_THREADS, smem, stream>>>(tq, tkv, out, N, H, nkp, nqt, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+    if (f16) launch_pdl(attn_fwd_tc_kernel<true>, grid, ATTN_THREADS, smem, stream, tq, tkv, out, N, H, nkp, nqt, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+    else launch_pdl(attn_fwd_tc_kernel<false>, grid, ATTN_THREADS, smem, stream, tq, tkv, out, N, H, nkp, nqt, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
     TC_LAUNCH_CHECK();
 }
 

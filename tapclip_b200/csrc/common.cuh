@@ -47,6 +47,27 @@ struct Error {
 
 #define TC_LAUNCH_CHECK() TC_CUDA(cudaGetLastError())
 
+// Programmatic dependent launch: every kernel of the library is launched with the stream-serialization attribute and
+// calls griddepcontrol.wait before it touches global memory, so a kernel's launch latency and prologue (barrier init,
+// TMEM allocation, descriptor prefetch) overlap the tail of its predecessor.  TAPCLIP_PDL=0 disables it.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) throw Error{std::string("kernel launch failed: ") + cudaGetErrorString(e)};
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
@@ -60,6 +81,10 @@ static inline int dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 // device helpers
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_and_trigger() { pdl_wait(); pdl_trigger(); }
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

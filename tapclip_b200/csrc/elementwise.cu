@@ -13,6 +13,7 @@ template <typename T> __device__ __forceinline__ void store_val(T* p, float v) {
 template <typename T>
 __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int R, int p, int g, int kdim,
                                 int kpad) {
+    pdl_wait_and_trigger();
     const int64_t total = (int64_t)B * g * g * kpad;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % kpad);
@@ -31,6 +32,7 @@ __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ o
 // open_clip VisionTransformer.forward: cat([class_embedding, patches]) + positional_embedding
 __global__ void assemble_tokens_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls,
                                        const float* __restrict__ pos, float* __restrict__ x, int B, int n_tokens, int d) {
+    pdl_wait_and_trigger();
     const int d4 = d >> 2;
     const int64_t total = (int64_t)B * n_tokens * d4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -50,6 +52,7 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ patch_out, cons
 // (ctx * attribution) and the expand/cat of models/model_wrapper.py:49-51,68-69 — one row per class, not per sample.
 __global__ void splice_kernel(const float* __restrict__ ctx, const float* __restrict__ tok, const float* __restrict__ attr,
                               int attr_p, float* __restrict__ x, int C, int P, int L, int D) {
+    pdl_wait_and_trigger();
     const int T = P + L, d4 = D >> 2;
     const int64_t total = (int64_t)C * T * d4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -74,6 +77,7 @@ __global__ void splice_kernel(const float* __restrict__ ctx, const float* __rest
 // backward of the splice: only the ctx rows are learnable; attribution is detached (clip_wrapper.py:36)
 __global__ void splice_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ attr, int attr_p,
                                   float* __restrict__ dctx, int C, int P, int T, int D) {
+    pdl_wait_and_trigger();
     const int d4 = D >> 2;
     const int64_t total = (int64_t)C * P * d4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -94,6 +98,7 @@ __global__ void splice_bwd_kernel(const float* __restrict__ dx, const float* __r
 // One warp per class; warp-shuffle reductions; P <= 64.
 __global__ void attribution_kernel(const float* __restrict__ probe, float* __restrict__ raw, float* __restrict__ attr,
                                    int C, int H, int P) {
+    pdl_wait_and_trigger();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
@@ -117,6 +122,7 @@ __global__ void attribution_kernel(const float* __restrict__ probe, float* __res
 template <typename T>
 __global__ void gather_rows_kernel(const float* __restrict__ x, T* __restrict__ out, int64_t rows, int64_t row_stride,
                                    int64_t row_offset, int d) {
+    pdl_wait_and_trigger();
     const int64_t total = rows * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / d;
@@ -128,6 +134,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, T* __restrict__ 
 template <typename T>
 __global__ void scatter_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, T* __restrict__ dst_cast,
                                     int64_t rows, int64_t row_stride, int64_t row_offset, int d) {
+    pdl_wait_and_trigger();
     const int64_t total = rows * d;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / d;
@@ -140,12 +147,14 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, float* __rest
 
 template <typename T>
 __global__ void cast_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n) {
+    pdl_wait_and_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         store_val<T>(dst + i, src[i]);
 }
 
 template <typename T, typename TH, int ACT>
 __global__ void act_bwd_kernel(T* __restrict__ dh, const TH* __restrict__ h_pre, int64_t n) {
+    pdl_wait_and_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dh[i] = from_f32<T>(to_f32<T>(dh[i]) * act_bwd<ACT>(to_f32<TH>(h_pre[i])));
 }
@@ -153,6 +162,7 @@ __global__ void act_bwd_kernel(T* __restrict__ dh, const TH* __restrict__ h_pre,
 // models/model_wrapper.py:79,83 for all (b, c) at once: logits = exp(logit_scale) * I_hat . T_hat^T.  One warp per pair.
 __global__ void cosine_logits_kernel(const float* __restrict__ img, const float* __restrict__ txt,
                                      const float* __restrict__ logit_scale, float* __restrict__ logits, int B, int C, int E) {
+    pdl_wait_and_trigger();
     const int64_t pair = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pair >= (int64_t)B * C) return;
     const int lane = threadIdx.x & 31;
@@ -170,6 +180,7 @@ __global__ void cosine_logits_kernel(const float* __restrict__ img, const float*
 // models/model_wrapper.py:91 F.cross_entropy (mean reduction); one warp per sample; also dloss/dlogits.
 __global__ void ce_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, float* __restrict__ row_loss,
                                float* __restrict__ dlogits, int B, int C, float inv_batch_total) {
+    pdl_wait_and_trigger();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
     const int lane = threadIdx.x & 31;
@@ -189,6 +200,7 @@ __global__ void ce_rows_kernel(const float* __restrict__ logits, const int64_t* 
 }
 // deterministic single-block sum
 __global__ void sum_kernel(const float* __restrict__ v, float* __restrict__ out, int n) {
+    pdl_wait_and_trigger();
     __shared__ float sh[32];
     float s = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
@@ -206,6 +218,7 @@ __global__ void sum_kernel(const float* __restrict__ v, float* __restrict__ out,
 __global__ void logits_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ logits,
                                   const float* __restrict__ img, const float* __restrict__ logit_scale,
                                   float* __restrict__ d_txt, float* __restrict__ d_scale_part, int B, int C, int E) {
+    pdl_wait_and_trigger();
     const int c = blockIdx.x;
     const float es = expf(__ldg(logit_scale));
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
@@ -224,6 +237,7 @@ __global__ void logits_bwd_kernel(const float* __restrict__ dlogits, const float
 // torch.optim.AdamW (train.py:65-67): decoupled weight decay, bias-corrected moments
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              int64_t n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
+    pdl_wait_and_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float gi = g[i];
         float pi = p[i] * (1.f - lr * wd);
@@ -239,6 +253,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 // utils/eval_metrics.py:19-29: argmax over classes (first max wins, as torch.argmax) + correct count
 __global__ void argmax_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int64_t* __restrict__ pred,
                               int* __restrict__ correct, int B, int C) {
+    pdl_wait_and_trigger();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
     const int lane = threadIdx.x & 31;
@@ -268,9 +283,9 @@ void patchify(const float* images, void* out, int out_dt, int B, int R, int p, i
     const int g = R / p, kdim = 3 * p * p;
     const int64_t total = (int64_t)B * g * g * kpad;
     if (total == 0) return;
-    if (out_dt == DT_BF16) patchify_kernel<bf16><<<grid_for(total), 256, 0, stream>>>(images, (bf16*)out, B, R, p, g, kdim, kpad);
-    else if (out_dt == DT_F16) patchify_kernel<f16><<<grid_for(total), 256, 0, stream>>>(images, (f16*)out, B, R, p, g, kdim, kpad);
-    else patchify_kernel<float><<<grid_for(total), 256, 0, stream>>>(images, (float*)out, B, R, p, g, kdim, kpad);
+    if (out_dt == DT_BF16) launch_pdl(patchify_kernel<bf16>, grid_for(total), 256, 0, stream, images, (bf16*)out, B, R, p, g, kdim, kpad);
+    else if (out_dt == DT_F16) launch_pdl(patchify_kernel<f16>, grid_for(total), 256, 0, stream, images, (f16*)out, B, R, p, g, kdim, kpad);
+    else launch_pdl(patchify_kernel<float>, grid_for(total), 256, 0, stream, images, (float*)out, B, R, p, g, kdim, kpad);
     TC_LAUNCH_CHECK();
 }
 
@@ -278,7 +293,7 @@ void assemble_tokens(const float* patch_out, const float* cls, const float* pos,
                      cudaStream_t stream) {
     const int64_t total = (int64_t)B * n_tokens * (d / 4);
     if (total == 0) return;
-    assemble_tokens_kernel<<<grid_for(total), 256, 0, stream>>>(patch_out, cls, pos, x, B, n_tokens, d);
+    launch_pdl(assemble_tokens_kernel, grid_for(total), 256, 0, stream, patch_out, cls, pos, x, B, n_tokens, d);
     TC_LAUNCH_CHECK();
 }
 
@@ -286,30 +301,30 @@ void splice_prompts(const float* ctx, const float* tok, const float* attr, int a
                     cudaStream_t stream) {
     const int64_t total = (int64_t)C * (P + L) * (D / 4);
     if (total == 0) return;
-    splice_kernel<<<grid_for(total), 256, 0, stream>>>(ctx, tok, attr, attr_p, x, C, P, L, D);
+    launch_pdl(splice_kernel, grid_for(total), 256, 0, stream, ctx, tok, attr, attr_p, x, C, P, L, D);
     TC_LAUNCH_CHECK();
 }
 
 void splice_bwd(const float* dx, const float* attr, int attr_p, float* dctx, int C, int P, int T, int D, cudaStream_t stream) {
     const int64_t total = (int64_t)C * P * (D / 4);
     if (total == 0) return;
-    splice_bwd_kernel<<<grid_for(total), 256, 0, stream>>>(dx, attr, attr_p, dctx, C, P, T, D);
+    launch_pdl(splice_bwd_kernel, grid_for(total), 256, 0, stream, dx, attr, attr_p, dctx, C, P, T, D);
     TC_LAUNCH_CHECK();
 }
 
 void attribution_reduce(const float* probe, float* raw, float* attr, int C, int H, int P, cudaStream_t stream) {
     TC_CHECK(P >= 1 && P <= 64, "prompt_len %d unsupported by the attribution kernel (1..64)", P);
     if (C == 0) return;
-    attribution_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, stream>>>(probe, raw, attr, C, H, P);
+    launch_pdl(attribution_kernel, (unsigned)ceil_div(C, 4), 128, 0, stream, probe, raw, attr, C, H, P);
     TC_LAUNCH_CHECK();
 }
 
 void gather_rows(const float* x, void* out, int out_dt, int64_t rows, int64_t row_stride, int64_t row_offset, int d,
                  cudaStream_t stream) {
     if (rows == 0) return;
-    if (out_dt == DT_BF16) gather_rows_kernel<bf16><<<grid_for(rows * d), 256, 0, stream>>>(x, (bf16*)out, rows, row_stride, row_offset, d);
-    else if (out_dt == DT_F16) gather_rows_kernel<f16><<<grid_for(rows * d), 256, 0, stream>>>(x, (f16*)out, rows, row_stride, row_offset, d);
-    else gather_rows_kernel<float><<<grid_for(rows * d), 256, 0, stream>>>(x, (float*)out, rows, row_stride, row_offset, d);
+    if (out_dt == DT_BF16) launch_pdl(gather_rows_kernel<bf16>, grid_for(rows * d), 256, 0, stream, x, (bf16*)out, rows, row_stride, row_offset, d);
+    else if (out_dt == DT_F16) launch_pdl(gather_rows_kernel<f16>, grid_for(rows * d), 256, 0, stream, x, (f16*)out, rows, row_stride, row_offset, d);
+    else launch_pdl(gather_rows_kernel<float>, grid_for(rows * d), 256, 0, stream, x, (float*)out, rows, row_stride, row_offset, d);
     TC_LAUNCH_CHECK();
 }
 
@@ -317,16 +332,16 @@ void scatter_rows(const float* src, float* dst, void* dst_cast, int cast_dt, int
                   int64_t row_offset, int d, cudaStream_t stream) {
     if (rows == 0) return;
     TC_CHECK(cast_dt != DT_F16, "gradients are never fp16");
-    if (cast_dt == DT_BF16) scatter_rows_kernel<bf16><<<grid_for(rows * d), 256, 0, stream>>>(src, dst, (bf16*)dst_cast, rows, row_stride, row_offset, d);
-    else scatter_rows_kernel<float><<<grid_for(rows * d), 256, 0, stream>>>(src, dst, (float*)dst_cast, rows, row_stride, row_offset, d);
+    if (cast_dt == DT_BF16) launch_pdl(scatter_rows_kernel<bf16>, grid_for(rows * d), 256, 0, stream, src, dst, (bf16*)dst_cast, rows, row_stride, row_offset, d);
+    else launch_pdl(scatter_rows_kernel<float>, grid_for(rows * d), 256, 0, stream, src, dst, (float*)dst_cast, rows, row_stride, row_offset, d);
     TC_LAUNCH_CHECK();
 }
 
 void cast_f32(const float* src, void* dst, int dst_dt, int64_t n, cudaStream_t stream) {
     if (n == 0) return;
-    if (dst_dt == DT_BF16) cast_kernel<bf16><<<grid_for(n), 256, 0, stream>>>(src, (bf16*)dst, n);
-    else if (dst_dt == DT_F16) cast_kernel<f16><<<grid_for(n), 256, 0, stream>>>(src, (f16*)dst, n);
-    else cast_kernel<float><<<grid_for(n), 256, 0, stream>>>(src, (float*)dst, n);
+    if (dst_dt == DT_BF16) launch_pdl(cast_kernel<bf16>, grid_for(n), 256, 0, stream, src, (bf16*)dst, n);
+    else if (dst_dt == DT_F16) launch_pdl(cast_kernel<f16>, grid_for(n), 256, 0, stream, src, (f16*)dst, n);
+    else launch_pdl(cast_kernel<float>, grid_for(n), 256, 0, stream, src, (float*)dst, n);
     TC_LAUNCH_CHECK();
 }
 
@@ -335,8 +350,8 @@ void act_bwd_inplace(void* dh, int dh_dt, const void* h_pre, int h_dt, int act, 
     const unsigned grid = grid_for(n);
 #define TC_ACT_BWD(T, TH)                                                                                             \
     do {                                                                                                              \
-        if (act == ACT_GELU_ERF) act_bwd_kernel<T, TH, ACT_GELU_ERF><<<grid, 256, 0, stream>>>((T*)dh, (const TH*)h_pre, n); \
-        else act_bwd_kernel<T, TH, ACT_QUICK_GELU><<<grid, 256, 0, stream>>>((T*)dh, (const TH*)h_pre, n);             \
+        if (act == ACT_GELU_ERF) launch_pdl(act_bwd_kernel<T, TH, ACT_GELU_ERF>, grid, 256, 0, stream, (T*)dh, (const TH*)h_pre, n); \
+        else launch_pdl(act_bwd_kernel<T, TH, ACT_QUICK_GELU>, grid, 256, 0, stream, (T*)dh, (const TH*)h_pre, n);             \
     } while (0)
     if (dh_dt == DT_F32 && h_dt == DT_F32) TC_ACT_BWD(float, float);
     else if (dh_dt == DT_BF16 && h_dt == DT_BF16) TC_ACT_BWD(bf16, bf16);
@@ -351,25 +366,25 @@ void cosine_logits(const float* img, const float* txt, const float* logit_scale,
     TC_CHECK(E % 4 == 0, "embed dim must be a multiple of 4");
     const int64_t pairs = (int64_t)B * C;
     if (pairs == 0) return;
-    cosine_logits_kernel<<<(unsigned)ceil_div(pairs, 8), 256, 0, stream>>>(img, txt, logit_scale, logits, B, C, E);
+    launch_pdl(cosine_logits_kernel, (unsigned)ceil_div(pairs, 8), 256, 0, stream, img, txt, logit_scale, logits, B, C, E);
     TC_LAUNCH_CHECK();
 }
 
 void cross_entropy(const float* logits, const int64_t* labels, float* loss, float* dlogits, float* row_scratch, int B, int C,
                    float inv_batch_total, cudaStream_t stream) {
     if (B == 0) return;
-    ce_rows_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, stream>>>(logits, labels, row_scratch, dlogits, B, C, inv_batch_total);
+    launch_pdl(ce_rows_kernel, (unsigned)ceil_div(B, 8), 256, 0, stream, logits, labels, row_scratch, dlogits, B, C, inv_batch_total);
     TC_LAUNCH_CHECK();
-    sum_kernel<<<1, 256, 0, stream>>>(row_scratch, loss, B);
+    launch_pdl(sum_kernel, 1, 256, 0, stream, row_scratch, loss, B);
     TC_LAUNCH_CHECK();
 }
 
 void logits_bwd(const float* dlogits, const float* logits, const float* img, const float* logit_scale, float* d_txt,
                 float* d_scale, float* class_scratch, int B, int C, int E, cudaStream_t stream) {
     if (C == 0) return;
-    logits_bwd_kernel<<<C, 256, 0, stream>>>(dlogits, logits, img, logit_scale, d_txt, class_scratch, B, C, E);
+    launch_pdl(logits_bwd_kernel, C, 256, 0, stream, dlogits, logits, img, logit_scale, d_txt, class_scratch, B, C, E);
     TC_LAUNCH_CHECK();
-    sum_kernel<<<1, 256, 0, stream>>>(class_scratch, d_scale, C);
+    launch_pdl(sum_kernel, 1, 256, 0, stream, class_scratch, d_scale, C);
     TC_LAUNCH_CHECK();
 }
 
@@ -378,13 +393,13 @@ void adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float l
     if (n == 0) return;
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-    adamw_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    launch_pdl(adamw_kernel, grid_for(n), 256, 0, stream, p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
     TC_LAUNCH_CHECK();
 }
 
 void argmax_count(const float* logits, const int64_t* labels, int64_t* pred, int* correct, int B, int C, cudaStream_t stream) {
     if (B == 0) return;
-    argmax_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, stream>>>(logits, labels, pred, correct, B, C);
+    launch_pdl(argmax_kernel, (unsigned)ceil_div(B, 8), 256, 0, stream, logits, labels, pred, correct, B, C);
     TC_LAUNCH_CHECK();
 }
 

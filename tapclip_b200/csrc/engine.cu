@@ -7,6 +7,7 @@
 // prompt).  Residual streams stay fp32; bf16 is used only for tensor-core operands.
 #include "engine.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <sstream>
@@ -17,12 +18,17 @@ namespace {
 thread_local std::string g_error;
 }
 void set_error(const std::string& msg) { g_error = msg; }
+bool pdl_enabled() {
+    static const bool on = !(getenv("TAPCLIP_PDL") && atoi(getenv("TAPCLIP_PDL")) == 0);
+    return on;
+}
 const char* get_error() { return g_error.c_str(); }
 
 namespace {
 
 template <typename T>
 __global__ void convert_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int R, int C, int dst_ld, int transpose) {
+    pdl_wait_and_trigger();
     // dst is [R, dst_ld] (transpose == 0, dst[r][c] = src[r][c]) or [C, dst_ld] (transpose, dst[c][r] = src[r][c])
     const int64_t total = (int64_t)R * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -34,6 +40,7 @@ __global__ void convert_weight_kernel(const float* __restrict__ src, T* __restri
 }
 
 __global__ void fill_kernel(float* p, float v, int64_t n) {
+    pdl_wait_and_trigger();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
@@ -110,9 +117,9 @@ void* Engine::store(const std::string& key, const float* src, int R, int C, int 
     TC_CUDA(cudaMemsetAsync(dst, 0, bytes, st));
     const int64_t total = (int64_t)R * C;
     const unsigned g = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
-    if (dt == DT_BF16) convert_weight_kernel<bf16><<<g, 256, 0, st>>>(src, (bf16*)dst, R, C, dst_ld, transpose ? 1 : 0);
-    else if (dt == DT_F16) convert_weight_kernel<f16><<<g, 256, 0, st>>>(src, (f16*)dst, R, C, dst_ld, transpose ? 1 : 0);
-    else convert_weight_kernel<float><<<g, 256, 0, st>>>(src, (float*)dst, R, C, dst_ld, transpose ? 1 : 0);
+    if (dt == DT_BF16) launch_pdl(convert_weight_kernel<bf16>, g, 256, 0, st, src, (bf16*)dst, R, C, dst_ld, transpose ? 1 : 0);
+    else if (dt == DT_F16) launch_pdl(convert_weight_kernel<f16>, g, 256, 0, st, src, (f16*)dst, R, C, dst_ld, transpose ? 1 : 0);
+    else launch_pdl(convert_weight_kernel<float>, g, 256, 0, st, src, (float*)dst, R, C, dst_ld, transpose ? 1 : 0);
     TC_LAUNCH_CHECK();
     ++launches;
     return dst;
@@ -399,7 +406,7 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
         if (out_attr) TC_CUDA(cudaMemcpyAsync(out_attr, t_attr.p, (size_t)C * P * 4, cudaMemcpyDeviceToDevice, st));
     } else if (out_attr) {
         // literal mode: the reference's attribution is identically 1.0; ctx*1 == ctx
-        fill_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(out_attr, 1.0f, C);
+        launch_pdl(fill_kernel, (unsigned)ceil_div(C, 256), 256, 0, st, out_attr, 1.0f, C);
         TC_LAUNCH_CHECK(); ++launches;
     }
     // feature pass (rows A9/A10)

@@ -107,6 +107,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail (PDL);
+    // from here on global memory written by that kernel is read
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -387,15 +391,17 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
         cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = C::SMEM_BYTES;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
         TC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug));
     } else {
         const int64_t tiles = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, BLOCK_N);
         const int grid = (int)std::min<int64_t>(tiles, g_num_sms);
-        kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug);
+        launch_pdl(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug);
     }
     TC_LAUNCH_CHECK();
 }

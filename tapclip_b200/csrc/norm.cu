@@ -29,6 +29,7 @@ template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
 layernorm_fwd_kernel(const float* x, int64_t x_row_stride, const float* __restrict__ gamma,
                      const float* __restrict__ beta, T* out, float* x_copy, int64_t rows, int d) {
+    pdl_wait_and_trigger();
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, nv = d >> 7;
@@ -70,6 +71,7 @@ template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      float* dx_acc, T* dx_cast, int64_t rows, int d) {
+    pdl_wait_and_trigger();
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, nv = d >> 7;
@@ -120,6 +122,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
 
 __global__ void __launch_bounds__(WARPS * 32)
 l2norm_fwd_kernel(const float* __restrict__ x, float* out, float* inv_norm, int64_t rows, int d) {
+    pdl_wait_and_trigger();
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, nv = d >> 7;
@@ -145,6 +148,7 @@ template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
 l2norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xhat, const float* __restrict__ inv_norm,
                   float* dx, T* dx_cast, int64_t rows, int d) {
+    pdl_wait_and_trigger();
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, nv = d >> 7;
@@ -181,9 +185,9 @@ void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, con
     check_d(d);
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (out_dt == DT_BF16) layernorm_fwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (bf16*)out, x_copy, rows, d);
-    else if (out_dt == DT_F16) layernorm_fwd_kernel<f16><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (f16*)out, x_copy, rows, d);
-    else layernorm_fwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(x, x_row_stride, gamma, beta, (float*)out, x_copy, rows, d);
+    if (out_dt == DT_BF16) launch_pdl(layernorm_fwd_kernel<bf16>, grid, WARPS * 32, 0, stream, x, x_row_stride, gamma, beta, (bf16*)out, x_copy, rows, d);
+    else if (out_dt == DT_F16) launch_pdl(layernorm_fwd_kernel<f16>, grid, WARPS * 32, 0, stream, x, x_row_stride, gamma, beta, (f16*)out, x_copy, rows, d);
+    else launch_pdl(layernorm_fwd_kernel<float>, grid, WARPS * 32, 0, stream, x, x_row_stride, gamma, beta, (float*)out, x_copy, rows, d);
     TC_LAUNCH_CHECK();
 }
 
@@ -193,15 +197,15 @@ void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* d
     TC_CHECK(cast_dt != DT_F16, "gradients are never fp16");
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (cast_dt == DT_BF16) layernorm_bwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d);
-    else layernorm_bwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(dy, x, gamma, dx_acc, (float*)dx_cast, rows, d);
+    if (cast_dt == DT_BF16) launch_pdl(layernorm_bwd_kernel<bf16>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d);
+    else launch_pdl(layernorm_bwd_kernel<float>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (float*)dx_cast, rows, d);
     TC_LAUNCH_CHECK();
 }
 
 void l2norm_fwd(const float* x, float* out, float* inv_norm, int64_t rows, int d, cudaStream_t stream) {
     check_d(d);
     if (rows == 0) return;
-    l2norm_fwd_kernel<<<(unsigned)ceil_div(rows, WARPS), WARPS * 32, 0, stream>>>(x, out, inv_norm, rows, d);
+    launch_pdl(l2norm_fwd_kernel, (unsigned)ceil_div(rows, WARPS), WARPS * 32, 0, stream, x, out, inv_norm, rows, d);
     TC_LAUNCH_CHECK();
 }
 
@@ -211,8 +215,8 @@ void l2norm_bwd(const float* g, const float* xhat, const float* inv_norm, float*
     TC_CHECK(cast_dt != DT_F16, "gradients are never fp16");
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (cast_dt == DT_BF16) l2norm_bwd_kernel<bf16><<<grid, WARPS * 32, 0, stream>>>(g, xhat, inv_norm, dx, (bf16*)dx_cast, rows, d);
-    else l2norm_bwd_kernel<float><<<grid, WARPS * 32, 0, stream>>>(g, xhat, inv_norm, dx, (float*)dx_cast, rows, d);
+    if (cast_dt == DT_BF16) launch_pdl(l2norm_bwd_kernel<bf16>, grid, WARPS * 32, 0, stream, g, xhat, inv_norm, dx, (bf16*)dx_cast, rows, d);
+    else launch_pdl(l2norm_bwd_kernel<float>, grid, WARPS * 32, 0, stream, g, xhat, inv_norm, dx, (float*)dx_cast, rows, d);
     TC_LAUNCH_CHECK();
 }
 
