@@ -157,6 +157,12 @@ class FullModel(nn.Module):
         pl = self.prompt_learner
         params = [pl.context_bank[k] for k in pl.context_bank.keys()]          # model_wrapper.py:47 (insertion order)
         images = images.contiguous().float()
+        if images.shape[0] == 0:                                               # empty batch: cat of empty columns (:83)
+            outputs = {"logits": images.new_zeros(0, pl.n_cls)}
+            if labels is not None:
+                nan = images.new_full((), float("nan"))                        # F.cross_entropy over an empty batch
+                outputs.update({"loss": nan, "loss_cls": nan})
+            return outputs
         # grad mode is off inside autograd.Function.forward, so decide here whether activations must be kept
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         logits, loss = _TapClipFunction.apply(self, images, labels, need_grad, self.logit_scale, *params)

@@ -77,6 +77,53 @@ def test_image_features_and_cls_rows_vs_oracle(dtype):
     assert (rows.sum(-1) - 1).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "mixed"])
+@pytest.mark.parametrize("name,B,C,P", [("ViT-L-14-336", 2, 3, 16), ("ViT-B-32", 3, 4, 5)])
+def test_other_architectures_vs_oracle(name, B, C, P, dtype):
+    """BASELINE configs[3] shapes (ViT-L/14@336: 577 tokens -> flash mma.sync attention, d=1024, text width 768, 24 layers)
+    and the reference's default model ViT-B/32 (clip_wrapper.py:10; 50 tokens, prompt_len 5), against the CPU oracle."""
+    import os
+    torch.set_num_threads(os.cpu_count())
+    cfg = get_config(name)
+    ow, om = build_oracle(name, C, P, "intended")
+    clip, model = build_cuda(name, C, P, "intended", dtype, ow)
+    images, labels = synthetic_images(B, cfg.image_size), synthetic_labels(B, C)
+    om.train(); model.train()
+    ref = om.forward_dedup(images, labels, return_aux=True)
+    ref["loss"].backward()
+    out = model(images.cuda(), labels.cuda())
+    out["loss"].backward()
+    tol = LOGIT_TOL[dtype]
+    e_logits = max_abs(out["logits"], ref["logits"])
+    e_attr = ((model.last_attribution.cpu() - ref["attribution"]).abs() / ref["attribution"].abs()).max().item()
+    g_ref = torch.stack([om.prompt_learner.context_bank[n].grad for n in class_names(C)])
+    e_grad = rel_err(ctx_grads(model, C), g_ref)
+    print(f"\n[parity] {name} B={B} C={C} P={P} {dtype}: max|dlogit|={e_logits:.3e} attr_rel={e_attr:.3e} ctx_grad_relL2={e_grad:.3e}")
+    assert e_logits <= tol and e_attr <= 1e-3 and e_grad <= GRAD_TOL[dtype]
+
+
+@pytest.mark.parametrize("B,C,P", [(1, 1, 1), (5, 2, 27), (2, 9, 5)])
+def test_edge_shapes_fp32(B, C, P):
+    """Ragged / extreme shapes: single image, single class, one ctx token, the longest trainable prompt (P + 77 <= 104)."""
+    ow, om = build_oracle("mini-16", C, P, "intended")
+    clip, model = build_cuda("mini-16", C, P, "intended", "fp32", ow)
+    images, labels = synthetic_images(B, 64), synthetic_labels(B, C)
+    om.train(); model.train()
+    ref = om.forward_dedup(images, labels)
+    ref["loss"].backward()
+    out = model(images.cuda(), labels.cuda())
+    out["loss"].backward()
+    g_ref = torch.stack([om.prompt_learner.context_bank[n].grad for n in class_names(C)])
+    assert max_abs(out["logits"], ref["logits"]) <= 1e-4
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 1e-4
+    if g_ref.abs().max() > 0:
+        assert rel_err(ctx_grads(model, C), g_ref) <= 2e-3
+    # empty batch in eval: logits [0, C] (model_wrapper.py:83 cat of empty columns)
+    model.eval()
+    with torch.no_grad():
+        assert model(torch.zeros(0, 3, 64, 64, device="cuda"))["logits"].shape == (0, C)
+
+
 def test_full_size_properties_mixed():
     """BASELINE configs[1] shapes (B=128, C=65, P=16, ViT-B/16, bf16): size-independent properties."""
     import tapclip_b200 as tb
