@@ -29,6 +29,36 @@ __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ o
     }
 }
 
+// Fast path for patch sizes that are multiples of 4 (16, 32): one thread moves 4 consecutive pixels of one patch row
+// (16-byte load, 8-byte store); consecutive threads cover consecutive pixels, then patch rows, then channels, so both
+// sides are coalesced.  116 MB of traffic at B=128: HBM-bound.
+template <typename T>
+__global__ void patchify4_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int R, int p, int g, int kdim, int kpad) {
+    pdl_wait_and_trigger();
+    const int k4 = kpad >> 2;
+    const int64_t total = (int64_t)B * g * g * k4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % k4) * 4;
+        const int64_t row = i / k4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < kdim) {
+            const int px = k % p, py = (k / p) % p, c = k / (p * p);
+            const int gx = (int)(row % g), gy = (int)((row / g) % g);
+            const int64_t b = row / ((int64_t)g * g);
+            v = __ldg(reinterpret_cast<const float4*>(img + ((b * 3 + c) * R + (gy * p + py)) * (int64_t)R + gx * p + px));
+        }
+        T* o = out + row * kpad + k;
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(o) = v;
+        } else {
+            uint2 u;
+            u.x = pack2<T>(v.x, v.y);
+            u.y = pack2<T>(v.z, v.w);
+            *reinterpret_cast<uint2*>(o) = u;
+        }
+    }
+}
+
 // open_clip VisionTransformer.forward: cat([class_embedding, patches]) + positional_embedding
 __global__ void assemble_tokens_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls,
                                        const float* __restrict__ pos, float* __restrict__ x, int B, int n_tokens, int d) {
@@ -283,6 +313,13 @@ void patchify(const float* images, void* out, int out_dt, int B, int R, int p, i
     const int g = R / p, kdim = 3 * p * p;
     const int64_t total = (int64_t)B * g * g * kpad;
     if (total == 0) return;
+    if (p % 4 == 0 && R % 4 == 0 && kpad % 4 == 0 && out_dt != DT_F32) {
+        const int64_t t4 = total / 4;
+        if (out_dt == DT_BF16) launch_pdl(patchify4_kernel<bf16>, grid_for(t4), 256, 0, stream, images, (bf16*)out, B, R, p, g, kdim, kpad);
+        else launch_pdl(patchify4_kernel<f16>, grid_for(t4), 256, 0, stream, images, (f16*)out, B, R, p, g, kdim, kpad);
+        TC_LAUNCH_CHECK();
+        return;
+    }
     if (out_dt == DT_BF16) launch_pdl(patchify_kernel<bf16>, grid_for(total), 256, 0, stream, images, (bf16*)out, B, R, p, g, kdim, kpad);
     else if (out_dt == DT_F16) launch_pdl(patchify_kernel<f16>, grid_for(total), 256, 0, stream, images, (f16*)out, B, R, p, g, kdim, kpad);
     else launch_pdl(patchify_kernel<float>, grid_for(total), 256, 0, stream, images, (float*)out, B, R, p, g, kdim, kpad);

@@ -63,7 +63,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool f16) {
 template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               void* __restrict__ out, void* __restrict__ out_pre, int ldo,
+               void* out, void* out_pre, int ldo,
                const float* __restrict__ bias, int M, int N, int K, int dbg) {
     using C = Cfg<BLOCK_N, CTA2>;
     using T16 = typename std::conditional<F16, f16, bf16>::type;
@@ -261,20 +261,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     uint8_t* gbase = reinterpret_cast<uint8_t*>(is_pre ? out_pre : out);
                     const int gcol = col0 + rd_ch * (16 / OUT_ESZ);
                     if (dbg != 1) {
+                        if constexpr (EPI == EPI_F32_ADD) {
+                            // residual update x += tile as fire-and-forget vector reductions (measured faster than a plain
+                            // read-modify-write: 37 vs 54 us on the 25216x768x768 out-projection); every element has exactly
+                            // one contributor, so the result is deterministic
 #pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int r = it * 4 + rd_row;
-                            uint32_t x0, x1, x2, x3;
-                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
-                                         : "r"(sb + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
-                            if (row0 + r < M && gcol < N) {
-                                uint8_t* gp = gbase + ((int64_t)(row0 + r) * ldo + gcol) * OUT_ESZ;
-                                if constexpr (EPI == EPI_F32_ADD) {
-                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "f"(__uint_as_float(x0)),
-                                                 "f"(__uint_as_float(x1)), "f"(__uint_as_float(x2)), "f"(__uint_as_float(x3)) : "memory");
-                                } else {
-                                    *reinterpret_cast<uint4*>(gp) = make_uint4(x0, x1, x2, x3);
-                                }
+                            for (int it = 0; it < 8; ++it) {
+                                const int r = it * 4 + rd_row;
+                                float a0, a1, a2, a3;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                                             : "r"(sb + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
+                                if (row0 + r < M && gcol < N)
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + ((int64_t)(row0 + r) * ldo + gcol) * 4),
+                                                 "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+                            }
+                        } else {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int r = it * 4 + rd_row;
+                                uint32_t x0, x1, x2, x3;
+                                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                                             : "r"(sb + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
+                                if (row0 + r < M && gcol < N)
+                                    *reinterpret_cast<uint4*>(gbase + ((int64_t)(row0 + r) * ldo + gcol) * OUT_ESZ) = make_uint4(x0, x1, x2, x3);
                             }
                         }
                     }
