@@ -72,10 +72,11 @@ TAPCLIP_API int tapclip_weights_complete(tapclip_handle h);
 
 /* ---- hot path ------------------------------------------------------------------------------------ */
 /* CLIPWrapper.encode_image (clip_wrapper.py:46-47; row A4): images [B,3,R,R] -> out_feat [B,E] (NOT
- * normalised).  out_cls_rows (nullable): north-star extension, per-layer per-head CLS-row attention
- * probabilities [B, L, H, N] emitted by the attention kernel's probe epilogue. */
+ * normalised).  North-star extensions (not in the reference; nullable): out_cls_rows = per-layer per-head CLS-row
+ * attention probabilities [B, L, H, N] emitted by the attention kernel's probe epilogue; out_rollout = attention
+ * rollout of the CLS token over all L layers, [B, N-1] (Abnar & Zuidema: prod_l (0.5*mean_h P_l + 0.5*I), CLS row). */
 TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int32_t B, float* out_feat, float* out_cls_rows,
-                         void* stream);
+                         float* out_rollout, void* stream);
 
 /* Rows A2,A6-A10 for `C` class prompts at once (model_wrapper.py:32-35,47-75; prompt_learner.py:45-66;
  * attribution_monitor.py:24-34; prompt_adjustor.py:35-36):

@@ -95,6 +95,12 @@ class EngineCLIP(nn.Module):
         """[B,3,R,R] -> [B,E] un-normalised features (open_clip CLIP.encode_image, normalize=False)."""
         return self._engine.encode_image(image.contiguous().float())
 
+    def image_attribution(self, image, rollout=True):
+        """North-star extension (not in the reference): image features plus CLS attention attribution.
+        Returns (features [B,E], cls_rows [B,L,H,N], rollout [B,N-1] or None)."""
+        out = self._engine.encode_image(image.contiguous().float(), want_cls_rows=True, want_rollout=rollout)
+        return out if rollout else (out[0], out[1], None)
+
     def encode_text(self, text):
         raise NotImplementedError(
             "the standard CLIP text path (positional embedding + causal mask + ln_final + EOT pooling) is not on the "

@@ -51,11 +51,12 @@ TAPCLIP_API int tapclip_weights_complete(tapclip_handle h) {
     TC_API_END
 }
 
-TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int32_t B, float* out_feat, float* out_cls_rows, void* stream) {
+TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int32_t B, float* out_feat, float* out_cls_rows,
+                                     float* out_rollout, void* stream) {
     TC_API_BEGIN
     NEED(h);
     TC_CHECK(B == 0 || (images != nullptr && out_feat != nullptr), "null argument");
-    h->impl.encode_image(images, B, out_feat, out_cls_rows, S(stream));
+    h->impl.encode_image(images, B, out_feat, out_cls_rows, out_rollout, S(stream));
     TC_API_END
 }
 

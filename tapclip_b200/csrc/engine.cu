@@ -93,7 +93,7 @@ Engine::~Engine() {
 }
 
 std::vector<DevBuf*> Engine::all_bufs() {
-    return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled,
+    return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled, &v_abar,
             &t_x, &t_ln, &t_qkv, &t_attn, &t_h, &t_pooled, &t_feat, &t_tfeat, &t_inv_norm, &t_probe, &t_attr, &t_attr_raw,
             &t_save_x, &t_save_qkv, &t_save_h, &b_dx, &b_dxc, &b_dh, &b_dln, &b_dattn, &b_dqkv, &b_dfeat, &b_dfeatc, &b_dpool,
             &s_rows, &s_cls};
@@ -305,7 +305,7 @@ void Engine::attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int
 //   stop_after_attention_probs : attribution pass, last block: only the probabilities are needed
 //   save       : keep x copies / qkv / h_pre for the backward pass (slot = layer)
 void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
-                           DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st) {
+                           DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar) {
     const int64_t M = (int64_t)S * N;
     float* sx0 = nullptr; float* sx1 = nullptr; void* sqkv = qkv.p; void* shpre = nullptr;
     if (save_slot >= 0) {
@@ -317,6 +317,7 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
     layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, dt, sx0, M, d, st); ++launches;
     gemm(ln.p, b.w_qkv, b.b_qkv, sqkv, nullptr, M, 3 * d, d, EPI_BF16, ACT_NONE, dt, st);
     attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
+    if (abar) { attention_headmean(sqkv, abar, dt, S, N, H, st); ++launches; }      // rollout extension: head-mean map of this layer
     if (probs_only) return;
     gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, dt, st);
     layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, dt, sx1, M, d, st); ++launches;
@@ -325,7 +326,7 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
 }
 
 // ---- image tower (row A4) ---------------------------------------------------------------------------
-void Engine::encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, cudaStream_t st) {
+void Engine::encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, float* out_rollout, cudaStream_t st) {
     TC_CHECK(B >= 0, "negative batch");
     if (B == 0) return;
     const std::string miss = missing_weights();
@@ -340,6 +341,7 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
     v_attn.ensure(M * d * esz);
     v_h.ensure(M * 4 * d * esz);
     v_pooled.ensure((int64_t)B * d * esz);
+    if (out_rollout) v_abar.ensure((size_t)L * B * N * N * sizeof(float));     // [L, B, N, N] head-mean maps (rollout extension only)
 
     patchify(images, v_patches.p, vdt, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
     gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, vdt, st);
@@ -352,10 +354,12 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
             probe.out = out_cls_rows + (int64_t)l * H * N;
             probe.seq_stride = (int64_t)L * H * N;
         }
-        block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st);
+        block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st,
+                      out_rollout ? (float*)v_abar.p + (int64_t)l * B * N * N : nullptr);
     }
     layernorm_fwd((const float*)v_x.p, (int64_t)N * d, ln_post_g, ln_post_b, v_pooled.p, vdt, nullptr, B, d, st); ++launches;
     gemm(v_pooled.p, w_vproj, nullptr, out_feat, nullptr, B, E, d, EPI_F32, ACT_NONE, vdt, st);
+    if (out_rollout) { attention_rollout((const float*)v_abar.p, out_rollout, B, N, L, st); ++launches; }
 }
 
 // ---- text side (rows A2, A6-A10) ----------------------------------------------------------------------

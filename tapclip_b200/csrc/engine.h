@@ -40,7 +40,7 @@ struct Engine {
     std::vector<BlockWeights> vis, txt;
 
     // workspaces (grow-only)
-    DevBuf v_patches, v_patch_out, v_x, v_ln, v_qkv, v_attn, v_h, v_pooled;
+    DevBuf v_patches, v_patch_out, v_x, v_ln, v_qkv, v_attn, v_h, v_pooled, v_abar;
     DevBuf t_x, t_ln, t_qkv, t_attn, t_h, t_pooled, t_feat, t_tfeat, t_inv_norm, t_probe, t_attr, t_attr_raw;
     DevBuf t_save_x, t_save_qkv, t_save_h;
     DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
@@ -70,8 +70,8 @@ struct Engine {
     void attn_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
     void attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st);
     void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
-                       DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st);
-    void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, cudaStream_t st);
+                       DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar = nullptr);
+    void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, float* out_rollout, cudaStream_t st);
     void text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
                       float* out_text_feat, cudaStream_t st);
     void text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st);

@@ -38,6 +38,10 @@ void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, cons
 // tcgen05 version of attention_fwd for 16-bit inputs and N <= 256 (attention_tc.cu); same contract
 bool attention_fwd_tc_supported(int dt, int N);
 void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream);
+// rollout extension: abar [S, N, N] = head-mean attention probabilities of one layer; attention_rollout propagates the CLS
+// row through all L stored layers (abar_all [L, B, N, N]) and writes out [B, N-1] (CLS -> patch relevance)
+void attention_headmean(const void* qkv, float* abar, int dt, int S, int N, int H, cudaStream_t stream);
+void attention_rollout(const float* abar_all, float* out, int B, int N, int L, cudaStream_t stream);
 // dqkv [S*N, 3*H*64] from d_out [S*N, H*64] and the saved qkv (probabilities recomputed). N <= 128.
 // qkv may be fp16 (mixed mode) while gradients are bf16; fp32 mode: everything fp32.
 void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, int grad_dt, int S, int N, int H,

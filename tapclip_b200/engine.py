@@ -53,7 +53,7 @@ class Engine:
             _lib.check(self.lib.tapclip_weights_complete(self._h))
 
     # ---- hot path -------------------------------------------------------------------------------------
-    def encode_image(self, images: torch.Tensor, want_cls_rows: bool = False):
+    def encode_image(self, images: torch.Tensor, want_cls_rows: bool = False, want_rollout: bool = False):
         _check_cuda_f32(images, "images")
         cfg = self.cfg
         if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != cfg.image_size or images.shape[3] != cfg.image_size:
@@ -63,7 +63,11 @@ class Engine:
         rows = None
         if want_cls_rows:
             rows = torch.empty(B, cfg.vision_layers, cfg.vision_heads, cfg.vision_tokens, device=images.device, dtype=torch.float32)
-        _lib.check(self.lib.tapclip_encode_image(self._h, _lib.ptr(images), B, _lib.ptr(feat), _lib.ptr(rows), _lib.stream_ptr()))
+        roll = torch.empty(B, cfg.vision_tokens - 1, device=images.device, dtype=torch.float32) if want_rollout else None
+        _lib.check(self.lib.tapclip_encode_image(self._h, _lib.ptr(images), B, _lib.ptr(feat), _lib.ptr(rows), _lib.ptr(roll),
+                                                 _lib.stream_ptr()))
+        if want_rollout:
+            return (feat, rows, roll) if want_cls_rows else (feat, roll)
         return (feat, rows) if want_cls_rows else feat
 
     def text_forward(self, ctx: torch.Tensor, tok: torch.Tensor, mode: str, save_for_backward: bool):

@@ -69,12 +69,17 @@ def test_image_features_and_cls_rows_vs_oracle(dtype):
     clip, _ = build_cuda(name, 3, 4, "literal", dtype, ow)
     images = synthetic_images(5, get_config(name).image_size)
     feats_ref, rows_ref = vision_cls_attention(ow.model, images)
-    feats, rows = clip.engine.encode_image(images.cuda(), want_cls_rows=True)
+    from oracle.clip_standin import vision_attention_rollout
+    roll_ref = vision_attention_rollout(ow.model, images)
+    feats, rows, roll = clip.model.image_attribution(images.cuda(), rollout=True)
     torch.cuda.synchronize()
     tol_f, tol_r = (2e-4, 1e-5) if dtype == "fp32" else (5e-2, 5e-3)
     assert max_abs(feats, feats_ref) < tol_f * max(1.0, feats_ref.abs().max().item())
     assert max_abs(rows, rows_ref) < tol_r
     assert (rows.sum(-1) - 1).abs().max().item() < 1e-3
+    # attention rollout (Abnar & Zuidema): CLS -> patch relevance over all layers; rows of the product sum to 1
+    assert roll.shape == roll_ref.shape
+    assert ((roll.cpu() - roll_ref).abs() / roll_ref.abs()).max().item() < (1e-4 if dtype == "fp32" else 2e-2)
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "mixed"])
@@ -98,8 +103,17 @@ def test_other_architectures_vs_oracle(name, B, C, P, dtype):
     e_attr = ((model.last_attribution.cpu() - ref["attribution"]).abs() / ref["attribution"].abs()).max().item()
     g_ref = torch.stack([om.prompt_learner.context_bank[n].grad for n in class_names(C)])
     e_grad = rel_err(ctx_grads(model, C), g_ref)
-    print(f"\n[parity] {name} B={B} C={C} P={P} {dtype}: max|dlogit|={e_logits:.3e} attr_rel={e_attr:.3e} ctx_grad_relL2={e_grad:.3e}")
+    # north-star extension at configs[3] shapes: CLS-row probes and the 24-layer attention rollout (577 tokens -> three key ranges)
+    from oracle.clip_standin import vision_attention_rollout, vision_cls_attention
+    _, rows_ref = vision_cls_attention(ow.model, images)
+    roll_ref = vision_attention_rollout(ow.model, images)
+    _, rows, roll = clip.model.image_attribution(images.cuda(), rollout=True)
+    e_rows = max_abs(rows, rows_ref)
+    e_roll = ((roll.cpu() - roll_ref).abs() / roll_ref.abs()).max().item()
+    print(f"\n[parity] {name} B={B} C={C} P={P} {dtype}: max|dlogit|={e_logits:.3e} attr_rel={e_attr:.3e} ctx_grad_relL2={e_grad:.3e} "
+          f"cls_rows={e_rows:.3e} rollout_rel={e_roll:.3e}")
     assert e_logits <= tol and e_attr <= 1e-3 and e_grad <= GRAD_TOL[dtype]
+    assert e_rows <= (1e-5 if dtype == "fp32" else 5e-3) and e_roll <= (1e-4 if dtype == "fp32" else 3e-2)
 
 
 @pytest.mark.parametrize("B,C,P", [(1, 1, 1), (5, 2, 27), (2, 9, 5)])
