@@ -63,8 +63,8 @@ TAPCLIP_API const char* tapclip_version(void);
 /* Replaces model.load_state_dict (clip_wrapper.py:14-15): one call per open_clip state-dict entry
  * (`visual.conv1.weight`, `visual.transformer.resblocks.3.attn.in_proj_weight`, `text_projection`, ...).
  * `data` is an fp32 device tensor of the given shape; the engine keeps its own converted copy.
- * Entries the hot path does not use (token_embedding.weight, positional_embedding, ln_final.*,
- * logit_scale) are accepted and ignored.  Returns non-zero for unknown names or wrong shapes. */
+ * token_embedding.weight, positional_embedding and ln_final.* are kept for tapclip_encode_text only; logit_scale is
+ * accepted and ignored (FullModel owns its own logit_scale parameter, model_wrapper.py:26).  Returns non-zero for unknown names or wrong shapes. */
 TAPCLIP_API int tapclip_load_weight(tapclip_handle h, const char* name, const float* data, int32_t ndim, const int64_t* shape,
                         void* stream);
 /* Non-zero (with the list of missing entries in last_error) until every weight has been loaded. */
@@ -88,6 +88,11 @@ TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int3
 TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const float* tok, int32_t C, int32_t P, int32_t mode,
                          int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat,
                          void* stream);
+
+/* CLIPWrapper.encode_text (clip_wrapper.py:49-51 -> open_clip CLIP.encode_text; SURVEY 8f rank 1 — FullModel never calls
+ * it): token_ids int64 [S, context_length] (device) -> out_feat [S,E] (NOT normalised): token + positional embedding,
+ * causal transformer, ln_final, pooling at the EOT position (argmax id), @ text_projection. */
+TAPCLIP_API int tapclip_encode_text(tapclip_handle h, const int64_t* token_ids, int32_t S, float* out_feat, void* stream);
 
 /* Rows A5,A11,A12 (model_wrapper.py:41,79,83,90-93): out_img_norm [B,E] = L2-normalised image features,
  * out_logits [B,C] = exp(*logit_scale) * img_norm . text_feat^T.  If labels (int64 [B], device) is

@@ -38,6 +38,7 @@ PROTOTYPES = {
     "tapclip_load_weight": (C.c_int, [_vp, C.c_char_p, _vp, _i32, C.POINTER(_i64), _vp]),
     "tapclip_weights_complete": (C.c_int, [_vp]),
     "tapclip_encode_image": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "tapclip_encode_text": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "tapclip_text_forward": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tapclip_logits": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "tapclip_logits_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),

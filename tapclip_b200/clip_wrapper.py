@@ -102,9 +102,8 @@ class EngineCLIP(nn.Module):
         return out if rollout else (out[0], out[1], None)
 
     def encode_text(self, text):
-        raise NotImplementedError(
-            "the standard CLIP text path (positional embedding + causal mask + ln_final + EOT pooling) is not on the "
-            "TAP-CLIP hot path (FullModel never calls it: models/model_wrapper.py:58,72); SURVEY.md 8f rank 1")
+        """Standard CLIP text path (open_clip CLIP.encode_text, normalize=False): int64 token ids [S, 77] -> [S, E]."""
+        return self._engine.encode_text(text.to(self.text_projection.device))
 
 
 @torch.no_grad()

@@ -26,7 +26,7 @@ constexpr int KC = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 attn_fwd_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, int npad, float scale_log2,
-                    int probe_mode, float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride) {
+                    int probe_mode, float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride, int causal) {
     pdl_wait_and_trigger();
     extern __shared__ __align__(128) uint8_t smem[];
     const int nwarps = blockDim.x >> 5;
@@ -77,7 +77,9 @@ attn_fwd_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H
     const bool cls_probe = cls_any && g == 0;
     float* cls_out = probe_out ? probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N : nullptr;
 
-    for (int kc = 0; kc < npad; kc += KC) {
+    // causal: keys beyond this warp's last query row are all masked, so the key loop stops at the diagonal block
+    const int kend = causal ? min(npad, ((r0 + 16 + KC - 1) / KC) * KC) : npad;
+    for (int kc = 0; kc < kend; kc += KC) {
         float sc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f; }
@@ -93,7 +95,7 @@ attn_fwd_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H
             }
         }
         float mx0 = -INFINITY, mx1 = -INFINITY;
-        if (kc + KC < N && !cls_any) {
+        if (kc + KC < N && !cls_any && !(causal && kc + KC > r0)) {
             // interior chunk (warp-uniform): no masking, no probe bookkeeping
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
@@ -109,6 +111,7 @@ attn_fwd_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H
                     const int key = kc + nb * 8 + tq * 2 + e;
                     float v0 = sc[nb][e] * scale_log2, v1 = sc[nb][e + 2] * scale_log2;
                     if (key >= N) { v0 = -INFINITY; v1 = -INFINITY; }
+                    if (causal) { if (key > r0 + g) v0 = -INFINITY; if (key > r0 + g + 8) v1 = -INFINITY; }
                     if (key == N - 1) { ps0 = v0; ps1 = v1; }
                     if (cls_probe && key < N) cls_out[key] = v0;
                     sc[nb][e] = v0; sc[nb][e + 2] = v1;
@@ -195,7 +198,7 @@ constexpr int KMAX = 19;   // keys per lane -> N <= 608
 template <typename T>
 __global__ void __launch_bounds__(128)
 attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, float scale, int probe_mode,
-                     float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride) {
+                     float* __restrict__ probe_out, int probe_P, int64_t probe_seq_stride, int causal) {
     pdl_wait_and_trigger();
     __shared__ float qs[4][DH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,7 +216,7 @@ attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int 
     for (int kk = 0; kk < KMAX; ++kk) {
         const int key = kk * 32 + lane;
         float v = -INFINITY;
-        if (key < N) {
+        if (key < N && !(causal && key > row)) {
             const T* kp = base + (int64_t)key * 3 * d + d;
             float acc = 0.f;
 #pragma unroll 8
@@ -227,7 +230,7 @@ attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int 
     float sum = 0.f;
 #pragma unroll
     for (int kk = 0; kk < KMAX; ++kk) {
-        const float e = (kk * 32 + lane < N) ? expf(pr[kk] - mx) : 0.f;
+        const float e = (kk * 32 + lane < N && !(causal && kk * 32 + lane > row)) ? expf(pr[kk] - mx) : 0.f;
         pr[kk] = e;
         sum += e;
     }
@@ -813,7 +816,7 @@ void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, cons
     // auto: the persistent tcgen05 kernel for N <= 208 when there are enough (sequence, head, q-tile) items to keep its
     // two softmax groups per SM busy (ViT-B/16 at B=128: 3072 items, 98 us vs 102 us); the mma.sync flash kernel for long
     // sequences (ViT-L/14@336) and for small problems such as the C=65 text tower (520 items: 10.5 us vs 12.8 us)
-    if (impl == 2 || (impl == 0 && attention_fwd_tc_supported(dt, N) && N <= 208 && (int64_t)S * H * ((N + 127) / 128) >= 1024)) {
+    if (!probe.causal && (impl == 2 || (impl == 0 && attention_fwd_tc_supported(dt, N) && N <= 208 && (int64_t)S * H * ((N + 127) / 128) >= 1024))) {
         attention_fwd_tc(qkv, out, dt, S, N, H, probe, stream);
         return;
     }
@@ -833,13 +836,13 @@ void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, cons
         }
         dim3 grid((unsigned)(S * H), (unsigned)nz);
         const float sl2 = 0.125f * 1.4426950408889634f;
-        if (which) launch_pdl(attn_fwd_mma_kernel<f16>, grid, nwarps * 32, smem, stream, (const f16*)qkv, (f16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
-        else launch_pdl(attn_fwd_mma_kernel<bf16>, grid, nwarps * 32, smem, stream, (const bf16*)qkv, (bf16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        if (which) launch_pdl(attn_fwd_mma_kernel<f16>, grid, nwarps * 32, smem, stream, (const f16*)qkv, (f16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, (int)probe.causal);
+        else launch_pdl(attn_fwd_mma_kernel<bf16>, grid, nwarps * 32, smem, stream, (const bf16*)qkv, (bf16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, (int)probe.causal);
     } else {
         TC_CHECK(N <= KMAX * 32, "sequence length %d too long for the fp32 attention kernel", N);
         dim3 grid((unsigned)ceil_div(N, 4), (unsigned)(S * H));
         launch_pdl(attn_fwd_simt_kernel<float>, grid, 128, 0, stream, (const float*)qkv, (float*)out, N, H, 0.125f, probe.mode, probe.out,
-                                                              probe.P, probe.seq_stride);
+                   probe.P, probe.seq_stride, (int)probe.causal);
     }
     TC_LAUNCH_CHECK();
 }

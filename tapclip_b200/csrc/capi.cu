@@ -69,6 +69,14 @@ TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const f
     TC_API_END
 }
 
+TAPCLIP_API int tapclip_encode_text(tapclip_handle h, const int64_t* token_ids, int32_t n_seq, float* out_feat, void* stream) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(n_seq == 0 || (token_ids != nullptr && out_feat != nullptr), "null argument");
+    h->impl.encode_text(token_ids, n_seq, out_feat, S(stream));
+    TC_API_END
+}
+
 TAPCLIP_API int tapclip_logits(tapclip_handle h, const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels,
                    int32_t B, int32_t C, float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss,
                    float* out_dlogits, void* stream) {

@@ -161,6 +161,37 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, T* __restrict__ 
     }
 }
 
+// open_clip CLIP.encode_text prologue: x = token_embedding(text) + positional_embedding; EOT position = argmax of the ids
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const float* __restrict__ emb, const float* __restrict__ pos,
+                                    float* __restrict__ x, int32_t* __restrict__ eot, int S, int L, int D) {
+    pdl_wait_and_trigger();
+    const int s = blockIdx.x;
+    const int d4 = D >> 2;
+    for (int i = threadIdx.x; i < L * d4; i += blockDim.x) {
+        const int t = i / d4, c = (i % d4) * 4;
+        const int64_t id = ids[(int64_t)s * L + t];
+        float4 v = __ldg(reinterpret_cast<const float4*>(emb + id * D + c));
+        const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)t * D + c));
+        v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
+        *reinterpret_cast<float4*>(x + ((int64_t)s * L + t) * D + c) = v;
+    }
+    if (threadIdx.x == 0) {
+        int best = 0; int64_t bv = ids[(int64_t)s * L];
+        for (int t = 1; t < L; ++t) { const int64_t v = ids[(int64_t)s * L + t]; if (v > bv) { bv = v; best = t; } }   // first max, as torch.argmax
+        eot[s] = best;
+    }
+}
+
+__global__ void gather_rows_indexed_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, float* __restrict__ out,
+                                           int64_t rows, int64_t row_stride, int d) {
+    pdl_wait_and_trigger();
+    const int64_t total = rows * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d;
+        out[i] = x[(r * row_stride + idx[r]) * d + (i % d)];
+    }
+}
+
 template <typename T>
 __global__ void scatter_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, T* __restrict__ dst_cast,
                                     int64_t rows, int64_t row_stride, int64_t row_offset, int d) {
@@ -362,6 +393,19 @@ void gather_rows(const float* x, void* out, int out_dt, int64_t rows, int64_t ro
     if (out_dt == DT_BF16) launch_pdl(gather_rows_kernel<bf16>, grid_for(rows * d), 256, 0, stream, x, (bf16*)out, rows, row_stride, row_offset, d);
     else if (out_dt == DT_F16) launch_pdl(gather_rows_kernel<f16>, grid_for(rows * d), 256, 0, stream, x, (f16*)out, rows, row_stride, row_offset, d);
     else launch_pdl(gather_rows_kernel<float>, grid_for(rows * d), 256, 0, stream, x, (float*)out, rows, row_stride, row_offset, d);
+    TC_LAUNCH_CHECK();
+}
+
+void embed_tokens(const int64_t* ids, const float* token_embedding, const float* pos, float* x, int32_t* eot, int S, int L, int D,
+                  cudaStream_t stream) {
+    if (S == 0) return;
+    launch_pdl(embed_tokens_kernel, S, 256, 0, stream, ids, token_embedding, pos, x, eot, S, L, D);
+    TC_LAUNCH_CHECK();
+}
+
+void gather_rows_indexed(const float* x, const int32_t* idx, float* out, int64_t rows, int64_t row_stride, int d, cudaStream_t stream) {
+    if (rows == 0) return;
+    launch_pdl(gather_rows_indexed_kernel, grid_for(rows * d), 256, 0, stream, x, idx, out, rows, row_stride, d);
     TC_LAUNCH_CHECK();
 }
 

@@ -96,7 +96,7 @@ std::vector<DevBuf*> Engine::all_bufs() {
     return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled, &v_abar,
             &t_x, &t_ln, &t_qkv, &t_attn, &t_h, &t_pooled, &t_feat, &t_tfeat, &t_inv_norm, &t_probe, &t_attr, &t_attr_raw,
             &t_save_x, &t_save_qkv, &t_save_h, &b_dx, &b_dxc, &b_dh, &b_dln, &b_dattn, &b_dqkv, &b_dfeat, &b_dfeatc, &b_dpool,
-            &s_rows, &s_cls};
+            &s_rows, &s_cls, &e_eot, &e_pool};
 }
 
 int64_t Engine::workspace_bytes() {
@@ -143,10 +143,12 @@ void Engine::load_weight(const std::string& name, const float* data, int ndim, c
         os << "]";
         throw Error{os.str()};
     };
-    // entries the hot path does not use
-    if (name == "token_embedding.weight" || name == "positional_embedding" || name == "ln_final.weight" ||
-        name == "ln_final.bias" || name == "logit_scale" || name == "attn_mask")
-        return;
+    // entries only the standard CLIP text path (encode_text) uses
+    if (name == "token_embedding.weight") { if (ndim != 2 || shape[1] != dt) bad_shape(); vocab = (int)shape[0]; tok_emb = (float*)store(name, data, (int)shape[0], dt, dt, false, DT_F32, st); return; }
+    if (name == "positional_embedding") { if (!shape_is(ndim, shape, {cfg.context_length, dt})) bad_shape(); text_pos = (float*)store(name, data, cfg.context_length, dt, dt, false, DT_F32, st); return; }
+    if (name == "ln_final.weight") { if (!shape_is(ndim, shape, {dt})) bad_shape(); ln_final_g = (float*)store(name, data, 1, dt, dt, false, DT_F32, st); return; }
+    if (name == "ln_final.bias") { if (!shape_is(ndim, shape, {dt})) bad_shape(); ln_final_b = (float*)store(name, data, 1, dt, dt, false, DT_F32, st); return; }
+    if (name == "logit_scale" || name == "attn_mask") return;        // not used by any path
     if (name == "visual.conv1.weight") {
         if (!shape_is(ndim, shape, {dv, 3, cfg.patch_size, cfg.patch_size})) bad_shape();
         w_patch = store(name, data, dv, kpatch, kpatch_pad, false, vdt, st);
@@ -424,6 +426,36 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
     l2norm_fwd((const float*)t_feat.p, (float*)t_tfeat.p, (float*)t_inv_norm.p, C, E, st); ++launches;
     if (out_text_feat) TC_CUDA(cudaMemcpyAsync(out_text_feat, t_tfeat.p, (size_t)C * E * 4, cudaMemcpyDeviceToDevice, st));
     if (save) { saved.valid = true; saved.C = C; saved.P = P; saved.T = T; saved.PA = PA; saved.has_attr = (mode == 1); }
+}
+
+// ---- standard CLIP text path (CLIPWrapper.encode_text, clip_wrapper.py:49-51; never called by FullModel) ---------------
+// open_clip CLIP.encode_text: token + positional embedding, causal transformer, ln_final, EOT (argmax id) pooling, projection.
+void Engine::encode_text(const int64_t* ids, int S, float* out_feat, cudaStream_t st) {
+    if (S == 0) return;
+    const std::string miss = missing_weights();
+    TC_CHECK(miss.empty(), "weights missing: %s", miss.c_str());
+    TC_CHECK(tok_emb && text_pos && ln_final_g && ln_final_b, "encode_text needs token_embedding.weight, positional_embedding and ln_final.*");
+    const int D = cfg.text_width, H = cfg.text_heads, T = cfg.context_length, L = cfg.text_layers, E = cfg.embed_dim;
+    const int64_t M = (int64_t)S * T;
+    t_x.ensure(M * D * 4);
+    t_ln.ensure(M * D * esz);
+    t_qkv.ensure(M * 3 * D * esz);
+    t_attn.ensure(M * D * esz);
+    t_h.ensure(M * 4 * D * esz);
+    t_pooled.ensure((int64_t)S * D * esz);
+    e_eot.ensure((size_t)S * 4);
+    e_pool.ensure((size_t)S * D * 4);
+    saved.valid = false;                                  // shares the text workspaces with text_forward
+    float* x = (float*)t_x.p;
+    embed_tokens(ids, tok_emb, text_pos, x, (int32_t*)e_eot.p, S, T, D, st); ++launches;
+    for (int l = 0; l < L; ++l) {
+        AttnProbe causal;
+        causal.causal = true;
+        block_forward(txt[l], x, S, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, causal, false, -1, st);
+    }
+    gather_rows_indexed(x, (const int32_t*)e_eot.p, (float*)e_pool.p, S, T, D, st); ++launches;
+    layernorm_fwd((const float*)e_pool.p, D, ln_final_g, ln_final_b, t_pooled.p, tdt, nullptr, S, D, st); ++launches;
+    gemm(t_pooled.p, w_tproj, nullptr, out_feat, nullptr, S, E, D, EPI_F32, ACT_NONE, tdt, st);
 }
 
 // ---- backward to ctx (row A13) ---------------------------------------------------------------------------

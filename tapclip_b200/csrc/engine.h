@@ -30,13 +30,14 @@ struct Engine {
     int tdt = DT_BF16;          // ... of the text-tower forward (fp16 in mixed mode: see DESIGN.md "Precision")
     int gdt = DT_BF16;          // ... of the backward pass (gradients are never fp16)
     int esz = 2;                // bytes per activation element (same for all three)
-    int grid = 0, n_tok = 0, kpatch = 0, kpatch_pad = 0;
+    int grid = 0, n_tok = 0, kpatch = 0, kpatch_pad = 0, vocab = 0;
     int64_t launches = 0;
 
     std::map<std::string, void*> weights;     // owning storage, keyed by state-dict name (+"#T" for transposes)
     void* w_patch = nullptr; float* cls_emb = nullptr; float* pos_emb = nullptr;
     float *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
     void *w_vproj = nullptr, *w_tproj = nullptr, *wt_tproj = nullptr;
+    float *tok_emb = nullptr, *text_pos = nullptr, *ln_final_g = nullptr, *ln_final_b = nullptr;   // standard encode_text only
     std::vector<BlockWeights> vis, txt;
 
     // workspaces (grow-only)
@@ -44,7 +45,7 @@ struct Engine {
     DevBuf t_x, t_ln, t_qkv, t_attn, t_h, t_pooled, t_feat, t_tfeat, t_inv_norm, t_probe, t_attr, t_attr_raw;
     DevBuf t_save_x, t_save_qkv, t_save_h;
     DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
-    DevBuf s_rows, s_cls;
+    DevBuf s_rows, s_cls, e_eot, e_pool;
     struct { bool valid = false; int C = 0, P = 0, T = 0, PA = 1; bool has_attr = false; } saved;
 
     // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline numbers)
@@ -75,6 +76,7 @@ struct Engine {
     void text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
                       float* out_text_feat, cudaStream_t st);
     void text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st);
+    void encode_text(const int64_t* ids, int S, float* out_feat, cudaStream_t st);
     void logits(const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels, int B, int C,
                 float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss, float* out_dlogits, cudaStream_t st);
     void logits_backward(const float* dlogits, const float* logits_, const float* img_norm, const float* logit_scale, int B, int C,

@@ -29,6 +29,7 @@ struct AttnProbe {
                                  // out[s*seq_stride + h*N + n]
     int P = 0;
     int64_t seq_stride = 0;
+    bool causal = false;         // key j visible to query i only if j <= i (standard CLIP text tower, encode_text)
 };
 // qkv [S*N, 3*H*64] (packed in_proj output, activation type) -> out [S*N, H*64]; softmax(QK^T/8)V, no mask.
 // bf16 / fp16: mma.sync tensor-core flash kernel; fp32: SIMT kernel.  Probabilities asked for by `probe` are
@@ -59,6 +60,11 @@ void splice_prompts(const float* ctx, const float* tok, const float* attr, int a
 // dctx[c,t,:] = dx[c,t,:] * attr[c,...]  for t<P
 void splice_bwd(const float* dx, const float* attr, int attr_p, float* dctx, int C, int P, int T, int D,
                 cudaStream_t stream);
+// x[s,t,:] = token_embedding[ids[s,t],:] + pos[t,:];  eot[s] = argmax_t ids[s,t]   (open_clip CLIP.encode_text prologue)
+void embed_tokens(const int64_t* ids, const float* token_embedding, const float* pos, float* x, int32_t* eot, int S, int L, int D,
+                  cudaStream_t stream);
+// out[r,:] = x[(r*row_stride + idx[r]),:]   (fp32 gather of one row per sequence)
+void gather_rows_indexed(const float* x, const int32_t* idx, float* out, int64_t rows, int64_t row_stride, int d, cudaStream_t stream);
 // raw[c,p] = mean_h probe[c,h,p];  attr[c,:] = softmax_p(raw[c,:])      (K3)
 void attribution_reduce(const float* probe, float* raw, float* attr, int C, int H, int P, cudaStream_t stream);
 // out[r,:] = cast(x[(r*row_stride + row_offset),:])

@@ -70,6 +70,14 @@ class Engine:
             return (feat, rows, roll) if want_cls_rows else (feat, roll)
         return (feat, rows) if want_cls_rows else feat
 
+    def encode_text(self, token_ids: torch.Tensor):
+        if token_ids.dtype != torch.int64 or not token_ids.is_cuda or token_ids.dim() != 2 or token_ids.shape[1] != self.cfg.context_length:
+            raise ValueError(f"token ids must be an int64 CUDA tensor [S, {self.cfg.context_length}], got {tuple(token_ids.shape)} {token_ids.dtype}")
+        ids = token_ids.contiguous()
+        feat = torch.empty(ids.shape[0], self.cfg.embed_dim, device=ids.device, dtype=torch.float32)
+        _lib.check(self.lib.tapclip_encode_text(self._h, _lib.ptr(ids), ids.shape[0], _lib.ptr(feat), _lib.stream_ptr()))
+        return feat
+
     def text_forward(self, ctx: torch.Tensor, tok: torch.Tensor, mode: str, save_for_backward: bool):
         _check_cuda_f32(ctx, "ctx")
         _check_cuda_f32(tok, "tok")

@@ -115,6 +115,21 @@ def test_eval_text_feature_cache_and_argmax():
     assert torch.equal(pred, l1.argmax(1)) and correct.item() == (l1.argmax(1) == labels).sum().item()
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "mixed"])
+def test_standard_encode_text_path(dtype):
+    """CLIPWrapper.encode_text (clip_wrapper.py:49-51): positional embedding + causal mask + ln_final + EOT pooling."""
+    ow, _ = build_oracle("mini-16", 2, 4, "literal")
+    clip, _ = build_cuda("mini-16", 2, 4, "literal", dtype, ow)
+    texts = ["a photo of a cat", "a photo of a very tall giraffe eating leaves", "x"]
+    ids = ow.get_tokenizer()(texts)
+    with torch.no_grad():
+        ref = ow.encode_text(ids)
+    out = clip.encode_text(ids.cuda())
+    assert clip.attention_maps == []                       # encode_text resets the probe cache (clip_wrapper.py:50)
+    tol = 1e-4 if dtype == "fp32" else 2e-2
+    assert max_abs(out, ref) < tol * max(1.0, ref.abs().max().item())
+
+
 def test_logits_only_backward_path():
     """A caller that builds its own loss from outputs['logits'] (not outputs['loss']) still gets ctx gradients."""
     ow, om, clip, model = _mini(mode="literal", dtype="fp32")
