@@ -29,10 +29,11 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                        // two epilogue warps per TMEM lane quarter, alternating column chunks
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int STAGE_A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int EPI_BUF_BYTES = 32 * 128;             // 32 rows x 128 B, one TMA-store box
-constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES;    // 4 warps x 2 buffers
+constexpr int EPI_BYTES = EPI_WARPS * EPI_BUF_BYTES; // one staging buffer per epilogue warp
 
 template <int BLOCK_N, bool CTA2> struct Cfg {
     static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;          // rows of W this CTA stages per k-block
@@ -94,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 8 : 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 2 * EPI_WARPS : EPI_WARPS); }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
@@ -173,18 +174,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // nothing in this loop waits on the memory system except the tcgen05.ld itself.
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int ew = warp - 2;
-        const uint32_t stage_u32 = smem_u32(smem_epi + ew * 2 * EPI_BUF_BYTES);
+        const int chunk_par = ew >> 2;                       // this warp handles the chunks with (c & 1) == chunk_par
+        const uint32_t stage_u32 = smem_u32(smem_epi + ew * EPI_BUF_BYTES);
         const uint32_t row_off = (uint32_t)lane * 128u;
         const uint32_t sw = (uint32_t)(lane & 7);
         const int rd_row = lane >> 3, rd_ch = lane & 7;      // read-back mapping: 8 lanes cover one 128-byte row
         int acc = 0; uint32_t acc_phase = 0;
-        int buf = 0;
         for (int tile = unit; tile < num_tiles; tile += num_units) {
             const int m0 = (tile / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
             if (bias != nullptr) {
                 // stage this tile's bias in smem while the MMAs of the tile are still running (a global load per
                 // chunk inside the epilogue loop exposed its full latency: ncu long_scoreboard on the bias FADDs)
-                asm volatile("bar.sync 1, 128;" ::: "memory");               // everyone is done with the previous tile's bias
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // everyone is done with the previous tile's bias
                 const int et = (int)threadIdx.x - 64;
                 if (et < BLOCK_N / 4) {
                     const int col = n0 + et * 4;
@@ -192,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (col < N) b = __ldg(reinterpret_cast<const float4*>(bias + col));
                     *reinterpret_cast<float4*>(bias_s + et * 4) = b;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -200,8 +201,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int row0 = m0 + q * 32;
             constexpr int CH = (EPI == EPI_BF16) ? 64 : 32;  // columns per 128-byte staging row
             constexpr int OUT_ESZ = (EPI == EPI_BF16) ? 2 : 4;
+            constexpr int NCHUNK = BLOCK_N / CH;
+            constexpr int LAST_MINE = NCHUNK - 2;            // last chunk index (before adding chunk_par) of each warp
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / CH; ++c) {
+            for (int c = chunk_par; c < NCHUNK; c += 2) {
                 float v[CH];
                 {
                     uint32_t r0[32];
@@ -218,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
                     }
                 }
-                if (c == BLOCK_N / CH - 1) {                 // all TMEM reads of this tile are done
+                if (c >= LAST_MINE) {                        // this warp's TMEM reads of the tile are done
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0)); else mbar_arrive(&tmem_empty[acc]); }
@@ -240,8 +243,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < CH; ++j) v[j] = act_fwd_fast<ACT>(v[j]);
                     }
-                    const uint32_t sb = stage_u32 + buf * EPI_BUF_BYTES;
-                    buf ^= 1;
+                    const uint32_t sb = stage_u32;
+                    __syncwarp();                                     // previous read-back of the staging buffer is complete
                     // registers -> swizzled staging (conflict-free 16-byte shared stores)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -283,11 +286,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
                                              : "r"(sb + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
                                 if (row0 + r < M && gcol < N)
-                                    *reinterpret_cast<uint4*>(gbase + ((int64_t)(row0 + r) * ldo + gcol) * OUT_ESZ) = make_uint4(x0, x1, x2, x3);
+                                    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + ((int64_t)(row0 + r) * ldo + gcol) * OUT_ESZ),
+                                                 "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");   // streaming: keep A/W resident in L2
                             }
                         }
                     }
-                    // the other staging buffer is used next; this one is re-used two passes later, after a __syncwarp
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
