@@ -134,7 +134,9 @@ TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
 
 /* ---- single-kernel entry points (used by the per-kernel parity tests and micro-benchmarks) -------- */
 /* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias).  dtype BF16/FP16: A,W (and epi-0 out) 16-bit, tcgen05 path; FP32: SIMT path.
- * epi: 0 = store activation type (+act, optional out_pre), 1 = store fp32, 2 = fp32 += .
+ * epi: 0 = store activation type (+act, optional out_pre), 1 = store fp32, 2 = fp32 += ,
+ *      3 = out = (A.W^T + bias) * act'(out_pre) with out_pre READ as the saved pre-activations (same 16-bit type as A),
+ *      4 = as 3 with bf16 A/W/out and fp16 out_pre (the mixed mode's MLP dgrad).  3/4: bf16 A/W, block_n 0|128|256 only.
  * block_n: 0 = choose | 128 | 256 (single-CTA tiles) | 512 (2-CTA cta_group::2 pairs on 256x256 tiles) */
 TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N,
                     int64_t K, int32_t dtype, int32_t epi, int32_t act, int32_t block_n, void* stream);

@@ -140,7 +140,8 @@ TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias,
     TC_API_BEGIN
     GemmArgs g;
     g.a = a; g.w = w; g.bias = bias; g.out = out; g.out_pre = out_pre;
-    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.block_n = block_n; g.dt = dtype;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.block_n = block_n; g.dt = dtype; g.aux_dt = dtype;
+    if (epi == 4) { g.epi = EPI_BF16_ACTGRAD; g.aux_dt = DT_F16; }   // bf16 gradients against fp16 saved pre-activations (mixed mode)
     if (dtype != DT_F32) gemm_tc(g, S(stream));
     else gemm_simt_f32(g, S(stream));
     TC_API_END

@@ -274,10 +274,10 @@ const char* Engine::profile_report() {
 
 // ---- primitive wrappers ------------------------------------------------------------------------------
 void Engine::gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K,
-                  int epi, int act, int dt, cudaStream_t st) {
+                  int epi, int act, int dt, cudaStream_t st, int aux_dt) {
     GemmArgs g;
     g.a = a; g.w = w; g.bias = bias; g.out = out; g.out_pre = out_pre;
-    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.dt = dt;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.dt = dt; g.aux_dt = aux_dt;
     ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, epi};
     if (profiling) prof_begin(r, st);
     if (dt != DT_F32) gemm_tc(g, st);
@@ -486,8 +486,13 @@ void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream
         const void* qkv = (const uint8_t*)t_save_qkv.p + (int64_t)l * M * 3 * D * esz;
         const void* hpre = (const uint8_t*)t_save_h.p + (int64_t)l * M * 4 * D * esz;
         // MLP branch
-        gemm(b_dxc.p, b.wt_proj, nullptr, b_dh.p, nullptr, M, 4 * D, D, EPI_BF16, ACT_NONE, gdt, st);
-        act_bwd_inplace(b_dh.p, gdt, hpre, tdt, cfg.act, M * 4 * D, st); ++launches;
+        if (gdt != DT_F32) {
+            // dh = (dx . W_proj) * act'(h_pre): the activation derivative is applied in the dgrad GEMM's store stage
+            gemm(b_dxc.p, b.wt_proj, nullptr, b_dh.p, const_cast<void*>(hpre), M, 4 * D, D, EPI_BF16_ACTGRAD, cfg.act, gdt, st, tdt);
+        } else {
+            gemm(b_dxc.p, b.wt_proj, nullptr, b_dh.p, nullptr, M, 4 * D, D, EPI_BF16, ACT_NONE, gdt, st);
+            act_bwd_inplace(b_dh.p, gdt, hpre, tdt, cfg.act, M * 4 * D, st); ++launches;
+        }
         gemm(b_dh.p, b.wt_fc, nullptr, b_dln.p, nullptr, M, D, 4 * D, EPI_F32, ACT_NONE, gdt, st);
         layernorm_bwd((const float*)b_dln.p, x1, b.ln2_g, (float*)b_dx.p, b_dxc.p, gdt, M, D, st); ++launches;
         // attention branch

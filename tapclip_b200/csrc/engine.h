@@ -67,7 +67,7 @@ struct Engine {
     std::string missing_weights() const;
 
     void gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int epi,
-              int act, int dt, cudaStream_t st);
+              int act, int dt, cudaStream_t st, int aux_dt = DT_BF16);
     void attn_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
     void attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st);
     void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,

@@ -9,6 +9,8 @@ enum Epi : int {
     EPI_BF16 = 0,      // out (bf16) = act(acc + bias);  optional out_pre (bf16) = acc + bias
     EPI_F32 = 1,       // out (f32)  = acc + bias
     EPI_F32_ADD = 2,   // out (f32) += acc + bias        (residual stream update)
+    EPI_BF16_ACTGRAD = 3,  // out (bf16) = (acc + bias) * act'(out_pre)   (dgrad through the MLP activation; out_pre is READ:
+                           // the saved 16-bit pre-activations, type aux_dt, same [M,N] layout and leading dimension as out)
 };
 
 struct GemmArgs {
@@ -22,6 +24,7 @@ struct GemmArgs {
     int epi = EPI_F32;
     int act = ACT_NONE;
     int block_n = 0;           // 0 = choose; 128 / 256 = 128 x block_n single-CTA tiles; 512 = 2-CTA pairs, 256 x 256 tiles
+    int aux_dt = DT_BF16;      // EPI_BF16_ACTGRAD: type of the pre-activations behind out_pre (DT_BF16 or DT_F16)
     int dt = DT_BF16;          // tcgen05 path: 16-bit type of A, W and of the EPI_BF16 output (DT_BF16 or DT_F16)
 };
 

@@ -61,12 +61,25 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool f16) {
            ((uint32_t)(m >> 4) << 24);
 }
 
+// two packed 16-bit values x (type T16) times act'(h) of two packed pre-activations h (fp16 if h_f16 else bf16)
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack2<bf16>(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+template <> __device__ __forceinline__ float2 unpack2<f16>(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+template <int ACT, typename T16>
+__device__ __forceinline__ uint32_t mul_act_grad(uint32_t x, uint32_t h, int h_f16) {
+    const float2 xf = unpack2<T16>(x);
+    const float2 hf = h_f16 ? unpack2<f16>(h) : unpack2<bf16>(h);
+    return pack2<T16>(xf.x * act_bwd_fast<ACT>(hf.x), xf.y * act_bwd_fast<ACT>(hf.y));
+}
+
 template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                void* out, void* out_pre, int ldo,
-               const float* __restrict__ bias, int M, int N, int K, int dbg) {
+               const float* __restrict__ bias, int M, int N, int K, int dbg, int aux_f16) {
     using C = Cfg<BLOCK_N, CTA2>;
+    constexpr bool ACTGRAD = (EPI == EPI_BF16_ACTGRAD);      // out = (acc + bias) * act'(aux), aux = out_pre pointer, same layout as out
+    constexpr bool OUT16 = (EPI == EPI_BF16) || ACTGRAD;
     using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -199,8 +212,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
             const int row0 = m0 + q * 32;
-            constexpr int CH = (EPI == EPI_BF16) ? 64 : 32;  // columns per 128-byte staging row
-            constexpr int OUT_ESZ = (EPI == EPI_BF16) ? 2 : 4;
+            constexpr int CH = OUT16 ? 64 : 32;  // columns per 128-byte staging row
+            constexpr int OUT_ESZ = OUT16 ? 2 : 4;
             constexpr int NCHUNK = BLOCK_N / CH;
             constexpr int LAST_MINE = NCHUNK - 2;            // last chunk index (before adding chunk_par) of each warp
 #pragma unroll 1
@@ -236,10 +249,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 if (row0 >= M || col0 >= N || dbg == 2) continue;
                 constexpr int NPASS = (EPI == EPI_BF16 && STORE_PRE) ? 2 : 1;
+                uint4 hq[ACTGRAD ? 8 : 1];
+                if constexpr (ACTGRAD) {
+                    // the saved pre-activations of this chunk, fetched with the same coalesced (row, 16-byte) mapping the
+                    // stores below use; issued now so their latency hides behind the staging round trip
+                    const uint8_t* hbase = reinterpret_cast<const uint8_t*>(out_pre);
+                    const int hcol = col0 + rd_ch * 8;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + rd_row;
+                        hq[it] = make_uint4(0u, 0u, 0u, 0u);
+                        if (row0 + r < M && hcol < N)
+                            hq[it] = __ldg(reinterpret_cast<const uint4*>(hbase + ((int64_t)(row0 + r) * ldo + hcol) * 2));
+                    }
+                }
 #pragma unroll
                 for (int pass = 0; pass < NPASS; ++pass) {
                     const bool is_pre = STORE_PRE && pass == 0;       // first pass of STORE_PRE writes the pre-activation copy
-                    if (!is_pre) {
+                    if (!is_pre && !ACTGRAD) {
 #pragma unroll
                         for (int j = 0; j < CH; ++j) v[j] = act_fwd_fast<ACT>(v[j]);
                     }
@@ -249,7 +276,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         uint32_t p0, p1, p2, p3;
-                        if constexpr (EPI == EPI_BF16) {
+                        if constexpr (OUT16) {
                             p0 = pack2<T16>(v[8 * j + 0], v[8 * j + 1]); p1 = pack2<T16>(v[8 * j + 2], v[8 * j + 3]);
                             p2 = pack2<T16>(v[8 * j + 4], v[8 * j + 5]); p3 = pack2<T16>(v[8 * j + 6], v[8 * j + 7]);
                         } else {
@@ -285,6 +312,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                 uint32_t x0, x1, x2, x3;
                                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
                                              : "r"(sb + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
+                                if constexpr (ACTGRAD) {
+                                    x0 = mul_act_grad<ACT, T16>(x0, hq[it].x, aux_f16); x1 = mul_act_grad<ACT, T16>(x1, hq[it].y, aux_f16);
+                                    x2 = mul_act_grad<ACT, T16>(x2, hq[it].z, aux_f16); x3 = mul_act_grad<ACT, T16>(x3, hq[it].w, aux_f16);
+                                }
                                 if (row0 + r < M && gcol < N)
                                     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + ((int64_t)(row0 + r) * ldo + gcol) * OUT_ESZ),
                                                  "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");   // streaming: keep A/W resident in L2
@@ -392,9 +423,9 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
     }
     const CUtensorMap& ta = make_tmap(g.a, DT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K);
     const CUtensorMap& tb = make_tmap(g.w, DT16, 2, g.N, g.K, g.ldw, C::B_ROWS, BLOCK_K);
-    const int out_esz = (EPI == EPI_BF16) ? 2 : 4;
+    const int out_esz = (EPI == EPI_BF16 || EPI == EPI_BF16_ACTGRAD) ? 2 : 4;
     TC_CHECK((reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && (g.ldo * out_esz) % 16 == 0, "GEMM output must be 16-byte aligned with a 16-byte row pitch");
-    if (STORE_PRE) TC_CHECK((reinterpret_cast<uintptr_t>(g.out_pre) & 15) == 0, "GEMM pre-activation output must be 16-byte aligned");
+    if (STORE_PRE || EPI == EPI_BF16_ACTGRAD) TC_CHECK((reinterpret_cast<uintptr_t>(g.out_pre) & 15) == 0, "GEMM pre-activation output must be 16-byte aligned");
     if (CTA2) {
         const int64_t tiles = ceil_div(g.M, 2 * BLOCK_M) * ceil_div(g.N, BLOCK_N);
         const int clusters = (int)std::min<int64_t>(tiles, g_num_sms / 2);
@@ -409,11 +440,11 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        TC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug));
+        TC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug, (int)(g.aux_dt == DT_F16)));
     } else {
         const int64_t tiles = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, BLOCK_N);
         const int grid = (int)std::min<int64_t>(tiles, g_num_sms);
-        launch_pdl(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug);
+        launch_pdl(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug, (int)(g.aux_dt == DT_F16));
     }
     TC_LAUNCH_CHECK();
 }
@@ -422,6 +453,15 @@ template <int BLOCK_N, bool F16, bool CTA2>
 void dispatch(const GemmArgs& g, cudaStream_t stream) {
     if (g.epi == EPI_F32) return launch<BLOCK_N, EPI_F32, ACT_NONE, false, F16, CTA2>(g, stream);
     if (g.epi == EPI_F32_ADD) return launch<BLOCK_N, EPI_F32_ADD, ACT_NONE, false, F16, CTA2>(g, stream);
+    if (g.epi == EPI_BF16_ACTGRAD) {
+        // dgrad through the MLP activation: out = (A W^T) * act'(out_pre); only the shapes the backward uses are built
+        TC_CHECK(g.out_pre != nullptr && (g.aux_dt == DT_BF16 || g.aux_dt == DT_F16), "activation-gradient epilogue needs 16-bit pre-activations in out_pre");
+        if constexpr (!CTA2 && !F16) {
+            if (g.act == ACT_GELU_ERF) return launch<BLOCK_N, EPI_BF16_ACTGRAD, ACT_GELU_ERF, false, F16, CTA2>(g, stream);
+            if (g.act == ACT_QUICK_GELU) return launch<BLOCK_N, EPI_BF16_ACTGRAD, ACT_QUICK_GELU, false, F16, CTA2>(g, stream);
+        }
+        TC_CHECK(false, "activation-gradient epilogue: unsupported activation %d / tile shape / operand type", g.act);
+    }
     TC_CHECK(g.epi == EPI_BF16, "unknown epilogue %d", g.epi);
     const bool pre = g.out_pre != nullptr;
     if (g.act == ACT_NONE) { TC_CHECK(!pre, "out_pre needs an activation"); return launch<BLOCK_N, EPI_BF16, ACT_NONE, false, F16, CTA2>(g, stream); }

@@ -120,3 +120,27 @@ def test_gemm_simt_fp32(M, N, K):
     x = torch.randn(M, N, device="cuda", generator=g)
     out, _ = _gemm(a, w, bias, "fp32", _lib.EPI_F32_ADD, out_init=x)
     assert (out - (x + ref)).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("aux", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,N,K", [(93 * 65, 2048, 512), (130, 256, 64), (333, 384, 128)])
+@pytest.mark.parametrize("block_n", [0, 128])
+def test_gemm_tc_act_grad_epilogue(M, N, K, act, aux, block_n):
+    """epi 3/4: dh = (dy . W) * act'(h_pre), the MLP dgrad with the activation derivative fused into the store stage
+    (replaces autograd through open_clip's mlp.gelu for the text tower backward)."""
+    g = torch.Generator(device="cuda").manual_seed(17)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    h = (2.0 * torch.randn(M, N, device="cuda", generator=g)).to(torch.bfloat16 if aux == "bf16" else torch.float16)
+    from tapclip_b200 import _lib
+    lib = _lib.load()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.tapclip_op_gemm(_lib.ptr(a), _lib.ptr(w), None, _lib.ptr(out), _lib.ptr(h), M, N, K,
+                                   _lib.DTYPE["bf16"], 3 if aux == "bf16" else 4, act, block_n, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    hf = h.float().requires_grad_(True)
+    _ref_act(hf, act).sum().backward()
+    ref = (a.float() @ w.float().t()) * hf.grad
+    assert bool(((out.float() - ref).abs() <= 5e-3 + 2 ** -7 * ref.abs()).all())   # two bf16 roundings (2 x 2^-9 relative) + fast act'
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 6e-3
