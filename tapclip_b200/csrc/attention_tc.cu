@@ -36,6 +36,14 @@ __host__ __device__ constexpr uint32_t attn_idesc(int m, int n, bool f16, bool b
            ((uint32_t)(m >> 4) << 24);
 }
 
+#ifdef TAPCLIP_ATTN_TRACE
+// developer-only phase trace of CTA 0 (tools/micro/attn_trace.py builds a private copy of the library with this enabled)
+__device__ long long g_attn_trace[2 * 16 * 16];
+#define TRACE(slot) do { if (tr) tr[slot] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -49,30 +57,36 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // lane `cls_lane` writes) receives the unnormalised probabilities of that row.  Returns the row sum; *p_last = p[N-1].
 template <typename T16>
 __device__ __forceinline__ float softmax_to_tmem(uint32_t trow, int N, int nkp, float scale_log2, float* cls_out, bool cls_lane,
-                                                 float* p_last) {
+                                                 float* p_last, long long* tr = nullptr) {
     const int nch = nkp / 16;
-    float mx = -INFINITY;
+    // pass 1: row maximum, 4 x 16 columns per tcgen05.wait::ld; four independent accumulators keep the FMNMX chain off
+    // the critical path
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
     for (int c0 = 0; c0 < nch; c0 += 4) {
         uint32_t r[4][16];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
             if (c0 + u < nch) tmem_ld_32x16(trow + (c0 + u) * 16, r[u]);
         tmem_ld_wait();
-        if ((c0 + 4) * 16 <= N) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
+            if ((c0 + u + 1) * 16 <= N) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[u][j]));
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
+                for (int j = 0; j < 16; j += 4) {
+                    m0 = fmaxf(m0, __uint_as_float(r[u][j])); m1 = fmaxf(m1, __uint_as_float(r[u][j + 1]));
+                    m2 = fmaxf(m2, __uint_as_float(r[u][j + 2])); m3 = fmaxf(m3, __uint_as_float(r[u][j + 3]));
+                }
+            } else if (c0 + u < nch) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    if ((c0 + u) * 16 + j < N) mx = fmaxf(mx, __uint_as_float(r[u][j]));
+                    if ((c0 + u) * 16 + j < N) m0 = fmaxf(m0, __uint_as_float(r[u][j]));
+            }
         }
     }
+    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     const float mneg = -mx * scale_log2;
-    float l = 0.f, pl = 0.f;
+    TRACE(4);
+    float l = 0.f, l1 = 0.f, pl = 0.f;
     for (int c0 = 0; c0 < nch; c0 += 4) {
         uint32_t r[4][16];
 #pragma unroll
@@ -88,7 +102,7 @@ __device__ __forceinline__ float softmax_to_tmem(uint32_t trow, int N, int nkp, 
                 for (int j = 0; j < 16; j += 2) {
                     const float p0 = fast_exp2(fmaf(__uint_as_float(r[u][j]), scale_log2, mneg));
                     const float p1 = fast_exp2(fmaf(__uint_as_float(r[u][j + 1]), scale_log2, mneg));
-                    l += p0 + p1;
+                    if (j & 2) l1 += p0 + p1; else l += p0 + p1;
                     pk[j >> 1] = pack2<T16>(p0, p1);
                 }
                 tmem_st_32x8(trow + (c0 + u) * 8, pk);
@@ -117,7 +131,7 @@ __device__ __forceinline__ float softmax_to_tmem(uint32_t trow, int N, int nkp, 
         }
     }
     *p_last = pl;
-    return l;
+    return l + l1;
 }
 
 // O row (64 fp32 columns at trow + O_COL) -> registers, scaled by 1/rowsum and packed to 16 bits
@@ -253,19 +267,95 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
 // ------------------------------------------------------------------------------------------------------------------
 // Persistent, software-pipelined version (NKP <= 208, e.g. ViT-B/16 and the text tower): one CTA per SM loops over
-// (sequence, head, q-tile) items.  Three smem operand slots and two TMEM halves let the control thread prefetch item
-// i+1 and issue S(i) while one softmax group still works on item i-1; the two softmax groups (4 warps each) alternate
-// items, so the exp/sum work of consecutive items overlaps and no per-item setup (TMEM alloc, barrier init) remains.
+// (sequence, head, q-tile) items; item i belongs to softmax group i&1 and lives in TMEM half i&1.
+//   warp 0      loader: TMA of Q/K/V for up to three items ahead (three smem operand slots)
+//   warp 1      TMEM allocator + the only tcgen05.mma issuer.  Its control flow is warp-uniform (warp index and TMEM base
+//               come out of shuffles) and the issue is elect.sync-predicated: ptxas then keeps the MMA operands in uniform
+//               registers; a single-lane `if (lane == 0)` region wraps every UTCHMMA in an ELECT/R2UR waterfall
+//               (tools/micro/mma_issue_bench.cu: 13 P.V MMAs issue in 395 instead of 900 cycles)
+//   warps 2,3   idle: they pad warpgroup 0 so that setmaxnreg can hand its registers to the softmax warpgroups
+//   warps 4..11 two softmax groups of 4 warps (one thread per query row).  setmaxnreg gives these threads 232 registers,
+//               so the WHOLE S row (up to 208 fp32) is read from TMEM once and stays in registers for the max and the
+//               exp2/sum/pack pass; P goes back into TMEM over the S columns; then the group waits for O = P V, scales it,
+//               transposes it through the (dead) Q tile of the item's slot and stores 128-byte row segments.
+// The two groups run out of phase, so one group's MUFU-bound exp2 pass overlaps the other's TMEM/LSU phases.
+// All hand-offs are mbarriers (no CTA-wide or group-wide bar.sync inside the loop).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void group_sync(int g) {      // named barrier of one 128-thread softmax group
-    if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-    else asm volatile("bar.sync 2, 128;" ::: "memory");
-}
-
-constexpr int ATTN2_THREADS = 320;     // warp 0 loader (TMA), warp 1 TMEM alloc, warps 2..9 two softmax groups of 4 warps
+constexpr int ATTN2_THREADS = 384;
 constexpr int NSLOT = 3;
 
-template <bool F16>
+// warp-converged issue: one elected lane executes the instruction, operands stay warp-uniform
+__device__ __forceinline__ void umma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One 16-key chunk (keys [16u, 16u+16)) of a query row held in registers.  MAYBE_MASKED = false: the caller guarantees
+// every key of the chunk is < N (no per-key tests are even compiled).
+template <bool MAYBE_MASKED>
+__device__ __forceinline__ void chunk_max(const uint32_t (&c)[16], int u, int N, float& m0, float& m1, float& m2, float& m3) {
+    if (!MAYBE_MASKED || (u + 1) * 16 <= N) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            m0 = fmaxf(m0, __uint_as_float(c[j])); m1 = fmaxf(m1, __uint_as_float(c[j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(c[j + 2])); m3 = fmaxf(m3, __uint_as_float(c[j + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (u * 16 + j < N) m0 = fmaxf(m0, __uint_as_float(c[j]));
+    }
+}
+// exp2, row-sum, 16-bit pack and write-back of P chunk u (TMEM columns [8u, 8u+8) of the row); probe bookkeeping
+template <typename T16, bool MAYBE_MASKED>
+__device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N, float scale_log2, float mneg, uint32_t trow,
+                                          float* cls_out, bool cls_lane, float& l0, float& l1, float& p_last) {
+    float pv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pv[j] = fast_exp2(fmaf(__uint_as_float(c[j]), scale_log2, mneg));
+    if (MAYBE_MASKED && (u + 1) * 16 >= N) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (u * 16 + j >= N) pv[j] = 0.f;
+            if (u * 16 + j == N - 1) p_last = pv[j];
+        }
+    }
+    if (cls_out != nullptr && cls_lane) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (u * 16 + j < N) cls_out[u * 16 + j] = pv[j];
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        if (j & 2) l1 += pv[j] + pv[j + 1]; else l0 += pv[j] + pv[j + 1];
+        pk[j >> 1] = pack2<T16>(pv[j], pv[j + 1]);
+    }
+    tmem_st_32x8(trow + u * 8, pk);
+}
+
+// NCH = compile-time number of 16-key chunks the softmax handles (>= NKP/16: chunks past NKP are fully masked), so that every
+// register array below is indexed with constants; chunks below FIRST_MASKABLE are valid for every N this instance serves.
+template <bool F16, int NCH>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, void* __restrict__ out_,
                     int N, int H, int nkp, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out,
@@ -276,11 +366,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int slot_bytes = 128 * 128 + 2 * nkp * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSLOT * slot_bytes);
     uint64_t* bar_load = bars;            // [3] TMA transaction barriers, one per operand slot
-    uint64_t* bar_s = bars + 3;           // [2] S = QK^T complete (per softmax group / TMEM half)
-    uint64_t* bar_o = bars + 5;           // [2] O = PV complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* bar_s = bars + 3;           // [2] S = QK^T complete (per group / TMEM half)
+    uint64_t* bar_p = bars + 5;           // [2] P written to TMEM by the group's 4 warps
+    uint64_t* bar_o = bars + 7;           // [2] O = PV complete
+    uint64_t* bar_tfree = bars + 9;       // [2] O read out of TMEM by the group's 4 warps: the TMEM half may take the next S
+    uint64_t* bar_free = bars + 11;       // [2] O stored: the operand slot (its Q tile doubles as store staging) may be refilled
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int d = H * DH;
     const int n_mine = (n_items > (int)blockIdx.x) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -288,7 +381,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_kv);
         for (int i = 0; i < NSLOT; ++i) mbar_init(&bar_load[i], 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&bar_o[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 4); mbar_init(&bar_o[i], 1);
+            mbar_init(&bar_tfree[i], 4); mbar_init(&bar_free[i], 4);
+        }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
@@ -296,86 +392,203 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_trigger();
     pdl_wait();
 
-    if (warp == 0) {
-        // ---- loader: keeps up to three items of Q/K/V in flight ----
-        if (lane == 0) {
-            for (int i = 0; i < n_mine; ++i) {
-                // slot i%3 was last used by item i-3; its V tile is dead once PV(i-3) has completed
-                if (i >= NSLOT) mbar_wait(&bar_o[(i - NSLOT) & 1], (uint32_t)(((i - NSLOT) >> 1) & 1));
-                const int id = (int)blockIdx.x + i * (int)gridDim.x;
-                const int qt = id % nqt, sh = id / nqt, s = sh / H, h = sh % H;
-                uint8_t* Qs = smem + (i % NSLOT) * slot_bytes;
-                uint64_t* bl = &bar_load[i % NSLOT];
-                mbar_expect_tx(bl, (uint32_t)slot_bytes);
-                tma_load_2d(Qs, &tmap_q, h * DH, s * N + qt * 128, bl);
-                tma_load_2d(Qs + 128 * 128, &tmap_kv, d + h * DH, s * N, bl);
-                tma_load_2d(Qs + 128 * 128 + nkp * 128, &tmap_kv, 2 * d + h * DH, s * N, bl);
+    // register reallocation between warpgroups (each setmaxnreg sits at the top of its role's branch: ptxas budgets
+    // registers per dominated region)
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 4 x 40 + 8 x 232 = 12 x 168
+        if (warp == 0) {
+            // ---- loader ----
+            if (lane == 0) {
+                for (int i = 0; i < n_mine; ++i) {
+                    // slot i%3 was last used by item i-3: operands dead after PV(i-3), staging (Q area) dead once its O is stored
+                    if (i >= NSLOT) mbar_wait(&bar_free[(i - NSLOT) & 1], (uint32_t)(((i - NSLOT) >> 1) & 1));
+                    const int id = (int)blockIdx.x + i * (int)gridDim.x;
+                    const int qt = id % nqt, sh = id / nqt, s = sh / H, h = sh % H;
+                    uint8_t* Qs = smem + (i % NSLOT) * slot_bytes;
+                    uint64_t* bl = &bar_load[i % NSLOT];
+                    mbar_expect_tx(bl, (uint32_t)slot_bytes);
+                    tma_load_2d(Qs, &tmap_q, h * DH, s * N + qt * 128, bl);
+                    tma_load_2d(Qs + 128 * 128, &tmap_kv, d + h * DH, s * N, bl);
+                    tma_load_2d(Qs + 128 * 128 + nkp * 128, &tmap_kv, 2 * d + h * DH, s * N, bl);
+                }
             }
-        }
-    } else if (warp >= 2) {
-        // ---- softmax group g: owns TMEM half g and every second item; its first thread also issues the two MMAs ----
-        const int g = (warp - 2) >> 2;
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
-        const uint32_t thalf = tmem_base + g * 256;
-        const uint32_t trow = thalf + ((uint32_t)(q * 32) << 16);
-        const uint32_t idesc_s = attn_idesc(128, nkp, F16, false), idesc_o = attn_idesc(128, DH, F16, true);
-        for (int i = g; i < n_mine; i += 2) {
-            const int id = (int)blockIdx.x + i * (int)gridDim.x;
-            const int qt = id % nqt, sh = id / nqt, s = sh / H, h = sh % H;
-            const uint32_t par = (uint32_t)((i >> 1) & 1);
-            uint8_t* Qs = smem + (i % NSLOT) * slot_bytes;
-            if (leader) {
+        } else if (warp == 1) {
+            // ---- MMA issuer (all 32 lanes run the control flow; elect.sync picks the issuing lane) ----
+            const uint32_t idesc_s = attn_idesc(128, nkp, F16, false), idesc_o = attn_idesc(128, DH, F16, true);
+            const int nks = nkp / 16;
+            auto issue_s = [&](int i) {
+                const int hf = i & 1;
+                uint8_t* Qs = smem + (i % NSLOT) * slot_bytes;
                 mbar_wait(&bar_load[i % NSLOT], (uint32_t)((i / NSLOT) & 1));
+                if (i >= 2) mbar_wait(&bar_tfree[hf], (uint32_t)(((i >> 1) - 1) & 1));     // O(i-2) has left this TMEM half
                 tc_fence_after();
+                const uint32_t thalf = tmem_base + hf * 256;
                 const uint64_t qd = smem_desc_sw128(smem_u32(Qs)), kd = smem_desc_sw128(smem_u32(Qs + 128 * 128));
 #pragma unroll
-                for (int k = 0; k < DH / 16; ++k) umma_bf16(thalf, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-                umma_commit(&bar_s[g]);
+                for (int k = 0; k < DH / 16; ++k) umma_ss_elect(thalf, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+                umma_commit_elect(&bar_s[hf]);
+            };
+            auto issue_pv = [&](int j) {
+                const int hf = j & 1;
+                const uint32_t thalf = tmem_base + hf * 256;
+                mbar_wait(&bar_p[hf], (uint32_t)((j >> 1) & 1));
+                tc_fence_after();
+                const uint64_t vd = smem_desc_sw128(smem_u32(smem + (j % NSLOT) * slot_bytes + 128 * 128 + nkp * 128));
+#pragma unroll
+                for (int ks = 0; ks < 13; ++ks)                        // NKP <= 208: at most 13 k-steps
+                    if (ks < nks) umma_ts_elect(thalf + O_COL, thalf + ks * 8, vd + (uint64_t)(ks * 128), idesc_o, ks != 0);
+                umma_commit_elect(&bar_o[hf]);
+            };
+            // steady-state event order of the two (out-of-phase) groups: P(j), tfree(j), P(j+1), tfree(j+1), ...
+            if (n_mine > 0) issue_s(0);
+            if (n_mine > 1) issue_s(1);
+            for (int j = 0; j < n_mine; ++j) {
+                issue_pv(j);
+                if (j + 2 < n_mine) issue_s(j + 2);
             }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ---- softmax group g: owns TMEM half g and every second item ----
+        const int g = (warp - 4) >> 2;
+        const int q = warp & 3;                                        // TMEM lane quarter
+        const int row = q * 32 + lane;
+        const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
+        const int rd_row = lane >> 3, rd_ch = lane & 7;                // store mapping: 8 lanes cover one 128-byte row segment
+        // (q-tile, head, sequence) of the group's current item, advanced incrementally (no divisions inside the loop)
+        const int step2 = 2 * (int)gridDim.x;
+        const int step_qt = step2 % nqt, step_sh = step2 / nqt, step_h = step_sh % H, step_s = step_sh / H;
+        const int id0 = (int)blockIdx.x + g * (int)gridDim.x;
+        int qt = id0 % nqt, h = (id0 / nqt) % H, s = (id0 / nqt) / H;
+        for (int i = g; i < n_mine; i += 2) {
+            const uint32_t par = (uint32_t)((i >> 1) & 1);
+            uint8_t* Qs = smem + (i % NSLOT) * slot_bytes;
             const int grow = qt * 128 + row;
             const bool warp_active = qt * 128 + q * 32 < N;            // else: all 32 rows of this warp are padding
-            mbar_wait(&bar_s[g], par);
-            tc_fence_after();
-            float l = 1.f, p_last = 0.f;
             const bool cls_warp = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0;
             float* cls_out = cls_warp ? probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N : nullptr;
+#ifdef TAPCLIP_ATTN_TRACE
+            long long* tr = (blockIdx.x == 0 && lane == 0 && q == 0 && (i >> 1) < 16) ? g_attn_trace + (g * 16 + (i >> 1)) * 16 : nullptr;
+#endif
+            TRACE(0);
+            mbar_wait(&bar_s[g], par);
+            TRACE(3);
+            tc_fence_after();
+            float l = 1.f, p_last = 0.f;
             if (warp_active) {
-                l = softmax_to_tmem<T16>(trow, N, nkp, scale_log2, cls_out, lane == 0, &p_last);
+                // The S row is read from TMEM once and kept in registers for both the max and the exp2 pass -- except, for
+                // NCH = 13, its last 3 chunks, which are read twice (208 + ~60 registers is more than a thread can have).
+                // P chunk u overwrites S columns [8u, 8u+8), which never reach the re-read chunks [160, 208).
+                constexpr int NRES = NCH < 10 ? NCH : 10;                       // register-resident chunks
+                constexpr int NTAIL = NCH - NRES;                              // chunks read twice
+                constexpr int FIRST_MASKABLE = NCH == 13 ? 8 : NCH == 8 ? 4 : 0;   // N > 16 * FIRST_MASKABLE for this instance
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                if constexpr (NTAIL > 0) {
+                    uint32_t t[NTAIL > 0 ? NTAIL : 1][16];
+#pragma unroll
+                    for (int v = 0; v < NTAIL; ++v) tmem_ld_32x16(trow + (NRES + v) * 16, t[v]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < NTAIL; ++v) chunk_max<true>(t[v], NRES + v, N, m0, m1, m2, m3);
+                    // scheduling fence: the tail chunks' registers die here, before the resident chunks land
+                    asm volatile("" : "+f"(m0), "+f"(m1), "+f"(m2), "+f"(m3) :: "memory");
+                }
+                uint32_t r[NRES][16];
+#pragma unroll
+                for (int u = 0; u < NRES; ++u) tmem_ld_32x16(trow + u * 16, r[u]);
+                tmem_ld_wait();
+                TRACE(4);
+#pragma unroll
+                for (int u = 0; u < NRES; ++u) {
+                    if constexpr (true) {
+                        if (u < FIRST_MASKABLE) chunk_max<false>(r[u], u, N, m0, m1, m2, m3);
+                        else chunk_max<true>(r[u], u, N, m0, m1, m2, m3);
+                    }
+                }
+                const float mneg = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2;
+                TRACE(6);
+                float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+                for (int u = 0; u < NRES; ++u) {
+                    if (u < FIRST_MASKABLE) chunk_exp<T16, false>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                    else chunk_exp<T16, true>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                }
+                if constexpr (NTAIL > 0) {
+                    uint32_t t[NTAIL > 0 ? NTAIL : 1][16];
+#pragma unroll
+                    for (int v = 0; v < NTAIL; ++v) tmem_ld_32x16(trow + (NRES + v) * 16, t[v]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < NTAIL; ++v) chunk_exp<T16, true>(t[v], NRES + v, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                }
+                l = l0 + l1;
                 tmem_st_wait();
             }
+            TRACE(5);
             tc_fence_before();
-            group_sync(g);                                                     // P of all 128 rows is in TMEM
-            if (leader) {
-                tc_fence_after();
-                const uint64_t vd = smem_desc_sw128(smem_u32(Qs + 128 * 128 + nkp * 128));
-                for (int ks = 0; ks < nkp / 16; ++ks) umma_ts(thalf + O_COL, thalf + ks * 8, vd + (uint64_t)(ks * 128), idesc_o, ks != 0);
-                umma_commit(&bar_o[g]);
-            }
-            const float inv = 1.f / l;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_p[g]);                     // this warp's 32 rows of P are in TMEM
+            const float inv = __frcp_rn(l);
             if (warp_active) {
                 if (probe_mode == PROBE_TEXT_COL && grow < probe_P) probe_out[((int64_t)s * H + h) * probe_P + grow] = p_last * inv;
                 if (cls_warp && lane == 0)
                     for (int key = 0; key < N; ++key) cls_out[key] *= inv;      // own earlier writes
             }
+            TRACE(7);
             mbar_wait(&bar_o[g], par);
+            TRACE(8);
             tc_fence_after();
+            uint32_t o[4][16];
             if (warp_active) {
-                uint4 o[8];
-                load_o_row<T16>(trow, inv, o);
-                if (grow < N) {
-                    uint4* gp = reinterpret_cast<uint4*>(reinterpret_cast<T16*>(out_) + ((int64_t)s * N + grow) * d + h * DH);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) gp[c] = o[c];
-                }
+                for (int c = 0; c < 4; ++c) tmem_ld_32x16(trow + O_COL + c * 16, o[c]);
+                tmem_ld_wait();
             }
             tc_fence_before();
-            group_sync(g);                                                     // O drained: the next S may overwrite this half
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tfree[g]);                 // O is in registers: the next S may overwrite this TMEM half
+            if (warp_active) {
+                // O row (64 fp32 columns) -> scaled 16-bit -> XOR-swizzled staging in this warp's 4 KB of the item's Q tile
+                const uint32_t stage = smem_u32(Qs) + (uint32_t)(q * 32) * 128u;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t* rr = &o[c >> 1][(c & 1) * 8];
+                    const uint32_t x0 = pack2<T16>(__uint_as_float(rr[0]) * inv, __uint_as_float(rr[1]) * inv);
+                    const uint32_t x1 = pack2<T16>(__uint_as_float(rr[2]) * inv, __uint_as_float(rr[3]) * inv);
+                    const uint32_t x2 = pack2<T16>(__uint_as_float(rr[4]) * inv, __uint_as_float(rr[5]) * inv);
+                    const uint32_t x3 = pack2<T16>(__uint_as_float(rr[6]) * inv, __uint_as_float(rr[7]) * inv);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)lane * 128u + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4)),
+                                 "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");
+                }
+                __syncwarp();
+                uint8_t* gbase = reinterpret_cast<uint8_t*>(out_) + (((int64_t)s * N + qt * 128 + q * 32) * d + h * DH) * 2 + rd_ch * 16;
+                const int rows_left = N - (qt * 128 + q * 32);
+                uint4 x[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {                       // all eight reads first: their latencies overlap
+                    const int rr = it * 4 + rd_row;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[it].x), "=r"(x[it].y), "=r"(x[it].z), "=r"(x[it].w)
+                                 : "r"(stage + (uint32_t)rr * 128u + (((uint32_t)rd_ch ^ ((uint32_t)rr & 7u)) << 4)) : "memory");
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rd_row;
+                    if (rr < rows_left) *reinterpret_cast<uint4*>(gbase + (int64_t)rr * d * 2) = x[it];
+                }
+                fence_proxy_async_smem();                              // generic-proxy staging writes before the slot's next TMA fill
+            }
+            TRACE(9);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_free[g]);                  // O stored: the operand slot may be refilled
+            qt += step_qt;
+            if (qt >= nqt) { qt -= nqt; ++h; }
+            h += step_h;
+            if (h >= H) { h -= H; ++s; }
+            s += step_s;
         }
     }
     tc_fence_before();
@@ -385,6 +598,12 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 }
 
 }  // namespace
+
+#ifdef TAPCLIP_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int tapclip_debug_attn_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * 2 * 16 * 16);
+}
+#endif
 
 bool attention_fwd_tc_supported(int dt, int N) { return (dt == DT_BF16 || dt == DT_F16) && N >= 1 && N <= 256; }
 
@@ -400,19 +619,24 @@ void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
     const float sl2 = 0.125f * 1.4426950408889634f;
     if (nkp <= 208) {
         // persistent pipelined kernel: 3 operand slots of (Q 16 KB + K + V) fit in shared memory
-        const size_t smem2 = NSLOT * (128 * 128 + 2 * (size_t)nkp * 128) + 128 + 1024;
-        static size_t conf2[2] = {0, 0};
-        if (smem2 > conf2[f16]) {
-            if (f16) TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            else TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            conf2[f16] = smem2;
-        }
+        const size_t smem2 = NSLOT * (128 * 128 + 2 * (size_t)nkp * 128) + 128 + 1024;   // + barriers/TMEM slot, alignment slack
         static int num_sms = 0;
         if (num_sms == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
         const int n_items = S * H * nqt;
         const unsigned grid2 = (unsigned)std::min(n_items, num_sms);
-        if (f16) launch_pdl(attn_fwd_tc2_kernel<true>, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
-        else launch_pdl(attn_fwd_tc2_kernel<false>, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        // softmax chunk count instance: 4 (N <= 64, ViT-B/32), 8 (N <= 128, the text tower), 13 (N <= 208, ViT-B/16)
+        const int nch = nkp / 16;
+        auto go = [&](auto kern, size_t& configured) {
+            if (smem2 > configured) {
+                TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                configured = smem2;
+            }
+            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        };
+        static size_t conf2[2][3] = {{0, 0, 0}, {0, 0, 0}};
+        if (nch <= 4) { if (f16) go(attn_fwd_tc2_kernel<true, 4>, conf2[1][0]); else go(attn_fwd_tc2_kernel<false, 4>, conf2[0][0]); }
+        else if (nch <= 8) { if (f16) go(attn_fwd_tc2_kernel<true, 8>, conf2[1][1]); else go(attn_fwd_tc2_kernel<false, 8>, conf2[0][1]); }
+        else { if (f16) go(attn_fwd_tc2_kernel<true, 13>, conf2[1][2]); else go(attn_fwd_tc2_kernel<false, 13>, conf2[0][2]); }
         TC_LAUNCH_CHECK();
         return;
     }
