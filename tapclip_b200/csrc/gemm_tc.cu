@@ -94,7 +94,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* bias_s = reinterpret_cast<float*>(smem_epi + EPI_BYTES + 256);      // bias of the current tile, shared by the 4 epilogue warps
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index (and below the TMEM base) come out of shuffles so that ptxas knows they are warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // work decomposition: a "unit" is one CTA (CTA2 = false) or one 2-CTA cluster owning 256 rows (CTA2 = true)
     constexpr int UNIT_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
     const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
@@ -120,7 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if constexpr (CTA2) cluster_sync_all();        // the peer's barriers must be initialised before any remote arrive
     else __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_base_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_slot, 0);
     // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail (PDL);
     // from here on global memory written by that kernel is read
     pdl_trigger();
@@ -152,7 +153,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0 && cta_rank == 0) {
+        if constexpr (!CTA2) {
+            // all 32 lanes run the warp-uniform control flow; elect.sync picks the issuing lane (see common.cuh)
             constexpr uint32_t idesc = make_idesc(UNIT_M, BLOCK_N, F16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -166,17 +168,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * STAGE_A_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::STAGE_B_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        // advance 32 B (= 16 bf16) inside the 128B swizzle row: +2 in the >>4 address field
-                        if constexpr (CTA2) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                        else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    // frees this smem stage (in both CTAs of a pair) once the MMAs retire
-                    if constexpr (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)      // advance 32 B (= 16 bf16) inside the 128B swizzle row: +2 in the >>4 address field
+                        umma_ss_elect(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_elect(&empty_bar[stage]);           // frees this smem stage once the MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                // accumulator ready for the epilogue warps (of both CTAs)
-                if constexpr (CTA2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+                umma_commit_elect(&tmem_full[acc]);                 // accumulator ready for the epilogue warps
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        } else if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = make_idesc(UNIT_M, BLOCK_N, F16);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * STAGE_A_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::STAGE_B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty_bar[stage]);             // frees this smem stage in both CTAs of the pair
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full[acc]);                   // accumulator ready for the epilogue warps of both CTAs
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
