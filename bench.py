@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the TAP-CLIP hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train_c2|fwd_c1|eval_c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train_c2|fwd_c1|eval_c3|fwd_c4|train_c5]
 
 One "step" = one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json
 configs[1]: ViT-B/16 prompt-tuning train step (attribution-instrumented forward + backward to the ctx vectors +
@@ -35,7 +35,14 @@ WORKLOADS = {
                "BASELINE configs[0]: ViT-B/16 attribution-instrumented forward, batch 8, 65 classes, 16 ctx tokens"),
     "eval_c3": ("ViT-B-16-quickgelu", 256, 345, 16, False,
                 "BASELINE configs[2]: ViT-B/16 cross-domain eval, 345 classes, batch 256/GPU, class-sharded text encoder"),
+    "fwd_c4": ("ViT-L-14-336-quickgelu", 512, 65, 16, False,
+               "BASELINE configs[3]: ViT-L/14@336 attribution-instrumented forward, batch 512/GPU, 65 classes, CLS-row probes of "
+               "all 24 layers + attention rollout"),
+    "train_c5": ("ViT-B-16-quickgelu", 128, 345, 16, True,
+                 "BASELINE configs[4]: ViT-B/16 few-shot prompt-tuning train step, 345 classes, batch 128/GPU, class-sharded text "
+                 "tower, ctx-gradient all-gather"),
 }
+IMAGE_ATTRIBUTION = {"fwd_c4": "rollout"}          # workloads whose step also emits the image-side attribution
 
 
 def measured_peaks():
@@ -193,7 +200,8 @@ def run_ours(args, wl):
 
     clip = tb.CLIPWrapper(model_name, None, "cuda", seed=0, attribution="intended", dtype=args.dtype)
     torch.manual_seed(4)
-    model = tb.FullModel([f"class_{i:03d}" for i in range(C)], clip, prompt_len=P, cache_text_features=False)
+    model = tb.FullModel([f"class_{i:03d}" for i in range(C)], clip, prompt_len=P, cache_text_features=False,
+                         image_attribution=IMAGE_ATTRIBUTION.get(wl))
     opt = tb.FusedAdamW(model, lr=2e-3, weight_decay=0.01) if train else None
     model.train(train)
 

@@ -577,7 +577,7 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __res
 //   phase 2 (warp owns 16 key rows):    dV = P^T dO, dK = dS^T Q   (A operands via ldmatrix.trans on P / dS)
 // ------------------------------------------------------------------------------------------------
 template <int NB16, typename TQ>
-__global__ void __launch_bounds__(NB16 * 32, 1)
+__global__ void __launch_bounds__(NB16 * 32, NB16 <= 6 ? 2 : 1)     // two CTAs per SM up to N = 96 (the kernel is latency-bound)
 attn_bwd_mma_kernel(const TQ* __restrict__ qkv, const bf16* __restrict__ d_out, bf16* __restrict__ dqkv, int N, int H,
                     float scale) {
     pdl_wait_and_trigger();

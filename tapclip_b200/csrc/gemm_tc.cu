@@ -498,6 +498,8 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     TC_CHECK(g.dt == DT_BF16 || g.dt == DT_F16, "tcgen05 GEMM operands must be bf16 or fp16");
     // block_n: 0 = choose; 128 / 256 = one CTA per 128 x block_n tile; 512 = 2-CTA pairs on 256 x 256 tiles
     int bn = g.block_n;
+    static const int env_bn = getenv("TAPCLIP_GEMM_BN") ? atoi(getenv("TAPCLIP_GEMM_BN")) : 0;   // measurement override: 128 | 256 | 512
+    if (bn == 0 && env_bn != 0 && g.N % 256 == 0 && g.epi != EPI_BF16_ACTGRAD) bn = env_bn;
     if (bn == 0) {
         // Measured (tools/gemm_bench.py, B200): 128x256 single-CTA tiles are within 3 % of the 2-CTA 256x256 tiles on the
         // image-tower shapes (both ~0.95 of cuBLAS: the mainloop is not L2-feed-bound) and 10-15 % faster on the small

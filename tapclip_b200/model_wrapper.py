@@ -46,13 +46,13 @@ class _TapClipFunction(torch.autograd.Function):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad)   # rows A6-A10, this rank's classes
-            img_feat = eng.encode_image(images)                                   # row A4
+            img_feat = model._encode_image(images)                                # row A4 (+ A-ext probes)
             main.wait_stream(side)
             for t in (text_local, attr_local, raw_local):
                 if t is not None:
                     t.record_stream(main)
         else:
-            img_feat = eng.encode_image(images)
+            img_feat = model._encode_image(images)
             text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad)
         text_feat = all_gather_rows(text_local, shard, n_cls)                     # [C, E]
         if labels is not None:
@@ -104,7 +104,7 @@ class FullModel(nn.Module):
 
     def __init__(self, class_names, clip_wrapper, prompt_len=5, attr_lambda=1.0, stab_lambda=0.1,
                  adjustor_method="scale", class_specific=False, *, distributed=None, cache_text_features=True,
-                 overlap_towers=True):
+                 overlap_towers=True, image_attribution=None):
         super().__init__()
         self.clip = clip_wrapper
         self.class_names = class_names
@@ -123,6 +123,13 @@ class FullModel(nn.Module):
         self.last_attribution = None
         self.overlap_towers = overlap_towers
         self._side = None
+        # north-star extension (SURVEY 8a row A-ext, not in the reference): None | 'cls' (per-layer, per-head CLS-row
+        # attention probabilities [B,L,H,N]) | 'rollout' (additionally the attention-rollout map [B,N-1]); emitted by the
+        # same image pass that produces the features, returned in the forward() dict
+        if image_attribution not in (None, "cls", "rollout"):
+            raise ValueError(f"Unknown image_attribution: {image_attribution}")
+        self.image_attribution = image_attribution
+        self.last_image_attribution = None
 
     @property
     def prompt_len(self):
@@ -135,6 +142,19 @@ class FullModel(nn.Module):
         if self._side is None:
             self._side = torch.cuda.Stream(device=device)
         return self._side
+
+    def _encode_image(self, images):
+        eng = self.clip.engine
+        if self.image_attribution is None:
+            self.last_image_attribution = None
+            return eng.encode_image(images)
+        if self.image_attribution == "cls":
+            feat, rows = eng.encode_image(images, want_cls_rows=True)
+            self.last_image_attribution = (rows, None)
+        else:
+            feat, rows, roll = eng.encode_image(images, want_cls_rows=True, want_rollout=True)
+            self.last_image_attribution = (rows, roll)
+        return feat
 
     def _sharding(self) -> ClassSharding:
         return ClassSharding.current(self.distributed)
@@ -169,4 +189,9 @@ class FullModel(nn.Module):
         outputs = {"logits": logits}                                           # model_wrapper.py:88
         if labels is not None:                                                 # model_wrapper.py:90-93
             outputs.update({"loss": loss, "loss_cls": loss})
+        if self.last_image_attribution is not None:
+            rows, roll = self.last_image_attribution
+            outputs["image_cls_attention"] = rows
+            if roll is not None:
+                outputs["image_attribution"] = roll
         return outputs

@@ -139,3 +139,30 @@ def test_logits_only_backward_path():
     (om.forward_dedup(images)["logits"].logsumexp(1).sum()).backward()
     ref = torch.stack([om.prompt_learner.context_bank[n].grad for n in class_names(5)])
     assert ((ctx_grads(model, 5) - ref).norm() / ref.norm()).item() < 2e-3
+
+
+@pytest.mark.parametrize("kind", ["cls", "rollout"])
+def test_forward_with_image_attribution(kind):
+    """FullModel(image_attribution=...) (north-star extension, SURVEY 8a row A-ext): the image pass that feeds the logits
+    also emits the per-layer CLS-row attention (and the rollout map); logits are unchanged by the probes."""
+    import tapclip_b200 as tb
+    from oracle.clip_standin import vision_attention_rollout, vision_cls_attention
+    ow, om, clip, plain = _mini(mode="literal", dtype="fp32")
+    torch.manual_seed(4)
+    model = tb.FullModel(class_names(5), clip, prompt_len=4, image_attribution=kind)
+    images = synthetic_images(4, 64)
+    with torch.no_grad():
+        out = model(images.cuda())
+        ref_logits = plain(images.cuda())["logits"]
+        _, rows_ref = vision_cls_attention(ow.model, images)                    # [B, L, H, N]
+    assert torch.equal(out["logits"], ref_logits)
+    assert out["image_cls_attention"].shape == rows_ref.shape
+    assert max_abs(out["image_cls_attention"], rows_ref) < 1e-4
+    if kind == "rollout":
+        with torch.no_grad():
+            roll_ref = vision_attention_rollout(ow.model, images)
+        assert max_abs(out["image_attribution"], roll_ref) < 1e-4
+    else:
+        assert "image_attribution" not in out
+    with pytest.raises(ValueError):
+        tb.FullModel(class_names(5), clip, prompt_len=4, image_attribution="gradcam")
