@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtapclip.so")
+LIB_PATH = os.environ.get("TAPCLIP_LIB") or os.path.join(_HERE, "lib", "libtapclip.so")   # TAPCLIP_LIB: developer override (kernel variants)
 
 ACT = {"gelu_erf": 0, "quick_gelu": 1}
 DTYPE = {"fp32": 0, "bf16": 1, "mixed": 2, "fp16": 2}     # engine precision / element type (include/tapclip.h)

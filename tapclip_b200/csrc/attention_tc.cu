@@ -49,6 +49,19 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, minimax cubic for 2^f
+// (max relative error 7.5e-5, below the rounding of the 16-bit probabilities), n added into the exponent field.
+// The softmax pass is MUFU-bound (16 exp2/clk/SM, tools/micro/mufu_bench.cu): moving a third of the exponentials here
+// shortens it, as in FlashAttention-4's software exp2.
+__device__ __forceinline__ float poly_exp2(float x) {
+    x = fmaxf(x, -125.f);
+    const float t = x + 12582912.f;                  // 1.5 * 2^23: n = round(x) lands in the low mantissa bits
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(f, 0.05517084f, 0.24260908f);
+    p = fmaf(p, f, 0.69326109f);
+    p = fmaf(p, f, 0.99992847f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
 // Softmax of ONE query row held in TMEM (one thread = one TMEM lane).  Two passes over the S row (max, then exp2/sum),
 // read in groups of up to 64 columns with 4 tcgen05.ld in flight per wait; the 16-bit probabilities are written back
@@ -281,6 +294,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 // The two groups run out of phase, so one group's MUFU-bound exp2 pass overlaps the other's TMEM/LSU phases.
 // All hand-offs are mbarriers (no CTA-wide or group-wide bar.sync inside the loop).
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef ATTN_NRES
+#define ATTN_NRES 10
+#endif
 constexpr int ATTN2_THREADS = 384;
 constexpr int NSLOT = 3;
 
@@ -300,13 +316,19 @@ __device__ __forceinline__ void chunk_max(const uint32_t (&c)[16], int u, int N,
             if (u * 16 + j < N) m0 = fmaxf(m0, __uint_as_float(c[j]));
     }
 }
+constexpr int POLY_EVERY = 0;          // n > 0: every n-th exponential of the persistent kernel's softmax runs on the FMA pipe.
+                                       // Measured (ViT-B/16 layer, B=128): 0 -> 62 us, 3 -> 77 us: the pass is latency/issue-bound, not MUFU-bound
+
 // exp2, row-sum, 16-bit pack and write-back of P chunk u (TMEM columns [8u, 8u+8) of the row); probe bookkeeping
 template <typename T16, bool MAYBE_MASKED>
 __device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N, float scale_log2, float mneg, uint32_t trow,
                                           float* cls_out, bool cls_lane, float& l0, float& l1, float& p_last) {
     float pv[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) pv[j] = fast_exp2(fmaf(__uint_as_float(c[j]), scale_log2, mneg));
+    for (int j = 0; j < 16; ++j) {
+        const float x = fmaf(__uint_as_float(c[j]), scale_log2, mneg);
+        pv[j] = (POLY_EVERY > 0 && j % POLY_EVERY == 1) ? poly_exp2(x) : fast_exp2(x);
+    }
     if (MAYBE_MASKED && (u + 1) * 16 >= N) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -458,7 +480,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 // The S row is read from TMEM once and kept in registers for both the max and the exp2 pass -- except, for
                 // NCH = 13, its last 3 chunks, which are read twice (208 + ~60 registers is more than a thread can have).
                 // P chunk u overwrites S columns [8u, 8u+8), which never reach the re-read chunks [160, 208).
-                constexpr int NRES = NCH < 10 ? NCH : 10;                       // register-resident chunks
+                constexpr int NRES = NCH < ATTN_NRES ? NCH : ATTN_NRES;                       // register-resident chunks
                 constexpr int NTAIL = NCH - NRES;                              // chunks read twice
                 constexpr int FIRST_MASKABLE = NCH == 13 ? 8 : NCH == 8 ? 4 : 0;   // N > 16 * FIRST_MASKABLE for this instance
                 float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
