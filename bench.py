@@ -326,6 +326,8 @@ def run_ours(args, wl):
     c_local = -(-C // world)
     f_img, f_txt = flops_per_image(cfg), flops_per_text_sequence(cfg, P + cfg.context_length)
     flops_step = B * f_img + 2 * c_local * f_txt + 2 * B * C * cfg.embed_dim + (c_local * f_txt if train else 0)
+    # executed FLOPs: the last vision block runs its out-projection and MLP on the CLS row only (dead-row elimination)
+    dead = 0.0 if os.environ.get("TAPCLIP_DEAD_ROWS") == "0" else B * (cfg.vision_tokens - 1) * 18.0 * cfg.vision_width ** 2
     gemm = prof.get("gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
     gemm_tflops = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else None
     top = sorted(((k, v) for k, v in prof.get("shapes", {}).items()), key=lambda kv: -kv[1]["ms"])[:8]
@@ -354,6 +356,7 @@ def run_ours(args, wl):
             "attention_fwd_ms_per_step": prof.get("attention_fwd", {}).get("ms", 0.0) / args.steps,
             "attention_bwd_ms_per_step": prof.get("attention_bwd", {}).get("ms", 0.0) / args.steps,
             "step_algorithmic_tflop_per_gpu": flops_step / 1e12,
+            "step_executed_tflop_per_gpu": (flops_step - dead) / 1e12,
             "step_tflops_achieved_per_gpu": flops_step / (ms_resident / args.steps * 1e-3) / 1e12,
             "step_frac_of_peak": flops_step / (ms_resident / args.steps * 1e-3) / 1e12 / peaks["bf16_sustained"],
             "top_shapes": [{"shape": k, "launches": v["launches"], "ms": round(v["ms"], 4),

@@ -274,10 +274,10 @@ const char* Engine::profile_report() {
 
 // ---- primitive wrappers ------------------------------------------------------------------------------
 void Engine::gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K,
-                  int epi, int act, int dt, cudaStream_t st, int aux_dt) {
+                  int epi, int act, int dt, cudaStream_t st, int aux_dt, int64_t lda, int64_t ldo) {
     GemmArgs g;
     g.a = a; g.w = w; g.bias = bias; g.out = out; g.out_pre = out_pre;
-    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = epi; g.act = act; g.dt = dt; g.aux_dt = aux_dt;
+    g.M = M; g.N = N; g.K = K; g.lda = lda ? lda : K; g.ldw = K; g.ldo = ldo ? ldo : N; g.epi = epi; g.act = act; g.dt = dt; g.aux_dt = aux_dt;
     ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, epi};
     if (profiling) prof_begin(r, st);
     if (dt != DT_F32) gemm_tc(g, st);
@@ -307,7 +307,8 @@ void Engine::attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int
 //   stop_after_attention_probs : attribution pass, last block: only the probabilities are needed
 //   save       : keep x copies / qkv / h_pre for the backward pass (slot = layer)
 void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
-                           DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar) {
+                           DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar,
+                           int live_row) {
     const int64_t M = (int64_t)S * N;
     float* sx0 = nullptr; float* sx1 = nullptr; void* sqkv = qkv.p; void* shpre = nullptr;
     if (save_slot >= 0) {
@@ -321,6 +322,19 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
     attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
     if (abar) { attention_headmean(sqkv, abar, dt, S, N, H, st); ++launches; }      // rollout extension: head-mean map of this layer
     if (probs_only) return;
+    if (live_row >= 0) {
+        // Dead-row elimination: after the LAST block only token `live_row` of every sequence is read (ln_post(x[:,0])
+        // / pooling), and past the attention every row is independent.  The out-projection and the MLP therefore run on the
+        // S live rows only, addressed in place through the GEMM's leading dimensions (no gather, no copy).
+        TC_CHECK(save_slot < 0, "dead-row elimination is forward-only");
+        const int64_t ld = (int64_t)N * d;
+        float* xl = x + (int64_t)live_row * d;
+        gemm((const uint8_t*)attn.p + (int64_t)live_row * d * esz, b.w_o, b.b_o, xl, nullptr, S, d, d, EPI_F32_ADD, ACT_NONE, dt, st, DT_BF16, ld, ld);
+        layernorm_fwd(xl, ld, b.ln2_g, b.ln2_b, ln.p, dt, nullptr, S, d, st); ++launches;
+        gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, nullptr, S, 4 * d, d, EPI_BF16, cfg.act, dt, st);
+        gemm(hbuf.p, b.w_proj, b.b_proj, xl, nullptr, S, d, 4 * d, EPI_F32_ADD, ACT_NONE, dt, st, DT_BF16, 0, ld);
+        return;
+    }
     gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, dt, st);
     layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, dt, sx1, M, d, st); ++launches;
     gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, M, 4 * d, d, EPI_BF16, cfg.act, dt, st);
@@ -357,7 +371,8 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
             probe.seq_stride = (int64_t)L * H * N;
         }
         block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st,
-                      out_rollout ? (float*)v_abar.p + (int64_t)l * B * N * N : nullptr);
+                      out_rollout ? (float*)v_abar.p + (int64_t)l * B * N * N : nullptr,
+                      (l == L - 1 && dead_rows) ? 0 : -1);                   // only the CLS row feeds ln_post
     }
     layernorm_fwd((const float*)v_x.p, (int64_t)N * d, ln_post_g, ln_post_b, v_pooled.p, vdt, nullptr, B, d, st); ++launches;
     gemm(v_pooled.p, w_vproj, nullptr, out_feat, nullptr, B, E, d, EPI_F32, ACT_NONE, vdt, st);

@@ -1,5 +1,6 @@
 // Engine state behind the opaque tapclip_handle.
 #pragma once
+#include <cstdlib>
 #include "../../include/tapclip.h"
 #include "gemm.h"
 #include "kernels.h"
@@ -51,6 +52,8 @@ struct Engine {
     // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline numbers)
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; int64_t M, N, K; int epi; };
     bool profiling = false;
+    // last-block dead-row elimination (TAPCLIP_DEAD_ROWS=0 disables it: measurement / A-B parity only)
+    bool dead_rows = !(getenv("TAPCLIP_DEAD_ROWS") && atoi(getenv("TAPCLIP_DEAD_ROWS")) == 0);
     std::vector<ProfRec> prof;
     std::string prof_report;
     void prof_begin(ProfRec& r, cudaStream_t st);
@@ -67,11 +70,12 @@ struct Engine {
     std::string missing_weights() const;
 
     void gemm(const void* a, const void* w, const float* bias, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int epi,
-              int act, int dt, cudaStream_t st, int aux_dt = DT_BF16);
+              int act, int dt, cudaStream_t st, int aux_dt = DT_BF16, int64_t lda = 0, int64_t ldo = 0);   // lda/ldo 0 = dense
     void attn_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
     void attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st);
     void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
-                       DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar = nullptr);
+                       DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar = nullptr,
+                       int live_row = -1);
     void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, float* out_rollout, cudaStream_t st);
     void text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
                       float* out_text_feat, cudaStream_t st);
