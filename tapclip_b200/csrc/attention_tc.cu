@@ -608,7 +608,8 @@ void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
     TC_CHECK(attention_fwd_tc_supported(dt, N), "tcgen05 attention supports 16-bit inputs and N <= 256");
 
     const int d = H * DH;
-    const int nkp = (int)round_up(N, 16), nqt = (int)ceil_div(N, 128);
+    const int nkp = (int)round_up(N, 16);
+    const int nqt = (int)ceil_div(probe.live_q_rows > 0 ? std::min(N, probe.live_q_rows) : N, 128);   // query tiles actually computed
     const bool f16 = dt == DT_F16;
     const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const CUtensorMap& tq = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, 128, 64);

@@ -370,6 +370,7 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
             probe.out = out_cls_rows + (int64_t)l * H * N;
             probe.seq_stride = (int64_t)L * H * N;
         }
+        if (l == L - 1 && dead_rows) probe.live_q_rows = 1;
         block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st,
                       out_rollout ? (float*)v_abar.p + (int64_t)l * B * N * N : nullptr,
                       (l == L - 1 && dead_rows) ? 0 : -1);                   // only the CLS row feeds ln_post

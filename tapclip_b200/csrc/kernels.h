@@ -30,6 +30,8 @@ struct AttnProbe {
     int P = 0;
     int64_t seq_stride = 0;
     bool causal = false;         // key j visible to query i only if j <= i (standard CLIP text tower, encode_text)
+    int live_q_rows = 0;         // > 0: only query rows [0, live_q_rows) are consumed downstream (last block: the CLS row); the
+                                 // tcgen05 kernel then skips whole 128-row query tiles past them, other rows of `out` are unspecified
 };
 // qkv [S*N, 3*H*64] (packed in_proj output, activation type) -> out [S*N, H*64]; softmax(QK^T/8)V, no mask.
 // bf16 / fp16: mma.sync tensor-core flash kernel; fp32: SIMT kernel.  Probabilities asked for by `probe` are
