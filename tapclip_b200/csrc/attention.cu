@@ -596,22 +596,45 @@ attn_bwd_mma_kernel(const TQ* __restrict__ qkv, const bf16* __restrict__ d_out, 
     const int d = H * DH;
     const TQ* base = qkv + (int64_t)s * N * 3 * d + h * DH;
     const bf16* dobase = d_out + (int64_t)s * N * d + h * DH;
-    for (int idx = threadIdx.x; idx < NP * 8; idx += NB16 * 32) {
-        const int row = idx >> 3, ch = idx & 7;
-        const bool ok = row < N;
-        const TQ* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
-        const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
-        if constexpr (sizeof(TQ) == 2 && std::is_same<TQ, bf16>::value) {
+    // NP * 8 sixteen-byte chunks per operand, NB16 * 32 threads: exactly 4 chunks per thread
+    if constexpr (std::is_same<TQ, bf16>::value) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int idx = threadIdx.x + it * NB16 * 32;
+            const int row = idx >> 3, ch = idx & 7;
+            const bool ok = row < N;
+            const TQ* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
+            const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
             cp_async_16(smem_u32(Qs + off), src, ok);
             cp_async_16(smem_u32(Ks + off), src + d, ok);
             cp_async_16(smem_u32(Vs + off), src + 2 * d, ok);
-        } else {
-            // saved activations are fp16 (mixed mode): gradients are bf16, so Q/K/V are converted once here
+            cp_async_16(smem_u32(Os + off), dobase + (int64_t)(ok ? row : 0) * d + ch * 8, ok);
+        }
+    } else {
+        // saved activations are fp16 (mixed mode) while gradients are bf16: Q/K/V are converted once here.  All twelve
+        // global loads of a thread are issued before the first conversion so that their latencies overlap.
+        uint4 raw[4][3];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int idx = threadIdx.x + it * NB16 * 32;
+            const int row = idx >> 3, ch = idx & 7;
+            const bool ok = row < N;
+            const TQ* src = base + (int64_t)(ok ? row : 0) * 3 * d + ch * 8;
+            cp_async_16(smem_u32(Os + row * 128 + ((ch ^ (row & 7)) << 4)), dobase + (int64_t)(ok ? row : 0) * d + ch * 8, ok);
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
-                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-                if (ok) raw = *reinterpret_cast<const uint4*>(src + part * d);
-                const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+                raw[it][part] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) raw[it][part] = __ldg(reinterpret_cast<const uint4*>(src + part * d));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int idx = threadIdx.x + it * NB16 * 32;
+            const int row = idx >> 3, ch = idx & 7;
+            const uint32_t off = row * 128 + ((ch ^ (row & 7)) << 4);
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const __half2* hp = reinterpret_cast<const __half2*>(&raw[it][part]);
                 uint4 cv;
                 uint32_t* cp = reinterpret_cast<uint32_t*>(&cv);
 #pragma unroll
@@ -623,7 +646,6 @@ attn_bwd_mma_kernel(const TQ* __restrict__ qkv, const bf16* __restrict__ d_out, 
                 *reinterpret_cast<uint4*>(dst + off) = cv;
             }
         }
-        cp_async_16(smem_u32(Os + off), dobase + (int64_t)(ok ? row : 0) * d + ch * 8, ok);
     }
     cp_async_commit();
     cp_async_wait<0>();
