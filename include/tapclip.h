@@ -84,6 +84,8 @@ TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int3
  *   mode INTENDED: attribution pass on the un-adjusted prompt, a = softmax_P(mean_h P_last[h, 0:P, T-1]),
  *                  out_attr_raw / out_attr [C,P];   mode LITERAL: a == 1, out_attr [C,1] (raw not produced)
  *   feature pass on [ctx*a | tok], last position, @ text_projection, L2-norm -> out_text_feat [C,E].
+ *   mode 2 (ATTRIBUTION_ONLY): the INTENDED attribution pass alone (out_attr_raw / out_attr), no feature pass: used by the
+ *   'gate' / 'residual' adjustors (prompt_adjustor.py:38-44), whose small networks run on the host side between the passes.
  * save_for_backward != 0 keeps the activations `tapclip_text_backward` needs. */
 TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const float* tok, int32_t C, int32_t P, int32_t mode,
                          int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat,

@@ -39,6 +39,11 @@ CASES = [
     ("mini14_b2c3p16", "mini-14",           2,  3, 16),
     ("vitb16_c1",      "ViT-B-16",          8, 65, 16),     # BASELINE.json configs[0]
 ]
+# PromptAdjustor 'gate' / 'residual' (models/prompt_adjustor.py:13-25,38-44): name, model, B, C, P, method
+ADJUSTOR_CASES = [
+    ("mini16_gate_b3c4p4",      "mini-16",   3, 4, 4, "gate"),
+    ("minit512_resid_b2c3p5",   "mini-t512", 2, 3, 5, "residual"),       # residual_net hard-codes a 512-wide text tower
+]
 CTX_SEED = 4
 
 
@@ -55,11 +60,11 @@ def import_reference():
     return FullModel
 
 
-def run_reference(FullModel, model_name, B, C, P, mode):
+def run_reference(FullModel, model_name, B, C, P, mode, method="scale"):
     cfg = get_config(model_name)
     wrapper = StandInCLIPWrapper(model_name, device="cpu", seed=0, attribution=mode)
     torch.manual_seed(CTX_SEED)                         # PromptLearner draws ctx from the global RNG (:41)
-    model = FullModel(class_names(C), wrapper, prompt_len=P)
+    model = FullModel(class_names(C), wrapper, prompt_len=P, adjustor_method=method)
     model.train()                                       # train.py:91
     captured = []
     h = model.attribution_monitor.register_forward_hook(lambda m, i, o: captured.append(o.detach().clone()))
@@ -77,14 +82,18 @@ def run_reference(FullModel, model_name, B, C, P, mode):
     return model, {
         "logits": out["logits"].detach(), "loss": out["loss"].detach(), "attribution": attribution,
         "ctx_grad": ctx_grad, "logit_scale_grad": model.logit_scale.grad.detach().clone(),
+        "adjustor_grad": {k: p.grad.detach().clone() for k, p in model.prompt_adjustor.named_parameters()},
+        "adjustor_state": {k: v.detach().clone() for k, v in model.prompt_adjustor.state_dict().items()},
         "seconds_fwd_bwd": dt,
     }, (images, labels)
 
 
-def check_oracle(model_name, B, C, P, mode, gold, images, labels, full_loop):
+def check_oracle(model_name, B, C, P, mode, gold, images, labels, full_loop, method="scale"):
     wrapper = StandInCLIPWrapper(model_name, device="cpu", seed=0, attribution=mode)
     torch.manual_seed(CTX_SEED)
-    orc = OracleFullModel(class_names(C), wrapper, prompt_len=P)
+    orc = OracleFullModel(class_names(C), wrapper, prompt_len=P, adjustor_method=method)
+    for k, v in orc.prompt_adjustor.state_dict().items():
+        assert torch.equal(v, gold["adjustor_state"][k]), "adjustor initialisation differs from the reference (RNG order)"
     orc.train()
     if full_loop:
         out = orc.forward_as_written(images, labels)
@@ -92,6 +101,8 @@ def check_oracle(model_name, B, C, P, mode, gold, images, labels, full_loop):
         g = torch.stack([orc.prompt_learner.context_bank[n].grad for n in class_names(C)])
         assert torch.equal(out["logits"], gold["logits"]), "restated loop form is not bit-exact vs the reference"
         assert torch.equal(g, gold["ctx_grad"])
+        for k, p in orc.prompt_adjustor.named_parameters():
+            assert torch.equal(p.grad, gold["adjustor_grad"][k]), k
         orc.zero_grad()
     out = orc.forward_dedup(images, labels, return_aux=True)
     out["loss"].backward()
@@ -111,7 +122,8 @@ def main():
     torch.set_num_threads(os.cpu_count())
     FullModel = import_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    for name, model_name, B, C, P in CASES:
+    only_adjustor = "--adjustor-only" in sys.argv
+    for name, model_name, B, C, P in ([] if only_adjustor else CASES):
         for mode in ("literal", "intended"):
             _, gold, (images, labels) = run_reference(FullModel, model_name, B, C, P, mode)
             err, dd = check_oracle(model_name, B, C, P, mode, gold, images, labels, full_loop=not name.startswith("vit"))
@@ -122,6 +134,14 @@ def main():
             path = os.path.join(ROOT, "tests", "golden", f"{name}_{mode}.pt")
             torch.save(gold, path)
             print(f"{name:16s} {mode:8s} ref fwd+bwd {gold['seconds_fwd_bwd']:.1f}s  dedup-vs-ref {err}", flush=True)
+    for name, model_name, B, C, P, method in ADJUSTOR_CASES:
+        for mode in ("literal", "intended"):
+            _, gold, (images, labels) = run_reference(FullModel, model_name, B, C, P, mode, method)
+            err, dd = check_oracle(model_name, B, C, P, mode, gold, images, labels, True, method)
+            gold.update({"case": name, "model_name": model_name, "B": B, "C": C, "P": P, "mode": mode, "method": method,
+                         "ctx_seed": CTX_SEED, "torch": torch.__version__, "oracle_dedup_err": err})
+            torch.save(gold, os.path.join(ROOT, "tests", "golden", f"{name}_{mode}.pt"))
+            print(f"{name:22s} {mode:8s} {method:8s} dedup-vs-ref {err}", flush=True)
 
 
 if __name__ == "__main__":

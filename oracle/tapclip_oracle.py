@@ -80,20 +80,42 @@ def prompt_adjustor_scale(prompt_embed, attribution_score):
     return prompt_embed * attribution_score.unsqueeze(-1)
 
 
+class OraclePromptAdjustor(nn.Module):
+    """models/prompt_adjustor.py:6-47, all three methods (the reference raises ValueError for an unknown method at the first
+    forward, :47; here at construction)."""
+
+    def __init__(self, method="scale"):
+        super().__init__()
+        self.method = method
+        if method == "gate":                                                   # :13-19
+            self.gate_net = nn.Sequential(nn.Linear(1, 64), nn.ReLU(), nn.Linear(64, 1), nn.Sigmoid())
+        elif method == "residual":                                             # :20-25
+            self.residual_net = nn.Sequential(nn.Linear(1, 64), nn.ReLU(), nn.Linear(64, 512))
+        elif method != "scale":
+            raise ValueError(f"Unknown method: {method}")
+
+    def forward(self, prompt_embed, attribution_score):                        # :27-44
+        a = attribution_score.unsqueeze(-1)
+        if self.method == "scale":
+            return prompt_embed * a
+        if self.method == "gate":
+            return prompt_embed * self.gate_net(a)
+        return prompt_embed + self.residual_net(a)
+
+
 class OracleFullModel(nn.Module):
     """models/model_wrapper.py:12-100."""
 
     def __init__(self, class_names, clip_wrapper, prompt_len=5, attr_lambda=1.0, stab_lambda=0.1,
                  adjustor_method="scale", class_specific=False, ctx_seed=None):
         super().__init__()
-        if adjustor_method != "scale":
-            raise ValueError(f"Unknown method: {adjustor_method}")   # gate/residual: SURVEY 8f rank 4
         self.clip = clip_wrapper
         self.class_names = class_names
         self.prompt_learner = OraclePromptLearner(class_names, clip_wrapper, prompt_len, class_specific,
                                                   device=clip_wrapper.device, ctx_seed=ctx_seed)
         self.n_cls = len(class_names)
         self.prompt_len = prompt_len
+        self.prompt_adjustor = OraclePromptAdjustor(adjustor_method)         # :22 (created after the prompt learner: RNG order)
         self.attr_lambda, self.stab_lambda = attr_lambda, stab_lambda
         self.logit_scale = nn.Parameter(torch.ones([]) * torch.log(torch.tensor(1 / 0.07)))   # :26
 
@@ -119,7 +141,7 @@ class OracleFullModel(nn.Module):
                     attn_map = attn_map.unsqueeze(0)
                 attributions.append(attribution_monitor(attn_map, P))
             attribution = torch.cat(attributions, dim=0)                   # :65
-            adjusted_ctx = prompt_adjustor_scale(ctx, attribution)         # :68
+            adjusted_ctx = self.prompt_adjustor(ctx, attribution)          # :68
             adjusted_prompt = torch.cat([adjusted_ctx, cls], dim=1)        # :69
             text_feat = self.clip.model.transformer(adjusted_prompt)       # :72
             text_feat = text_feat[torch.arange(B), -1, :]                  # :73
@@ -152,7 +174,7 @@ class OracleFullModel(nn.Module):
     def text_features(self, raw_prompt, attribution):
         """Rows A9/A10: adjust ctx, feature pass, last-position pool, projection, L2-norm -> [C,E]."""
         P = self.prompt_len
-        adjusted = torch.cat([raw_prompt[:, :P, :] * attribution.unsqueeze(-1), raw_prompt[:, P:, :]], dim=1)
+        adjusted = torch.cat([self.prompt_adjustor(raw_prompt[:, :P, :], attribution), raw_prompt[:, P:, :]], dim=1)
         x = self.clip.model.transformer(adjusted)
         feat = x[:, -1, :] @ self.clip.model.text_projection
         return feat / feat.norm(dim=-1, keepdim=True)

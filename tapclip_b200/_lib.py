@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("TAPCLIP_LIB") or os.path.join(_HERE, "lib", "libtapcl
 
 ACT = {"gelu_erf": 0, "quick_gelu": 1}
 DTYPE = {"fp32": 0, "bf16": 1, "mixed": 2, "fp16": 2}     # engine precision / element type (include/tapclip.h)
-ATTR_MODE = {"literal": 0, "intended": 1}
+ATTR_MODE = {"literal": 0, "intended": 1, "attribution_only": 2}
 EPI_ACT, EPI_F32, EPI_F32_ADD = 0, 1, 2
 PROBE_NONE, PROBE_TEXT_COL, PROBE_CLS_ROW = 0, 1, 2
 

@@ -384,7 +384,9 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
 void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw,
                           float* out_attr, float* out_text_feat, cudaStream_t st) {
     TC_CHECK(C >= 0 && P >= 1, "bad class count / prompt length");
-    TC_CHECK(mode == 0 || mode == 1, "attribution mode must be 0 (literal) or 1 (intended)");
+    TC_CHECK(mode >= 0 && mode <= 2, "attribution mode must be 0 (literal), 1 (intended) or 2 (intended attribution pass only)");
+    const bool attr_only = (mode == 2);
+    if (attr_only) { mode = 1; TC_CHECK(!save, "the attribution-only pass keeps nothing for backward"); }
     saved.valid = false;
     if (C == 0) return;
     const std::string miss = missing_weights();
@@ -431,6 +433,7 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
         launch_pdl(fill_kernel, (unsigned)ceil_div(C, 256), 256, 0, st, out_attr, 1.0f, C);
         TC_LAUNCH_CHECK(); ++launches;
     }
+    if (attr_only) return;          // 'gate' / 'residual' adjustors: the host applies its small network to out_attr (prompt_adjustor.py:38-44)
     // feature pass (rows A9/A10)
     splice_prompts(ctx, tok, attr, PA, x, C, P, Lc, D, st); ++launches;
     for (int l = 0; l < L; ++l) {

@@ -94,6 +94,19 @@ class Engine:
                                                  _lib.stream_ptr()))
         return feat, attr, raw
 
+    def text_attribution(self, ctx: torch.Tensor, tok: torch.Tensor):
+        """The INTENDED attribution pass alone (rows A7/A8): returns (attr [C,P], raw [C,P])."""
+        _check_cuda_f32(ctx, "ctx")
+        _check_cuda_f32(tok, "tok")
+        Cn, P, D = ctx.shape
+        if tok.shape != (Cn, self.cfg.context_length, D) or D != self.cfg.text_width:
+            raise ValueError(f"Unexpected token shape: {tuple(tok.shape)} for ctx {tuple(ctx.shape)}")
+        attr = torch.empty(Cn, P, device=ctx.device, dtype=torch.float32)
+        raw = torch.empty(Cn, P, device=ctx.device, dtype=torch.float32)
+        _lib.check(self.lib.tapclip_text_forward(self._h, _lib.ptr(ctx), _lib.ptr(tok), Cn, P, _lib.ATTR_MODE["attribution_only"], 0,
+                                                 _lib.ptr(raw), _lib.ptr(attr), None, _lib.stream_ptr()))
+        return attr, raw
+
     def logits(self, img_feat, text_feat, logit_scale, labels=None, inv_batch_total=None):
         B, Cn = img_feat.shape[0], text_feat.shape[0]
         dev = img_feat.device

@@ -31,12 +31,16 @@ class _TapClipFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, images, labels, need_grad, logit_scale, *ctx_params):
+        # ctx_params: the n_cls context Parameters ('scale': the engine reads them through the flat bank), or ONE adjusted
+        # [C,P,D] tensor produced by the 'gate' / 'residual' adjustor (then the engine runs its literal feature pass on it)
         eng = model.clip.engine
         pl = model.prompt_learner
         mode = model.clip.attribution
         shard = model._sharding()
         n_cls, P = pl.n_cls, pl.prompt_len
         lo, hi = shard.bounds(n_cls)
+        adjusted = ctx_params[0].detach().contiguous() if model._adjusted_path() else None
+        ctx.adjusted = adjusted is not None
 
         # The two towers are independent until the logit contraction: the (small, launch-bound) text passes run on a
         # side stream and fill the image tower's kernel tails; joined before the logits.
@@ -45,7 +49,7 @@ class _TapClipFunction(torch.autograd.Function):
             main = torch.cuda.current_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad)   # rows A6-A10, this rank's classes
+                text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad, adjusted)   # rows A6-A10, this rank's classes
             img_feat = model._encode_image(images)                                # row A4 (+ A-ext probes)
             main.wait_stream(side)
             for t in (text_local, attr_local, raw_local):
@@ -53,7 +57,7 @@ class _TapClipFunction(torch.autograd.Function):
                     t.record_stream(main)
         else:
             img_feat = model._encode_image(images)
-            text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad)
+            text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad, adjusted)
         text_feat = all_gather_rows(text_local, shard, n_cls)                     # [C, E]
         if labels is not None:
             b_total = shard.global_batch(images.shape[0])
@@ -61,8 +65,9 @@ class _TapClipFunction(torch.autograd.Function):
             loss = all_reduce_sum_(loss.clone(), shard) if shard.world > 1 else loss
         else:
             logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale)
-        model.clip.attention_maps[:] = [raw_local if raw_local is not None else attr_local]   # compact probe, see clip_wrapper.py
-        model.last_attribution = attr_local
+        if adjusted is None:
+            model.clip.attention_maps[:] = [raw_local if raw_local is not None else attr_local]   # compact probe, see clip_wrapper.py
+            model.last_attribution = attr_local
         ctx.model, ctx.shard, ctx.dims = model, shard, (n_cls, P, lo, hi)
         ctx.need_grad = need_grad
         ctx.save_for_backward(logits, dlogits_ce if dlogits_ce is not None else logits.new_empty(0), img_norm, logit_scale)
@@ -83,7 +88,7 @@ class _TapClipFunction(torch.autograd.Function):
             dl = dlogits_ce * g_loss
         if g_logits is not None:
             dl = g_logits.contiguous() if dl is None else dl + g_logits
-        n_in = 5 + n_cls
+        n_in = 5 + (1 if ctx.adjusted else n_cls)
         if dl is None:
             return (None,) * n_in
         d_text, d_scale = eng.logits_backward(dl.contiguous(), logits, img_norm, logit_scale)
@@ -95,7 +100,9 @@ class _TapClipFunction(torch.autograd.Function):
             d_local = d_text[lo:hi].contiguous()
             dctx_local = eng.text_backward(d_local, hi - lo, P)                    # row A13
             dctx = all_gather_rows(dctx_local.view(hi - lo, -1), shard, n_cls).view(n_cls, P, -1)
-            grads = list(dctx.unbind(0))
+            grads = [dctx] if ctx.adjusted else list(dctx.unbind(0))
+        elif ctx.adjusted:
+            grads = [None]
         return (None, None, None, None, d_scale.reshape(logit_scale.shape) if logit_scale.requires_grad else None, *grads)
 
 
@@ -112,7 +119,8 @@ class FullModel(nn.Module):
                                             device=clip_wrapper.device)
         self.n_cls = len(class_names)
         self.attribution_monitor = AttributionMonitor(prompt_len)
-        self.prompt_adjustor = PromptAdjustor(method=adjustor_method)
+        self.prompt_adjustor = PromptAdjustor(method=adjustor_method, dim=clip_wrapper.model.token_embedding.embedding_dim)
+        self.prompt_adjustor.to(clip_wrapper.model.text_projection.device)
         self.attr_lambda = attr_lambda          # stored, never read — as in the reference (model_wrapper.py:24-25)
         self.stab_lambda = stab_lambda
         dev = clip_wrapper.model.text_projection.device
@@ -159,10 +167,31 @@ class FullModel(nn.Module):
     def _sharding(self) -> ClassSharding:
         return ClassSharding.current(self.distributed)
 
-    def _text_features(self, lo, hi, need_grad):
+    def _adjusted_path(self):
+        """'gate' / 'residual': the adjusted context is built by torch ops outside the engine (prompt_adjustor.py:38-44)."""
+        return self.prompt_adjustor.method != "scale"
+
+    def _adjusted_context(self, params):
+        """model_wrapper.py:55-66 for all classes at once: attribution of the un-adjusted prompts (detached, as the hook's
+        ``.detach()`` makes it in the reference), then PromptAdjustor on the [C,P,D] bank -- differentiable w.r.t. the
+        context vectors and the adjustor's own parameters."""
+        pl = self.prompt_learner
+        bank = torch.stack(list(params), 0)                                   # [C, P, D], autograd fans the gradient back out
+        if self.clip.attribution == "intended":
+            attr, raw = self.clip.engine.text_attribution(pl.flat_ctx(), pl.flat_tok())
+            self.clip.attention_maps[:] = [raw]
+        else:
+            attr = bank.new_ones(bank.shape[0], 1)                             # literal hook: attribution == 1.0 (SURVEY fact 6)
+            self.clip.attention_maps[:] = [attr]
+        self.last_attribution = attr
+        return self.prompt_adjustor(bank, attr)            # attr [C,P] or [C,1]: broadcasts exactly like the reference's [B,1,1]
+
+    def _text_features(self, lo, hi, need_grad, adjusted=None):
         """Rows A6-A10 for classes [lo, hi).  With ctx unchanged and no gradient needed (evaluation: the reference
         recomputes the text side for every batch, test_cross_domain.py:84) the result is reused."""
         pl = self.prompt_learner
+        if adjusted is not None:                                               # feature pass on the host-adjusted context
+            return self.clip.engine.text_forward(adjusted[lo:hi].contiguous(), pl.flat_tok()[lo:hi], "literal", need_grad)
         ctx_bank = pl.flat_ctx()
         use_cache = self.cache_text_features and not need_grad and not self.training
         if use_cache:
@@ -185,7 +214,12 @@ class FullModel(nn.Module):
             return outputs
         # grad mode is off inside autograd.Function.forward, so decide here whether activations must be kept
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        logits, loss = _TapClipFunction.apply(self, images, labels, need_grad, self.logit_scale, *params)
+        if self._adjusted_path():
+            adj = self._adjusted_context(params)
+            need_grad = torch.is_grad_enabled() and adj.requires_grad
+            logits, loss = _TapClipFunction.apply(self, images, labels, need_grad, self.logit_scale, adj)
+        else:
+            logits, loss = _TapClipFunction.apply(self, images, labels, need_grad, self.logit_scale, *params)
         outputs = {"logits": logits}                                           # model_wrapper.py:88
         if labels is not None:                                                 # model_wrapper.py:90-93
             outputs.update({"loss": loss, "loss_cls": loss})

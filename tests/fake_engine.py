@@ -35,6 +35,9 @@ class FakeEngine:
         raw = amap[:, :P, amap.shape[1] - 1].clone()
         return F.softmax(raw, dim=-1), raw
 
+    def text_attribution(self, ctx, tok):
+        return self._attribution(torch.cat([ctx, tok], dim=1), ctx.shape[1], "intended")
+
     def text_forward(self, ctx, tok, mode, save_for_backward):
         P = ctx.shape[1]
         attr, raw = self._attribution(torch.cat([ctx, tok], dim=1), P, mode)

@@ -15,19 +15,19 @@ def load_golden(case, mode):
     return torch.load(os.path.join(GOLDEN_DIR, f"{case}_{mode}.pt"), map_location="cpu", weights_only=False)
 
 
-def build_oracle(model_name, C_, P, mode, seed=0):
+def build_oracle(model_name, C_, P, mode, seed=0, method="scale"):
     wrapper = StandInCLIPWrapper(model_name, device="cpu", seed=seed, attribution=mode)
     torch.manual_seed(CTX_SEED)
-    model = OracleFullModel(class_names(C_), wrapper, prompt_len=P)
+    model = OracleFullModel(class_names(C_), wrapper, prompt_len=P, adjustor_method=method)
     return wrapper, model
 
 
-def build_cuda(model_name, C_, P, mode, dtype, oracle_wrapper):
-    """tapclip_b200 model with the oracle's weights and the same ctx draw (global CPU RNG, seed 4)."""
+def build_cuda(model_name, C_, P, mode, dtype, oracle_wrapper, method="scale"):
+    """tapclip_b200 model with the oracle's weights and the same ctx (+ adjustor) draw (global CPU RNG, seed 4)."""
     import tapclip_b200 as tb
     clip = tb.CLIPWrapper(model_name, None, "cuda", state_dict=oracle_wrapper.model.state_dict(), attribution=mode, dtype=dtype)
     torch.manual_seed(CTX_SEED)
-    model = tb.FullModel(class_names(C_), clip, prompt_len=P)
+    model = tb.FullModel(class_names(C_), clip, prompt_len=P, adjustor_method=method)
     return clip, model
 
 

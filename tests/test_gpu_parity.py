@@ -177,3 +177,31 @@ def test_full_size_properties_mixed():
     with torch.no_grad():
         ls = sub(images)["logits"]
     assert torch.equal(ls, l0[:, :32])
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "mixed"])
+@pytest.mark.parametrize("mode", ["literal", "intended"])
+@pytest.mark.parametrize("case", ["mini16_gate_b3c4p4", "minit512_resid_b2c3p5"])
+def test_gate_and_residual_adjustors_vs_reference_golden(case, mode, dtype):
+    """PromptAdjustor 'gate' / 'residual' (models/prompt_adjustor.py:13-25,38-44) against the reference's
+    own FullModel: logits, ctx gradients and the gradients of the adjustor networks' parameters."""
+    gold = load_golden(case, mode)
+    name, B, C, P = gold["model_name"], gold["B"], gold["C"], gold["P"]
+    ow, _ = build_oracle(name, C, P, mode)
+    clip, model = build_cuda(name, C, P, mode, dtype, ow, method=gold["method"])
+    for k, v in model.prompt_adjustor.state_dict().items():
+        assert torch.equal(v.cpu(), gold["adjustor_state"][k])          # same constructor RNG order as the reference
+    model.train()
+    images, labels = synthetic_images(B, get_config(name).image_size).cuda(), synthetic_labels(B, C).cuda()
+    out = model(images, labels)
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    e_logits = max_abs(out["logits"], gold["logits"])
+    e_grad = rel_err(ctx_grads(model, C), gold["ctx_grad"])
+    e_adj = max(rel_err(p.grad, gold["adjustor_grad"][k]) for k, p in model.prompt_adjustor.named_parameters()
+                if gold["adjustor_grad"][k].norm() > 0)
+    e_attr = ((model.last_attribution.cpu() - gold["attribution"]).abs() / gold["attribution"].abs()).max().item()
+    print(f"\n[parity] {case} {mode} {dtype}: max|dlogit|={e_logits:.3e} ctx_grad_relL2={e_grad:.3e} adjustor_grad_relL2={e_adj:.3e} attr_rel={e_attr:.3e}")
+    assert e_logits <= LOGIT_TOL[dtype]
+    assert e_attr <= 1e-3
+    assert e_grad <= GRAD_TOL[dtype] and e_adj <= GRAD_TOL[dtype]

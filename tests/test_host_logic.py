@@ -11,7 +11,7 @@ from oracle.tapclip_oracle import class_names, synthetic_images, synthetic_label
 
 def test_configs_and_flops_match_the_survey():
     from tapclip_b200.configs import flops_per_image, flops_per_text_sequence, get_model_config
-    for name in ("ViT-B-32", "ViT-B-16", "ViT-L-14-336", "ViT-B-16-quickgelu", "mini-16", "mini-14"):
+    for name in ("ViT-B-32", "ViT-B-16", "ViT-L-14-336", "ViT-B-16-quickgelu", "mini-16", "mini-14", "mini-t512"):
         a, b = get_model_config(name), get_config(name)
         for f in ("embed_dim", "image_size", "patch_size", "vision_width", "vision_layers", "vision_heads", "text_width",
                   "text_layers", "text_heads", "context_length", "vocab_size", "quick_gelu"):
@@ -63,6 +63,31 @@ def test_fullmodel_host_path_matches_reference_golden(case, mode):
     assert set(model(images)) == {"logits"}                                        # model_wrapper.py:88-93
 
 
+@pytest.mark.parametrize("mode", ["literal", "intended"])
+@pytest.mark.parametrize("case", ["mini16_gate_b3c4p4", "minit512_resid_b2c3p5"])
+def test_fullmodel_gate_and_residual_adjustors_match_reference_golden(case, mode):
+    import tapclip_b200 as tb
+    gold = load_golden(case, mode)
+    B, C, P = gold["B"], gold["C"], gold["P"]
+    ow, _ = build_oracle(gold["model_name"], C, P, mode)
+    torch.manual_seed(4)
+    model = tb.FullModel(class_names(C), FakeWrapper(ow, mode), prompt_len=P, adjustor_method=gold["method"])
+    assert set(model.prompt_adjustor.state_dict()) == set(gold["adjustor_state"])
+    for k, v in model.prompt_adjustor.state_dict().items():
+        assert torch.equal(v, gold["adjustor_state"][k])                           # same constructor RNG order as the reference
+    images, labels = synthetic_images(B, get_config(gold["model_name"]).image_size), synthetic_labels(B, C)
+    model.train()
+    out = model(images, labels)
+    out["loss"].backward()
+    g = torch.stack([model.prompt_learner.context_bank[n].grad for n in class_names(C)])
+    assert (out["logits"] - gold["logits"]).abs().max().item() < 5e-5
+    assert ((g - gold["ctx_grad"]).norm() / gold["ctx_grad"].norm()).item() < 1e-4
+    for k, p in model.prompt_adjustor.named_parameters():
+        ref = gold["adjustor_grad"][k]
+        assert ((p.grad - ref).norm() / ref.norm().clamp_min(1e-12)).item() < 1e-4, k
+    assert (model.last_attribution - gold["attribution"]).abs().max().item() < 1e-6
+
+
 def test_flat_bank_parameter_identity_and_growth():
     gold, ow, om, model = _models("mini16_b4c5p4", "literal")
     pl = model.prompt_learner
@@ -105,10 +130,23 @@ def test_prompt_adjustor_and_errors():
     import tapclip_b200 as tb
     with pytest.raises(ValueError, match="Unknown method"):
         tb.PromptAdjustor("bogus")
-    with pytest.raises(NotImplementedError):
-        tb.PromptAdjustor("gate")
     x, a = torch.randn(2, 3, 8), torch.rand(2, 3)
     assert torch.equal(tb.PromptAdjustor("scale")(x, a), x * a.unsqueeze(-1))
+    # 'gate' / 'residual' against the reference module itself (models/prompt_adjustor.py:13-25,38-44), same weights
+    import importlib.util, os
+    ref_path = "/root/reference/models/prompt_adjustor.py"
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("ref_prompt_adjustor", ref_path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        x = torch.randn(2, 3, 512)
+        for method in ("gate", "residual"):
+            torch.manual_seed(0)
+            mine = tb.PromptAdjustor(method, dim=512)
+            theirs = ref.PromptAdjustor(method)
+            assert set(mine.state_dict()) == set(theirs.state_dict())
+            theirs.load_state_dict(mine.state_dict())
+            assert torch.equal(mine(x, a), theirs(x, a))
 
 
 def test_class_sharding_bounds():

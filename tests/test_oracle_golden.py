@@ -66,3 +66,33 @@ def test_text_side_does_not_depend_on_the_sample():
     x = raw_prompt[1].unsqueeze(0).expand(4, -1, -1)
     y = ow.model.transformer(x)
     assert torch.equal(y[0], y[3])
+
+
+ADJUSTOR = ["mini16_gate_b3c4p4", "minit512_resid_b2c3p5"]
+
+
+@pytest.mark.parametrize("mode", ["literal", "intended"])
+@pytest.mark.parametrize("case", ADJUSTOR)
+def test_gate_and_residual_adjustors_are_bit_exact(case, mode):
+    """PromptAdjustor 'gate' / 'residual' (models/prompt_adjustor.py:13-25,38-44) driven through the reference's FullModel:
+    logits, ctx gradients and the adjustor networks' own gradients."""
+    gold = load_golden(case, mode)
+    B, C, P = gold["B"], gold["C"], gold["P"]
+    _, m = build_oracle(gold["model_name"], C, P, mode, method=gold["method"])
+    for k, v in m.prompt_adjustor.state_dict().items():
+        assert torch.equal(v, gold["adjustor_state"][k])                  # same RNG order as the reference's constructor
+    m.train()
+    images, labels = synthetic_images(B, get_config(gold["model_name"]).image_size), synthetic_labels(B, C)
+    out = m.forward_as_written(images, labels)
+    out["loss"].backward()
+    assert torch.equal(out["logits"], gold["logits"]) and torch.equal(_grads(m, C), gold["ctx_grad"])
+    for k, p in m.prompt_adjustor.named_parameters():
+        assert torch.equal(p.grad, gold["adjustor_grad"][k]), k
+    m.zero_grad()
+    out = m.forward_dedup(images, labels)
+    out["loss"].backward()
+    assert (out["logits"] - gold["logits"]).abs().max().item() < 5e-5
+    assert ((_grads(m, C) - gold["ctx_grad"]).norm() / gold["ctx_grad"].norm()).item() < 1e-4
+    for k, p in m.prompt_adjustor.named_parameters():
+        ref = gold["adjustor_grad"][k]
+        assert ((p.grad - ref).norm() / ref.norm().clamp_min(1e-12)).item() < 1e-4, k
