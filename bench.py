@@ -366,6 +366,10 @@ def run_ours(args, wl):
             "step_executed_tflop_per_gpu": (flops_step - dead) / 1e12,
             "step_tflops_achieved_per_gpu": flops_step / (ms_resident / args.steps * 1e-3) / 1e12,
             "step_frac_of_peak": flops_step / (ms_resident / args.steps * 1e-3) / 1e12 / peaks["bf16_sustained"],
+            # per-launch DRAM traffic of the four image-tower GEMM shapes from the committed `ncu --set full` capture
+            # (profiles/r01n_ncu_full_gemm_tc_vision_layer0.csv: dram__bytes_read.sum + dram__bytes_write.sum, MB)
+            "ncu_dram_mb_per_launch": {"qkv M=25216 N=2304 K=768": 100.5, "out M=25216 N=768 K=768": 137.6,
+                                       "fc M=25216 N=3072 K=768": 139.7, "proj M=25216 N=768 K=3072": 279.3},
             "top_shapes": [{"shape": k, "launches": v["launches"], "ms": round(v["ms"], 4),
                             "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else None} for k, v in top],
         },
