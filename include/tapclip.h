@@ -135,6 +135,15 @@ TAPCLIP_API int tapclip_profile(tapclip_handle h, int32_t enable);
 TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
 
 /* ---- single-kernel entry points (used by the per-kernel parity tests and micro-benchmarks) -------- */
+/* Image preprocessing on the device: what `CLIPWrapper.get_preprocess()` (models/clip_wrapper.py:64-65,
+ * open_clip's inference transform, applied per image at dataset.py:31) does on the host with Pillow/torchvision:
+ * Resize(R, BICUBIC) of the shorter side -> CenterCrop(R) -> ToTensor -> Normalize(mean, std).
+ *   image_hwc [H, W, 3] uint8 RGB (device), out_chw [3, R, R] fp32 (device); (crop_top, crop_left) = the crop window's
+ *   origin in the resized image (torchvision: int(round((size - R) / 2.0))); mean3 / std3: HOST float[3].
+ * Bit-exact with Pillow's 8-bit antialiased bicubic resampling (two fixed-point passes, uint8 intermediate). */
+TAPCLIP_API int tapclip_op_preprocess(const uint8_t* image_hwc, int32_t H, int32_t W, float* out_chw, int32_t R, int32_t crop_top,
+                          int32_t crop_left, const float* mean3, const float* std3, void* stream);
+
 /* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias).  dtype BF16/FP16: A,W (and epi-0 out) 16-bit, tcgen05 path; FP32: SIMT path.
  * epi: 0 = store activation type (+act, optional out_pre), 1 = store fp32, 2 = fp32 += ,
  *      3 = out = (A.W^T + bias) * act'(out_pre) with out_pre READ as the saved pre-activations (same 16-bit type as A),

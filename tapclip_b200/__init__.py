@@ -10,9 +10,10 @@ from .clip_wrapper import CLIPWrapper
 from .configs import get_model_config
 from .model_wrapper import FullModel
 from .optim import FusedAdamW
+from .preprocess import GpuPreprocess
 from .prompt_adjustor import PromptAdjustor
 from .prompt_learner import PromptLearner
 
 __all__ = ["CLIPWrapper", "FullModel", "PromptLearner", "AttributionMonitor", "PromptAdjustor", "FusedAdamW",
-           "get_model_config"]
+           "GpuPreprocess", "get_model_config"]
 __version__ = "0.1.0"

@@ -25,6 +25,7 @@ import torch.nn as nn
 
 from .configs import ModelConfig, get_model_config
 from .engine import Engine
+from .preprocess import GpuPreprocess
 from .tokenizer import SyntheticTokenizer
 
 
@@ -168,7 +169,8 @@ class CLIPWrapper(nn.Module):
         self.dtype = dtype
         cfg = get_model_config(model_name)
         self.model = EngineCLIP(cfg).to(device)                      # clip_wrapper.py:13,16
-        self.preprocess = None                                       # PIL transform pipeline: host I/O, out of scope
+        # open_clip's inference transform (Resize-BICUBIC / CenterCrop / ToTensor / Normalize) on the device (clip_wrapper.py:13)
+        self.preprocess = GpuPreprocess(cfg.image_size, device=device) if torch.device(device).type == "cuda" else None
         if pretrained_path is not None and state_dict is None:       # clip_wrapper.py:14
             state_dict = torch.load(pretrained_path, map_location=device)
         self.engine = Engine(cfg, dtype=dtype, device=device)

@@ -147,6 +147,14 @@ TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias,
     TC_API_END
 }
 
+TAPCLIP_API int tapclip_op_preprocess(const uint8_t* image_hwc, int32_t H, int32_t W, float* out_chw, int32_t R, int32_t crop_top,
+                          int32_t crop_left, const float* mean3, const float* std3, void* stream) {
+    TC_API_BEGIN
+    TC_CHECK(image_hwc != nullptr && out_chw != nullptr && mean3 != nullptr && std3 != nullptr, "null argument");
+    preprocess_image(image_hwc, H, W, out_chw, R, crop_top, crop_left, mean3, std3, S(stream));
+    TC_API_END
+}
+
 TAPCLIP_API int tapclip_op_layernorm(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out, int32_t out_dtype,
                          float* x_copy, int64_t rows, int32_t d, void* stream) {
     TC_API_BEGIN

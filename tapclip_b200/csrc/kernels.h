@@ -93,4 +93,10 @@ void adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float l
 // argmax over classes + count of argmax==label (utils/eval_metrics.py:19-29 without per-sample .item())
 void argmax_count(const float* logits, const int64_t* labels, int64_t* pred, int* correct, int B, int C, cudaStream_t stream);
 
+// ---- preprocess.cu ---------------------------------------------------------------------------------
+// img [H, W, 3] uint8 RGB (device) -> out [3, R, R] fp32: bicubic resize of the shorter side to R (Pillow's antialiased
+// fixed-point resampling), crop window at (top, left) of the resized image, /255, (x - mean) / std.  mean / stdv: host float[3].
+void preprocess_image(const uint8_t* img, int H, int W, float* out, int R, int top, int left, const float* mean, const float* stdv,
+                      cudaStream_t stream);
+
 }  // namespace tapclip

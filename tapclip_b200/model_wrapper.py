@@ -50,15 +50,16 @@ class _TapClipFunction(torch.autograd.Function):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad, adjusted)   # rows A6-A10, this rank's classes
+                text_feat = all_gather_rows(text_local, shard, n_cls)             # [C, E]; the collective hides behind the image tower too
             img_feat = model._encode_image(images)                                # row A4 (+ A-ext probes)
             main.wait_stream(side)
-            for t in (text_local, attr_local, raw_local):
+            for t in (text_local, attr_local, raw_local, text_feat):
                 if t is not None:
                     t.record_stream(main)
         else:
             img_feat = model._encode_image(images)
             text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad, adjusted)
-        text_feat = all_gather_rows(text_local, shard, n_cls)                     # [C, E]
+            text_feat = all_gather_rows(text_local, shard, n_cls)                 # [C, E]
         if labels is not None:
             b_total = shard.global_batch(images.shape[0])
             logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale, labels, 1.0 / b_total)

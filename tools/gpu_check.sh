@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 files="$@"
-[ -z "$files" ] && files="tests/test_gpu_gemm.py tests/test_gpu_kernels.py tests/test_gpu_parity.py tests/test_gpu_api.py"
+[ -z "$files" ] && files="tests/test_gpu_gemm.py tests/test_gpu_kernels.py tests/test_gpu_parity.py tests/test_gpu_api.py tests/test_gpu_preprocess.py"
 rc=0
 for f in $files; do
   name=$(basename $f .py)
