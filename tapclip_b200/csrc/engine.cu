@@ -361,8 +361,7 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
 
     patchify(images, v_patches.p, vdt, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
     gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, vdt, st);
-    assemble_tokens((const float*)v_patch_out.p, cls_emb, pos_emb, (float*)v_x.p, B, N, d, st); ++launches;
-    layernorm_fwd((const float*)v_x.p, d, ln_pre_g, ln_pre_b, v_x.p, DT_F32, nullptr, M, d, st); ++launches;
+    assemble_ln_pre((const float*)v_patch_out.p, cls_emb, pos_emb, ln_pre_g, ln_pre_b, (float*)v_x.p, B, N, d, st); ++launches;
     for (int l = 0; l < L; ++l) {
         AttnProbe probe;
         if (out_cls_rows) {

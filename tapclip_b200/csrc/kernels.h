@@ -11,6 +11,9 @@ namespace tapclip {
 // (saved for the backward pass).  In-place fp32 (out == x) is allowed.
 void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out,
                    int out_dt, float* x_copy, int64_t rows, int d, cudaStream_t stream);
+// x[b,t,:] = LayerNorm(cat([cls, patch_out[b]])[t,:] + pos[t,:]) with (gamma, beta) = ln_pre: the vision tower's prologue
+void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta, float* x,
+                     int B, int n_tokens, int d, cudaStream_t stream);
 // dx_acc[r,:] += LN'(dy[r,:]; x[r,:], gamma)  (mean/rstd recomputed from x);  dx_cast (optional, activation
 // type) receives the updated dx_acc row cast to the activation type.
 void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast,

@@ -67,6 +67,54 @@ layernorm_fwd_kernel(const float* x, int64_t x_row_stride, const float* __restri
         }
 }
 
+// open_clip VisionTransformer.forward prologue in one pass: x[b,t,:] = ln_pre(cat([class_embedding, patches])[b,t,:] + pos[t,:])
+// (replaces assemble_tokens + an in-place LayerNorm: the fp32 token matrix is written once instead of three times)
+__global__ void __launch_bounds__(WARPS * 32)
+assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls, const float* __restrict__ pos,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x, int64_t rows,
+                       int n_tokens, int d) {
+    pdl_wait_and_trigger();
+    const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, nv = d >> 7;
+    const int t = (int)(row % n_tokens);
+    const int64_t b = row / n_tokens;
+    const float* src = (t == 0) ? cls : patch_out + (b * (n_tokens - 1) + (t - 1)) * d;
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            v[i] = __ldg(reinterpret_cast<const float4*>(src + c));
+            const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)t * d + c));
+            v[i].x += pe.x; v[i].y += pe.y; v[i].z += pe.z; v[i].w += pe.w;
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, e = v[i].w - mean;
+            q += (a * a + b2 * b2) + (c2 * c2 + e * e);
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float4 o;
+            o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+            o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+            o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+            o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+            *reinterpret_cast<float4*>(x + row * d + c) = o;
+        }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
@@ -188,6 +236,16 @@ void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, con
     if (out_dt == DT_BF16) launch_pdl(layernorm_fwd_kernel<bf16>, grid, WARPS * 32, 0, stream, x, x_row_stride, gamma, beta, (bf16*)out, x_copy, rows, d);
     else if (out_dt == DT_F16) launch_pdl(layernorm_fwd_kernel<f16>, grid, WARPS * 32, 0, stream, x, x_row_stride, gamma, beta, (f16*)out, x_copy, rows, d);
     else launch_pdl(layernorm_fwd_kernel<float>, grid, WARPS * 32, 0, stream, x, x_row_stride, gamma, beta, (float*)out, x_copy, rows, d);
+    TC_LAUNCH_CHECK();
+}
+
+void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta, float* x,
+                     int B, int n_tokens, int d, cudaStream_t stream) {
+    check_d(d);
+    const int64_t rows = (int64_t)B * n_tokens;
+    if (rows == 0) return;
+    launch_pdl(assemble_ln_pre_kernel, (unsigned)ceil_div(rows, WARPS), WARPS * 32, 0, stream, patch_out, cls, pos, gamma, beta, x, rows,
+               n_tokens, d);
     TC_LAUNCH_CHECK();
 }
 
