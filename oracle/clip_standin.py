@@ -71,6 +71,7 @@ _BASE = {
     # small shapes for tests (same code path, head_dim 64 everywhere)
     "mini-16": CLIPConfig("mini-16", 256, 64, 16, 256, 2, 4, 256, 2, 4),
     "mini-14": CLIPConfig("mini-14", 128, 56, 14, 128, 3, 2, 128, 2, 2),
+    "mini-n197": CLIPConfig("mini-n197", 128, 224, 16, 128, 2, 2, 128, 2, 2),   # ViT-B/16 token count (197) on a tiny width
     "mini-t512": CLIPConfig("mini-t512", 256, 64, 16, 256, 2, 4, 512, 2, 8),   # text width 512: PromptAdjustor 'residual' hard-codes it
 }
 

@@ -37,6 +37,7 @@ _TABLE = {
     "ViT-L-14-336": ModelConfig("ViT-L-14-336", 768, 336, 14, 1024, 24, 16, 768, 12, 12),
     "mini-16": ModelConfig("mini-16", 256, 64, 16, 256, 2, 4, 256, 2, 4),
     "mini-14": ModelConfig("mini-14", 128, 56, 14, 128, 3, 2, 128, 2, 2),
+    "mini-n197": ModelConfig("mini-n197", 128, 224, 16, 128, 2, 2, 128, 2, 2),   # ViT-B/16 token count (197) on a tiny width
     "mini-t512": ModelConfig("mini-t512", 256, 64, 16, 256, 2, 4, 512, 2, 8),   # text width 512 (PromptAdjustor 'residual')
 }
 

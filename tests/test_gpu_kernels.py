@@ -86,6 +86,38 @@ def test_attention_fwd_and_probes(S, N, H, dtype):
     assert (attr - torch.softmax(ref_raw, -1)).abs().max().item() < tol_p
 
 
+@pytest.mark.parametrize("S,N,H", [(86, 197, 6), (128, 93, 8), (100, 50, 12), (70, 208, 8), (90, 129, 6), (140, 64, 8)])
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_attention_fwd_tcgen05_persistent_kernel(S, N, H, dtype):
+    """Shapes with >= 1024 (sequence, head, q-tile) items take the persistent tcgen05 kernel (attention_tc.cu) in all three
+    chunk-count instances (N <= 64 / 128 / 208), with both probes; the small shapes above exercise the mma.sync kernel."""
+    assert S * H * ((N + 127) // 128) >= 1024
+    L, lib = _lib()
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(S + N + H)
+    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16}[dtype]
+    qkv = (torch.randn(S * N, 3 * d, device="cuda", generator=g) * 1.5).to(tdt)
+    ref_o, ref_p = _ref_attention(qkv, S, N, H)
+    tol_o, tol_p = {"bf16": (2e-2, 2e-3), "fp16": (3e-3, 3e-4)}[dtype]
+    out = torch.empty(S * N, d, device="cuda", dtype=tdt)
+    rows = torch.zeros(S, H, N, device="cuda")
+    L.check(lib.tapclip_op_attention(L.ptr(qkv), L.ptr(out), L.DTYPE[dtype], S, N, H, L.PROBE_CLS_ROW, L.ptr(rows), 0, H * N, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (out.float() - ref_o).abs().max().item() < tol_o
+    assert (rows - ref_p[:, :, 0, :]).abs().max().item() < tol_p
+    P = min(16, N - 1)
+    col = torch.zeros(S, H, P, device="cuda")
+    out2 = torch.empty_like(out)
+    L.check(lib.tapclip_op_attention(L.ptr(qkv), L.ptr(out2), L.DTYPE[dtype], S, N, H, L.PROBE_TEXT_COL, L.ptr(col), P, 0, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+    assert (col - ref_p[:, :, :P, N - 1]).abs().max().item() < tol_p
+    out3 = torch.empty_like(out)
+    L.check(lib.tapclip_op_attention(L.ptr(qkv), L.ptr(out3), L.DTYPE[dtype], S, N, H, L.PROBE_NONE, None, 0, 0, L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(out3, out)
+
+
 @pytest.mark.parametrize("S,N,H", [(5, 93, 8), (2, 82, 4), (3, 17, 2), (1, 128, 8)])
 @pytest.mark.parametrize("dtype", ["bf16", "fp16", "fp32"])
 def test_attention_bwd(S, N, H, dtype):

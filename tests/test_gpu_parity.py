@@ -205,3 +205,25 @@ def test_gate_and_residual_adjustors_vs_reference_golden(case, mode, dtype):
     assert e_logits <= LOGIT_TOL[dtype]
     assert e_attr <= 1e-3
     assert e_grad <= GRAD_TOL[dtype] and e_adj <= GRAD_TOL[dtype]
+
+
+def test_large_batch_image_tower_on_the_tcgen05_attention_path():
+    """B=288 images of a 197-token tower: 1152 (image, head, q-tile) items, so the vision attention runs on the persistent
+    tcgen05 kernel (two q-tiles per head, CLS probe, last block with dead-row elimination and the dead q-tile skipped);
+    features, CLS rows and rollout are compared with the CPU oracle."""
+    from oracle.clip_standin import vision_attention_rollout, vision_cls_attention
+    name = "mini-n197"
+    ow, _ = build_oracle(name, 2, 4, "literal")
+    clip, _ = build_cuda(name, 2, 4, "literal", "mixed", ow)
+    B = 288
+    images = synthetic_images(B, get_config(name).image_size)
+    feats_ref, rows_ref = vision_cls_attention(ow.model, images)
+    roll_ref = vision_attention_rollout(ow.model, images)
+    feats, rows, roll = clip.model.image_attribution(images.cuda(), rollout=True)
+    plain = clip.encode_image(images.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(plain, feats)                                   # probes do not change the features
+    assert max_abs(feats, feats_ref) < 5e-2 * max(1.0, feats_ref.abs().max().item())
+    assert max_abs(rows, rows_ref) < 5e-3
+    assert (rows.sum(-1) - 1).abs().max().item() < 1e-3
+    assert max_abs(roll, roll_ref) < 5e-3

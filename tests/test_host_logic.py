@@ -11,7 +11,7 @@ from oracle.tapclip_oracle import class_names, synthetic_images, synthetic_label
 
 def test_configs_and_flops_match_the_survey():
     from tapclip_b200.configs import flops_per_image, flops_per_text_sequence, get_model_config
-    for name in ("ViT-B-32", "ViT-B-16", "ViT-L-14-336", "ViT-B-16-quickgelu", "mini-16", "mini-14", "mini-t512"):
+    for name in ("ViT-B-32", "ViT-B-16", "ViT-L-14-336", "ViT-B-16-quickgelu", "mini-16", "mini-14", "mini-t512", "mini-n197"):
         a, b = get_model_config(name), get_config(name)
         for f in ("embed_dim", "image_size", "patch_size", "vision_width", "vision_layers", "vision_heads", "text_width",
                   "text_layers", "text_heads", "context_length", "vocab_size", "quick_gelu"):
