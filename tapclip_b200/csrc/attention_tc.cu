@@ -1,14 +1,16 @@
 // K2 on tcgen05: fused attention forward for sequences of up to 256 tokens (ViT-B/16: 197, ViT-B/32: 50, text: P+77),
 // head dim 64, no mask, with the same probe epilogue as attention.cu.
 //
-// One CTA per (sequence, head, 128-query tile):
+// Work item = (sequence, head, 128-query tile):
 //   TMA   Q tile [128 x 64], K and V [NKP x 64] (NKP = keys padded to 16) into 128B-swizzled smem
 //   MMA1  S = Q K^T        tcgen05.mma  M=128, N=NKP, K=64  (A, B K-major from smem)  -> TMEM columns [0, NKP)
-//   4 softmax warps: one thread per query row reads its S row from TMEM (two passes: max, then exp2/sum), writes
-//         the 16-bit probabilities BACK INTO TMEM over the S columns (two keys per 32-bit column) and emits the probe
+//   softmax: one thread per query row reads its S row from TMEM, takes the max, computes exp2 / row sum, writes the 16-bit
+//         probabilities BACK INTO TMEM over the S columns (two keys per 32-bit column) and emits the probe
 //   MMA2  O = P V          tcgen05.mma  M=128, N=64, K=NKP   (A = P from TMEM, B = V as stored: MN-major smem descriptor)
 //   epilogue: O / rowsum -> 16-bit -> global
 // S, P and O never touch shared memory or HBM; the N x N map is never materialised.
+// Two kernels: attn_fwd_tc2_kernel (NKP <= 208: persistent, warp-specialised, described at its definition) and
+// attn_fwd_tc_kernel (208 < NKP <= 256: one CTA per item, the simple form of the same data flow).
 #include "gemm.h"
 #include "kernels.h"
 #include <cstdlib>

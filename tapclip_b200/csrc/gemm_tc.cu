@@ -3,11 +3,13 @@
 // Replaces the cuBLAS `addmm` calls behind nn.Linear / nn.MultiheadAttention in_proj/out_proj of the
 // reference's third-party model (SURVEY.md 2.3 rows k2,k5,k8,k10 + patch-embed + the two projections).
 //
-// Structure (one persistent CTA per SM, 192 threads):
-//   warp 0      TMA producer: 128B-swizzled A (128x64) and W tiles into a 4..6-stage smem ring
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (fp32 accumulate in TMEM)
-//   warps 2..5  epilogue: tcgen05.ld TMEM -> registers -> bias / activation -> swizzled smem transpose -> coalesced
-//               16-byte global stores (red.global.add.v4.f32 for the fp32 residual stream)
+// Structure (one persistent CTA per SM, 320 threads):
+//   warp 0      TMA producer: 128B-swizzled A (128x64) and W tiles into a 4..8-stage smem ring
+//   warp 1      TMEM allocator + tcgen05.mma issuer (fp32 accumulate in TMEM).  The single-CTA path runs the issue loop
+//               warp-converged with elect.sync-predicated instructions, so the UTCHMMA operands live in uniform registers
+//   warps 2..9  epilogue, two warps per TMEM lane quarter (alternating 128-byte column chunks): tcgen05.ld TMEM ->
+//               registers -> bias (staged in smem) / activation / activation-gradient -> swizzled smem transpose ->
+//               coalesced 16-byte streaming stores (red.global.add.v4.f32 for the fp32 residual stream)
 // Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  M/N/K tails are handled by TMA zero-fill on loads and clipping on stores.
 //
@@ -15,7 +17,7 @@
 //   CTA2 = false  cta_group::1, UMMA 128 x BLOCK_N x 16, one CTA per tile (48 KB of operands per k-block).
 //   CTA2 = true   cta_group::2, UMMA 256 x BLOCK_N x 16 issued by the leader of a 2-CTA cluster: each CTA holds its
 //                 own 128 rows of A and HALF of the W tile (32 KB per k-block -> 1.5x fewer L2->SM bytes per flop,
-//                 6 stages in flight).  The mainloop of the 1-CTA shape is L2-feed-bound (ncu: 64-73 % tensor pipe).
+//                 6 stages in flight).  Measured equal to the 1-CTA shape on the image-tower GEMMs, slower on small ones.
 #include "gemm.h"
 #include <type_traits>
 #include <cstdlib>
