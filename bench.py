@@ -334,7 +334,11 @@ def run_ours(args, wl):
     f_img, f_txt = flops_per_image(cfg), flops_per_text_sequence(cfg, P + cfg.context_length)
     flops_step = B * f_img + 2 * c_local * f_txt + 2 * B * C * cfg.embed_dim + (c_local * f_txt if train else 0)
     # executed FLOPs: the last vision block runs its out-projection and MLP on the CLS row only (dead-row elimination)
-    dead = 0.0 if os.environ.get("TAPCLIP_DEAD_ROWS") == "0" else B * (cfg.vision_tokens - 1) * 18.0 * cfg.vision_width ** 2
+    # (and the text feature pass / its backward on position T-1 only)
+    t_len = P + cfg.context_length
+    dead = 0.0 if os.environ.get("TAPCLIP_DEAD_ROWS") == "0" else (
+        B * (cfg.vision_tokens - 1) * 18.0 * cfg.vision_width ** 2
+        + c_local * (t_len - 1) * 18.0 * cfg.text_width ** 2 * (2 if train else 1))
     gemm = prof.get("gemm", {"launches": 0, "ms": 0.0, "flops": 0.0})
     gemm_tflops = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else None
     top = sorted(((k, v) for k, v in prof.get("shapes", {}).items()), key=lambda kv: -kv[1]["ms"])[:8]

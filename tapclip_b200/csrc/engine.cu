@@ -326,12 +326,13 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
         // Dead-row elimination: after the LAST block only token `live_row` of every sequence is read (ln_post(x[:,0])
         // / pooling), and past the attention every row is independent.  The out-projection and the MLP therefore run on the
         // S live rows only, addressed in place through the GEMM's leading dimensions (no gather, no copy).
-        TC_CHECK(save_slot < 0, "dead-row elimination is forward-only");
+        // With save_slot >= 0 the LN2 input and the MLP pre-activation of the live rows are kept COMPACT ([S, d] / [S, 4d]) at
+        // the start of the layer's save slots: text_backward treats the last block the same way.
         const int64_t ld = (int64_t)N * d;
         float* xl = x + (int64_t)live_row * d;
         gemm((const uint8_t*)attn.p + (int64_t)live_row * d * esz, b.w_o, b.b_o, xl, nullptr, S, d, d, EPI_F32_ADD, ACT_NONE, dt, st, DT_BF16, ld, ld);
-        layernorm_fwd(xl, ld, b.ln2_g, b.ln2_b, ln.p, dt, nullptr, S, d, st); ++launches;
-        gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, nullptr, S, 4 * d, d, EPI_BF16, cfg.act, dt, st);
+        layernorm_fwd(xl, ld, b.ln2_g, b.ln2_b, ln.p, dt, sx1, S, d, st); ++launches;
+        gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, S, 4 * d, d, EPI_BF16, cfg.act, dt, st);
         gemm(hbuf.p, b.w_proj, b.b_proj, xl, nullptr, S, d, 4 * d, EPI_F32_ADD, ACT_NONE, dt, st, DT_BF16, 0, ld);
         return;
     }
@@ -437,13 +438,15 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
     splice_prompts(ctx, tok, attr, PA, x, C, P, Lc, D, st); ++launches;
     for (int l = 0; l < L; ++l) {
         AttnProbe none;
-        block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, none, false, save ? l : -1, st);
+        // last block: only position T-1 is pooled (model_wrapper.py:73) -> out-projection and MLP on C rows
+        block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, none, false, save ? l : -1, st, nullptr,
+                      (l == L - 1 && dead_rows) ? T - 1 : -1);
     }
     gather_rows(x, t_pooled.p, tdt, C, T, T - 1, D, st); ++launches;
     gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, tdt, st);
     l2norm_fwd((const float*)t_feat.p, (float*)t_tfeat.p, (float*)t_inv_norm.p, C, E, st); ++launches;
     if (out_text_feat) TC_CUDA(cudaMemcpyAsync(out_text_feat, t_tfeat.p, (size_t)C * E * 4, cudaMemcpyDeviceToDevice, st));
-    if (save) { saved.valid = true; saved.C = C; saved.P = P; saved.T = T; saved.PA = PA; saved.has_attr = (mode == 1); }
+    if (save) { saved.valid = true; saved.C = C; saved.P = P; saved.T = T; saved.PA = PA; saved.has_attr = (mode == 1); saved.dead_last = dead_rows; }
 }
 
 // ---- standard CLIP text path (CLIPWrapper.encode_text, clip_wrapper.py:49-51; never called by FullModel) ---------------
@@ -503,6 +506,29 @@ void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream
         const float* x1 = (const float*)t_save_x.p + (int64_t)(2 * l + 1) * M * D;
         const void* qkv = (const uint8_t*)t_save_qkv.p + (int64_t)l * M * 3 * D * esz;
         const void* hpre = (const uint8_t*)t_save_h.p + (int64_t)l * M * 4 * D * esz;
+        if (l == L - 1 && saved.dead_last) {
+            // Last block, dead-row form (see block_forward): the incoming gradient is non-zero at position T-1 only, so the MLP
+            // and out-projection backward run on C rows addressed in place (leading dimension T*D); the saved LN2 input and
+            // MLP pre-activation of those rows are compact.
+            const int64_t ld = (int64_t)T * D;
+            const int64_t off = (int64_t)(T - 1) * D;
+            float* dxl = (float*)b_dx.p + off;
+            uint8_t* dxcl = (uint8_t*)b_dxc.p + off * esz;
+            if (gdt != DT_F32) {
+                gemm(dxcl, b.wt_proj, nullptr, b_dh.p, const_cast<void*>(hpre), C, 4 * D, D, EPI_BF16_ACTGRAD, cfg.act, gdt, st, tdt, ld, 0);
+            } else {
+                gemm(dxcl, b.wt_proj, nullptr, b_dh.p, nullptr, C, 4 * D, D, EPI_BF16, ACT_NONE, gdt, st, DT_BF16, ld, 0);
+                act_bwd_inplace(b_dh.p, gdt, hpre, tdt, cfg.act, (int64_t)C * 4 * D, st); ++launches;
+            }
+            gemm(b_dh.p, b.wt_fc, nullptr, b_dln.p, nullptr, C, D, 4 * D, EPI_F32, ACT_NONE, gdt, st);
+            layernorm_bwd((const float*)b_dln.p, x1, b.ln2_g, dxl, dxcl, gdt, C, D, st, ld); ++launches;
+            TC_CUDA(cudaMemsetAsync(b_dattn.p, 0, (size_t)M * D * esz, st));                  // rows other than T-1 carry no gradient
+            gemm(dxcl, b.wt_o, nullptr, (uint8_t*)b_dattn.p + off * esz, nullptr, C, D, D, EPI_BF16, ACT_NONE, gdt, st, DT_BF16, ld, ld);
+            attn_bwd(qkv, b_dattn.p, b_dqkv.p, C, T, H, st);
+            gemm(b_dqkv.p, b.wt_qkv, nullptr, b_dln.p, nullptr, M, D, 3 * D, EPI_F32, ACT_NONE, gdt, st);
+            layernorm_bwd((const float*)b_dln.p, x0, b.ln1_g, (float*)b_dx.p, b_dxc.p, gdt, M, D, st); ++launches;
+            continue;
+        }
         // MLP branch
         if (gdt != DT_F32) {
             // dh = (dx . W_proj) * act'(h_pre): the activation derivative is applied in the dgrad GEMM's store stage

@@ -47,7 +47,7 @@ struct Engine {
     DevBuf t_save_x, t_save_qkv, t_save_h;
     DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
     DevBuf s_rows, s_cls, e_eot, e_pool;
-    struct { bool valid = false; int C = 0, P = 0, T = 0, PA = 1; bool has_attr = false; } saved;
+    struct { bool valid = false; int C = 0, P = 0, T = 0, PA = 1; bool has_attr = false; bool dead_last = false; } saved;
 
     // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline numbers)
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; int64_t M, N, K; int epi; };

@@ -16,8 +16,9 @@ void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos,
                      int B, int n_tokens, int d, cudaStream_t stream);
 // dx_acc[r,:] += LN'(dy[r,:]; x[r,:], gamma)  (mean/rstd recomputed from x);  dx_cast (optional, activation
 // type) receives the updated dx_acc row cast to the activation type.
+// dy and x are dense [rows, d]; dx_acc / dx_cast rows are dx_row_stride elements apart (0 = dense).
 void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast,
-                   int cast_dt, int64_t rows, int d, cudaStream_t stream);
+                   int cast_dt, int64_t rows, int d, cudaStream_t stream, int64_t dx_row_stride = 0);
 // out[r,:] = x[r,:] / ||x[r,:]||_2 ; inv_norm[r] (optional) = 1/||x||
 void l2norm_fwd(const float* x, float* out, float* inv_norm, int64_t rows, int d, cudaStream_t stream);
 // dx = (g - xhat * <xhat, g>) * inv_norm ; optional cast copy in the activation type

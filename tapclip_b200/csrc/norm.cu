@@ -118,7 +118,7 @@ assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restr
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                     float* dx_acc, T* dx_cast, int64_t rows, int d) {
+                     float* dx_acc, T* dx_cast, int64_t rows, int d, int64_t dx_row_stride) {
     pdl_wait_and_trigger();
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -158,13 +158,13 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     for (int i = 0; i < MAXV; ++i)
         if (i < nv) {
             const int c = (i * 32 + lane) * 4;
-            float4 a = *reinterpret_cast<const float4*>(dx_acc + row * d + c);
+            float4 a = *reinterpret_cast<const float4*>(dx_acc + row * dx_row_stride + c);
             a.x += rstd * (g[i].x - mg - v[i].x * mgx);
             a.y += rstd * (g[i].y - mg - v[i].y * mgx);
             a.z += rstd * (g[i].z - mg - v[i].z * mgx);
             a.w += rstd * (g[i].w - mg - v[i].w * mgx);
-            *reinterpret_cast<float4*>(dx_acc + row * d + c) = a;
-            if (dx_cast) store4<T>(dx_cast + row * d + c, a);
+            *reinterpret_cast<float4*>(dx_acc + row * dx_row_stride + c) = a;
+            if (dx_cast) store4<T>(dx_cast + row * dx_row_stride + c, a);
         }
 }
 
@@ -250,13 +250,13 @@ void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos,
 }
 
 void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* dx_acc, void* dx_cast, int cast_dt,
-                   int64_t rows, int d, cudaStream_t stream) {
+                   int64_t rows, int d, cudaStream_t stream, int64_t dx_row_stride) {
     check_d(d);
     TC_CHECK(cast_dt != DT_F16, "gradients are never fp16");
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (cast_dt == DT_BF16) launch_pdl(layernorm_bwd_kernel<bf16>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d);
-    else launch_pdl(layernorm_bwd_kernel<float>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (float*)dx_cast, rows, d);
+    if (cast_dt == DT_BF16) launch_pdl(layernorm_bwd_kernel<bf16>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d, dx_row_stride ? dx_row_stride : (int64_t)d);
+    else launch_pdl(layernorm_bwd_kernel<float>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (float*)dx_cast, rows, d, dx_row_stride ? dx_row_stride : (int64_t)d);
     TC_LAUNCH_CHECK();
 }
 
