@@ -379,7 +379,7 @@ def run_ours(args, wl):
         },
     }
     if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_reference_sample(model_name, B, C, P, train, sample_b=8, sample_c=16)     # ~10 s of host work (SURVEY 8d sub-grid)
+        cb = cpu_reference_sample(model_name, B, C, P, train, sample_b=8, sample_c=32)     # ~10 s of host work on 16 cores
         line["cpu_baseline"] = {"value": cb["images_per_s"], "unit": "images/s", "cores": cb["cores"], "kind": "port",
                                 "sample": cb["sample"], "seconds_sample": cb["seconds_sample"]}
     print(json.dumps(line), flush=True)
