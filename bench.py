@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the TAP-CLIP hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train_c2|fwd_c1|eval_c3|fwd_c4|train_c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train_c2|fwd_c1|fwd_b128|eval_c3|fwd_c4|train_c5]
 
 One "step" = one pass of the hot path over one batch of synthetic input.  Default workload = BASELINE.json
 configs[1]: ViT-B/16 prompt-tuning train step (attribution-instrumented forward + backward to the ctx vectors +
@@ -33,6 +33,9 @@ WORKLOADS = {
                  "fwd + attention-attribution + bwd to ctx + AdamW"),
     "fwd_c1": ("ViT-B-16-quickgelu", 8, 65, 16, False,
                "BASELINE configs[0]: ViT-B/16 attribution-instrumented forward, batch 8, 65 classes, 16 ctx tokens"),
+    "fwd_b128": ("ViT-B-16-quickgelu", 128, 65, 16, False,
+                 "north-star target shape: ViT-B/16 attribution-instrumented FORWARD (text attribution + per-layer CLS-row image "
+                 "probes), batch 128, 65 classes, 16 ctx tokens"),
     "eval_c3": ("ViT-B-16-quickgelu", 256, 345, 16, False,
                 "BASELINE configs[2]: ViT-B/16 cross-domain eval, 345 classes, batch 256/GPU, class-sharded text encoder"),
     "fwd_c4": ("ViT-L-14-336-quickgelu", 512, 65, 16, False,
@@ -42,7 +45,7 @@ WORKLOADS = {
                  "BASELINE configs[4]: ViT-B/16 few-shot prompt-tuning train step, 345 classes, batch 128/GPU, class-sharded text "
                  "tower, ctx-gradient all-gather"),
 }
-IMAGE_ATTRIBUTION = {"fwd_c4": "rollout"}          # workloads whose step also emits the image-side attribution
+IMAGE_ATTRIBUTION = {"fwd_c4": "rollout", "fwd_b128": "cls"}          # workloads whose step also emits the image-side attribution
 
 
 def measured_peaks():
