@@ -135,6 +135,12 @@ TAPCLIP_API int tapclip_profile(tapclip_handle h, int32_t enable);
 TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
 
 /* ---- single-kernel entry points (used by the per-kernel parity tests and micro-benchmarks) -------- */
+/* Residual GEMM with a fused pre-LN epilogue (K1-LN, gemm_ln.cu): x[M,N] (fp32, in place) += A[M,K].W[N,K]^T + bias, then
+ * ln_out[M,N] (16-bit, `dtype`) = LayerNorm(x; gamma, beta) and optionally x_copy[M,N] = x.  Replaces `x = x + f(...)` followed
+ * by the next `ln_1` / `ln_2` of open_clip's residual blocks.  N in {512, 768, 1024}; dtype BF16 or FP16 (mixed-mode value 2). */
+TAPCLIP_API int tapclip_op_gemm_resid_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x,
+                             void* ln_out, float* x_copy, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream);
+
 /* Image preprocessing on the device: what `CLIPWrapper.get_preprocess()` (models/clip_wrapper.py:64-65,
  * open_clip's inference transform, applied per image at dataset.py:31) does on the host with Pillow/torchvision:
  * Resize(R, BICUBIC) of the shorter side -> CenterCrop(R) -> ToTensor -> Normalize(mean, std).

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "tapclip_encode_image": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "tapclip_encode_text": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "tapclip_text_forward": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "tapclip_op_gemm_resid_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "tapclip_op_preprocess": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "tapclip_logits": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "tapclip_logits_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),

@@ -147,6 +147,16 @@ TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias,
     TC_API_END
 }
 
+TAPCLIP_API int tapclip_op_gemm_resid_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x,
+                             void* ln_out, float* x_copy, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream) {
+    TC_API_BEGIN
+    GemmLnArgs g;
+    g.a = a; g.w = w; g.bias = bias; g.gamma = gamma; g.beta = beta; g.x = x; g.ln_out = ln_out; g.x_copy = x_copy;
+    g.M = M; g.N = N; g.K = K; g.ldx = N; g.dt = dtype;
+    gemm_resid_ln(g, S(stream));
+    TC_API_END
+}
+
 TAPCLIP_API int tapclip_op_preprocess(const uint8_t* image_hwc, int32_t H, int32_t W, float* out_chw, int32_t R, int32_t crop_top,
                           int32_t crop_left, const float* mean3, const float* std3, void* stream) {
     TC_API_BEGIN

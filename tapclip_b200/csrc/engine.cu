@@ -306,9 +306,26 @@ void Engine::attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int
 //   probe      : attention probe for this layer (or PROBE_NONE)
 //   stop_after_attention_probs : attribution pass, last block: only the probabilities are needed
 //   save       : keep x copies / qkv / h_pre for the backward pass (slot = layer)
-void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
+bool Engine::gemm_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x, void* ln_out,
+                     float* x_copy, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st) {
+    if (!gemm_resid_ln_supported(N, K, dt)) return false;
+    GemmLnArgs g;
+    g.a = a; g.w = w; g.bias = bias; g.gamma = gamma; g.beta = beta; g.x = x; g.ln_out = ln_out; g.x_copy = x_copy;
+    g.M = M; g.N = N; g.K = K; g.ldx = N; g.dt = dt;
+    ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, 5};
+    if (profiling) prof_begin(r, st);
+    gemm_resid_ln(g, st);
+    if (profiling) prof_end(r, st);
+    ++launches;
+    return true;
+}
+
+// `next` (the following block, or null) and `ln1_ready` drive the LayerNorm fusion: with fuse_ln on, this block's
+// out-projection also emits ln_2(x) and its c_proj emits the NEXT block's ln_1(x) (+ the copies the backward pass needs), so
+// a block whose predecessor did that (`ln1_ready`) starts directly with its QKV GEMM.
+bool Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
                            DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar,
-                           int live_row) {
+                           int live_row, const BlockWeights* next, bool ln1_ready) {
     const int64_t M = (int64_t)S * N;
     float* sx0 = nullptr; float* sx1 = nullptr; void* sqkv = qkv.p; void* shpre = nullptr;
     if (save_slot >= 0) {
@@ -317,11 +334,11 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
         sqkv = (uint8_t*)t_save_qkv.p + (int64_t)save_slot * M * 3 * d * esz;
         shpre = (uint8_t*)t_save_h.p + (int64_t)save_slot * M * 4 * d * esz;
     }
-    layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, dt, sx0, M, d, st); ++launches;
+    if (!ln1_ready) { layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, dt, sx0, M, d, st); ++launches; }
     gemm(ln.p, b.w_qkv, b.b_qkv, sqkv, nullptr, M, 3 * d, d, EPI_BF16, ACT_NONE, dt, st);
     attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
     if (abar) { attention_headmean(sqkv, abar, dt, S, N, H, st); ++launches; }      // rollout extension: head-mean map of this layer
-    if (probs_only) return;
+    if (probs_only) return false;
     if (live_row >= 0) {
         // Dead-row elimination: after the LAST block only token `live_row` of every sequence is read (ln_post(x[:,0])
         // / pooling), and past the attention every row is independent.  The out-projection and the MLP therefore run on the
@@ -334,12 +351,19 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
         layernorm_fwd(xl, ld, b.ln2_g, b.ln2_b, ln.p, dt, sx1, S, d, st); ++launches;
         gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, S, 4 * d, d, EPI_BF16, cfg.act, dt, st);
         gemm(hbuf.p, b.w_proj, b.b_proj, xl, nullptr, S, d, 4 * d, EPI_F32_ADD, ACT_NONE, dt, st, DT_BF16, 0, ld);
-        return;
+        return false;
     }
-    gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, dt, st);
-    layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, dt, sx1, M, d, st); ++launches;
+    const bool fuse = dt != DT_F32 && ((fuse_ln >= 1 && d == cfg.text_width && &ln == &t_ln) || (fuse_ln >= 2 && &ln == &v_ln));
+    if (!(fuse && gemm_ln(attn.p, b.w_o, b.b_o, b.ln2_g, b.ln2_b, x, ln.p, sx1, M, d, d, dt, st))) {
+        gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, dt, st);
+        layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, dt, sx1, M, d, st); ++launches;
+    }
     gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, M, 4 * d, d, EPI_BF16, cfg.act, dt, st);
+    float* next_sx0 = (save_slot >= 0 && next) ? (float*)t_save_x.p + (int64_t)(2 * (save_slot + 1)) * M * d : nullptr;
+    if (fuse && next && gemm_ln(hbuf.p, b.w_proj, b.b_proj, next->ln1_g, next->ln1_b, x, ln.p, next_sx0, M, d, 4 * d, dt, st))
+        return true;                                                    // ln.p = ln_1 of the next block, its saved input written
     gemm(hbuf.p, b.w_proj, b.b_proj, x, nullptr, M, d, 4 * d, EPI_F32_ADD, ACT_NONE, dt, st);
+    return false;
 }
 
 // ---- image tower (row A4) ---------------------------------------------------------------------------
@@ -363,6 +387,7 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
     patchify(images, v_patches.p, vdt, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
     gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, vdt, st);
     assemble_ln_pre((const float*)v_patch_out.p, cls_emb, pos_emb, ln_pre_g, ln_pre_b, (float*)v_x.p, B, N, d, st); ++launches;
+    bool ln_ready = false;
     for (int l = 0; l < L; ++l) {
         AttnProbe probe;
         if (out_cls_rows) {
@@ -371,9 +396,10 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
             probe.seq_stride = (int64_t)L * H * N;
         }
         if (l == L - 1 && dead_rows) probe.live_q_rows = 1;
-        block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st,
-                      out_rollout ? (float*)v_abar.p + (int64_t)l * B * N * N : nullptr,
-                      (l == L - 1 && dead_rows) ? 0 : -1);                   // only the CLS row feeds ln_post
+        ln_ready = block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st,
+                                 out_rollout ? (float*)v_abar.p + (int64_t)l * B * N * N : nullptr,
+                                 (l == L - 1 && dead_rows) ? 0 : -1,                   // only the CLS row feeds ln_post
+                                 l + 1 < L ? &vis[l + 1] : nullptr, ln_ready);
     }
     layernorm_fwd((const float*)v_x.p, (int64_t)N * d, ln_post_g, ln_post_b, v_pooled.p, vdt, nullptr, B, d, st); ++launches;
     gemm(v_pooled.p, w_vproj, nullptr, out_feat, nullptr, B, E, d, EPI_F32, ACT_NONE, vdt, st);
@@ -418,11 +444,13 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
         TC_CHECK(P <= 64, "prompt_len %d unsupported (<= 64)", P);
         t_probe.ensure((int64_t)C * H * P * 4);
         splice_prompts(ctx, tok, nullptr, 1, x, C, P, Lc, D, st); ++launches;
+        bool ln_ready = false;
         for (int l = 0; l < L; ++l) {
             AttnProbe probe;
             const bool last = (l == L - 1);
             if (last) { probe.mode = PROBE_TEXT_COL; probe.out = (float*)t_probe.p; probe.P = P; }
-            block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, probe, last, -1, st);
+            ln_ready = block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, probe, last, -1, st, nullptr, -1,
+                                     l + 1 < L ? &txt[l + 1] : nullptr, ln_ready);
         }
         attribution_reduce((const float*)t_probe.p, (float*)t_attr_raw.p, (float*)t_attr.p, C, H, P, st); ++launches;
         attr = (const float*)t_attr.p;
@@ -436,11 +464,12 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
     if (attr_only) return;          // 'gate' / 'residual' adjustors: the host applies its small network to out_attr (prompt_adjustor.py:38-44)
     // feature pass (rows A9/A10)
     splice_prompts(ctx, tok, attr, PA, x, C, P, Lc, D, st); ++launches;
+    bool ln_ready2 = false;
     for (int l = 0; l < L; ++l) {
         AttnProbe none;
         // last block: only position T-1 is pooled (model_wrapper.py:73) -> out-projection and MLP on C rows
-        block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, none, false, save ? l : -1, st, nullptr,
-                      (l == L - 1 && dead_rows) ? T - 1 : -1);
+        ln_ready2 = block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, none, false, save ? l : -1, st, nullptr,
+                                  (l == L - 1 && dead_rows) ? T - 1 : -1, l + 1 < L ? &txt[l + 1] : nullptr, ln_ready2);
     }
     gather_rows(x, t_pooled.p, tdt, C, T, T - 1, D, st); ++launches;
     gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, tdt, st);

@@ -73,9 +73,14 @@ struct Engine {
               int act, int dt, cudaStream_t st, int aux_dt = DT_BF16, int64_t lda = 0, int64_t ldo = 0);   // lda/ldo 0 = dense
     void attn_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
     void attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st);
-    void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
+    bool block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
                        DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar = nullptr,
-                       int live_row = -1);
+                       int live_row = -1, const BlockWeights* next = nullptr, bool ln1_ready = false);
+    // residual GEMM with the following LayerNorm fused into its epilogue (gemm_ln.cu) when the shape allows it
+    bool gemm_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x, void* ln_out,
+                 float* x_copy, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st);
+    // 0 = LayerNorm as its own kernel; 1 = fused into the residual GEMMs of the text tower; 2 = of both towers (TAPCLIP_FUSE_LN)
+    int fuse_ln = getenv("TAPCLIP_FUSE_LN") ? atoi(getenv("TAPCLIP_FUSE_LN")) : 0;
     void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, float* out_rollout, cudaStream_t st);
     void text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
                       float* out_text_feat, cudaStream_t st);

@@ -36,6 +36,23 @@ const CUtensorMap& make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_b
 // tcgen05/TMEM/TMA path: A and W bf16 (or fp16, g.dt); out = same 16-bit type (EPI_BF16) or f32
 void gemm_tc(const GemmArgs& g, cudaStream_t stream);
 
+// Residual GEMM with fused LayerNorm epilogue (gemm_ln.cu):  x[M,N] += A[M,K] . W[N,K]^T + bias;  ln_out = LayerNorm(x; gamma, beta)
+// in the 16-bit type `dt` (dense [M,N]);  x_copy (optional, dense fp32 [M,N]) = the updated x.  N = 512 / 768 / 1024.
+struct GemmLnArgs {
+    const void* a = nullptr;       // [M, K] 16-bit, dense
+    const void* w = nullptr;       // [N, K] 16-bit, dense
+    const float* bias = nullptr;   // [N] or null
+    const float* gamma = nullptr;  // [N] LayerNorm weight
+    const float* beta = nullptr;   // [N] LayerNorm bias
+    float* x = nullptr;            // [M, N] fp32 residual stream, leading dimension ldx, updated in place
+    void* ln_out = nullptr;        // [M, N] 16-bit
+    float* x_copy = nullptr;
+    int64_t M = 0, N = 0, K = 0, ldx = 0;
+    int dt = DT_BF16;
+};
+bool gemm_resid_ln_supported(int64_t N, int64_t K, int dt);
+void gemm_resid_ln(const GemmLnArgs& g, cudaStream_t stream);
+
 // fp32 SIMT path for the fp32 parity mode: A, W, out all f32; EPI_BF16 means "store in the activation
 // type" (f32 here) with the optional activation / pre-activation copy
 void gemm_simt_f32(const GemmArgs& g, cudaStream_t stream);

@@ -144,3 +144,33 @@ def test_gemm_tc_act_grad_epilogue(M, N, K, act, aux, block_n):
     ref = (a.float() @ w.float().t()) * hf.grad
     assert bool(((out.float() - ref).abs() <= 5e-3 + 2 ** -7 * ref.abs()).all())   # two bf16 roundings (2 x 2^-9 relative) + fast act'
     assert ((out.float() - ref).norm() / ref.norm()).item() < 6e-3
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,N,K", [(93 * 65, 512, 512), (93 * 65, 512, 2048), (1576, 768, 768), (300, 1024, 1024), (129, 512, 64),
+                                   (197 * 64, 768, 3072), (128 * 40 + 5, 512, 512)])
+def test_gemm_residual_layernorm_epilogue(M, N, K, dtype):
+    """K1-LN (gemm_ln.cu): x += A.W^T + bias, ln_out = LayerNorm(x) in one launch; the CTAs owning the column slices of a
+    128-row block exchange their row statistics through distributed shared memory (cluster of N/256 CTAs)."""
+    from tapclip_b200 import _lib
+    lib = _lib.load()
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float16
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(tdt)
+    w = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).to(tdt)
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = 1.0 + 0.2 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    x0 = 3.0 * torch.randn(M, N, device="cuda", generator=g) + 0.5
+    x = x0.clone()
+    ln = torch.empty(M, N, device="cuda", dtype=tdt)
+    xc = torch.empty(M, N, device="cuda")
+    _lib.check(lib.tapclip_op_gemm_resid_ln(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(x),
+                                            _lib.ptr(ln), _lib.ptr(xc), M, N, K, _lib.DTYPE[dtype], _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    x_ref = x0 + a.float() @ w.float().t() + bias
+    ln_ref = torch.nn.functional.layer_norm(x_ref, (N,), gamma, beta, 1e-5)
+    assert (x - x_ref).abs().max().item() < 2e-3
+    assert torch.equal(xc, x)
+    tol = 3e-2 if dtype == "bf16" else 4e-3          # one 16-bit rounding of values up to ~5
+    assert (ln.float() - ln_ref).abs().max().item() < tol

@@ -227,3 +227,31 @@ def test_large_batch_image_tower_on_the_tcgen05_attention_path():
     assert max_abs(rows, rows_ref) < 5e-3
     assert (rows.sum(-1) - 1).abs().max().item() < 1e-3
     assert max_abs(roll, roll_ref) < 5e-3
+
+
+@pytest.mark.parametrize("mode", ["literal", "intended"])
+def test_text_tower_with_layernorm_fused_into_the_residual_gemms(mode, monkeypatch):
+    """TAPCLIP_FUSE_LN=1: the text tower's out-projection / c_proj GEMMs emit the following LayerNorm from their epilogue
+    (gemm_ln.cu, CTA clusters exchanging row statistics through DSMEM) and save the LN inputs for the backward pass.
+    Compared with the CPU oracle (forward + ctx gradients) and with the default two-kernel path."""
+    name, C, P, B = "mini-t512", 6, 5, 3
+    ow, om = build_oracle(name, C, P, mode)
+    images, labels = synthetic_images(B, get_config(name).image_size), synthetic_labels(B, C)
+    om.train()
+    ref = om.forward_dedup(images, labels)
+    ref["loss"].backward()
+    ref_grad = torch.stack([om.prompt_learner.context_bank[n].grad for n in class_names(C)])
+    results = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("TAPCLIP_FUSE_LN", fuse)
+        clip, model = build_cuda(name, C, P, mode, "mixed", ow)
+        model.train()
+        n0 = clip.engine.launch_count
+        out = model(images.cuda(), labels.cuda())
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        results[fuse] = (out["logits"].detach().cpu(), ctx_grads(model, C), clip.engine.launch_count - n0)
+        assert max_abs(out["logits"], ref["logits"]) <= LOGIT_TOL["mixed"]
+        assert rel_err(ctx_grads(model, C), ref_grad) <= GRAD_TOL["mixed"]
+    assert results["1"][2] < results["0"][2]                        # fewer launches: the LayerNorm kernels are gone
+    assert max_abs(results["1"][0], results["0"][0]) <= 5e-3        # same arithmetic up to the one-pass variance
