@@ -212,6 +212,8 @@ def run_ours(args, wl):
     torch.manual_seed(4)
     model = tb.FullModel([f"class_{i:03d}" for i in range(C)], clip, prompt_len=P, cache_text_features=False,
                          image_attribution=IMAGE_ATTRIBUTION.get(wl))
+    if os.environ.get("TAPCLIP_NO_OVERLAP") == "1":          # measurement switch: both towers on the caller's stream
+        model.overlap_towers = False
     opt = tb.FusedAdamW(model, lr=2e-3, weight_decay=0.01) if train else None
     model.train(train)
 
