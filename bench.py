@@ -364,7 +364,13 @@ def run_ours(args, wl):
         "roofline": {
             "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMEM/TMA bf16 GEMM, all shapes of the step)",
             "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-            "frac": (gemm_tflops / peaks["bf16_sustained"]) if gemm_tflops else None, "traffic": None,
+            "frac": (gemm_tflops / peaks["bf16_sustained"]) if gemm_tflops else None,
+            # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of the
+            # four image-tower shapes, launch-weighted; their algorithmic bytes (A + W + output) average 236 MB, so the operands are
+            # L2-resident and nothing is re-read from HBM.  Only reported for the workloads that capture describes.
+            "traffic": 162.9e6 if wl in ("train_c2", "fwd_b128") else None,
+            "traffic_note": "launch-weighted mean over the 45 image-tower GEMM launches of a step, profiles/r01n_ncu_full_gemm_tc_vision_layer0.csv",
+
             "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
             "gemm_launches_per_step": gemm["launches"] / args.steps, "gemm_ms_per_step": gemm["ms"] / args.steps,
             "gemm_share_of_step": gemm["ms"] / ms_serial if ms_serial else None,
