@@ -366,7 +366,7 @@ def run_ours(args, wl):
             "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": (gemm_tflops / peaks["bf16_sustained"]) if gemm_tflops else None,
             # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of the
-            # four image-tower shapes, launch-weighted; their algorithmic bytes (A + W + output) average 236 MB, so the operands are
+            # four image-tower shapes, launch-weighted; their algorithmic bytes (A + W + output, residual read+write) average 215 MB, so the operands are
             # L2-resident and nothing is re-read from HBM.  Only reported for the workloads that capture describes.
             "traffic": 162.9e6 if wl in ("train_c2", "fwd_b128") else None,
             "traffic_note": "launch-weighted mean over the 45 image-tower GEMM launches of a step, profiles/r01n_ncu_full_gemm_tc_vision_layer0.csv",
