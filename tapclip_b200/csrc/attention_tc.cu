@@ -596,6 +596,266 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Long sequences (N > 208, e.g. ViT-L/14@336: 577 tokens): the same warp-specialised persistent structure with a loop over
+// 128-key blocks and an online softmax (flash attention).  Per (item, key block j):
+//   MMA   S_j = Q K_j^T (128 x 128) into the group's TMEM half           [after P_{j-1} has been consumed by PV_{j-1}]
+//   softmax  one thread per query row: S_j row -> registers, running max m and sum l, alpha = 2^((m_old - m_new) c);
+//            P_j = 2^(S_j c - m_new c) -> 16 bit -> TMEM over the S columns;  O *= alpha in TMEM (skipped when no row of the
+//            warp moved its max);  l = l alpha + sum(P_j)
+//   MMA   O += P_j V_j (TS-MMA, accumulates in TMEM columns [128, 192))
+// and O / l is written once per item.  K/V blocks stream through a 5-stage TMA ring in the order the MMA warp consumes them:
+// the two groups' items advance in lock step, (A, j), (B, j), (A, j+1), ...
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KVB = 128;               // keys per block
+constexpr int KV_STAGES = 5;
+constexpr int KV_STAGE_BYTES = 2 * KVB * 128;
+constexpr int ATTN3_SMEM = 2 * 128 * 128 + KV_STAGES * KV_STAGE_BYTES + 256 + 1024;
+
+template <bool F16>
+__global__ void __launch_bounds__(ATTN2_THREADS, 1)
+attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, void* __restrict__ out_,
+                      int N, int H, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out, int probe_P,
+                      int64_t probe_seq_stride) {
+    using T16 = typename std::conditional<F16, f16, bf16>::type;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* qbuf = smem;                                   // [2 groups][128 x 128 B]; doubles as the O staging of the group
+    uint8_t* kvbuf = smem + 2 * 128 * 128;                  // [KV_STAGES][K block | V block]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(kvbuf + KV_STAGES * KV_STAGE_BYTES);
+    uint64_t* q_full = bars;              // [2]
+    uint64_t* q_free = bars + 2;          // [2] the group's 4 warps are done with the Q buffer (O stored)
+    uint64_t* kv_full = bars + 4;         // [KV_STAGES]
+    uint64_t* kv_empty = bars + 4 + KV_STAGES;   // [KV_STAGES] PV of the block complete
+    uint64_t* bar_s = bars + 4 + 2 * KV_STAGES;  // [2]
+    uint64_t* bar_p = bar_s + 2;          // [2] count 4
+    uint64_t* bar_o = bar_s + 4;          // [2]
+    uint64_t* bar_tfree = bar_s + 6;      // [2] count 4: O of the finished item has left TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int d = H * DH;
+    const int nkb = (N + KVB - 1) / KVB;
+    const int n_mine = (n_items > (int)blockIdx.x) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_free[i], 4); mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 4);
+            mbar_init(&bar_o[i], 1); mbar_init(&bar_tfree[i], 4);
+        }
+        for (int i = 0; i < KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        fence_mbar_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0) {
+            // ---- loader: Q of the pair's items, then their K/V blocks in consumption order ----
+            if (lane == 0) {
+                int stage = 0; uint32_t phase = 0;
+                for (int i0 = 0; i0 < n_mine; i0 += 2) {
+                    for (int g = 0; g < 2; ++g) {
+                        const int i = i0 + g;
+                        if (i >= n_mine) break;
+                        if (i >= 2) mbar_wait(&q_free[g], (uint32_t)(((i >> 1) - 1) & 1));
+                        const int id = (int)blockIdx.x + i * (int)gridDim.x;
+                        const int qt = id % nqt, sh = id / nqt, s = sh / H, h = sh % H;
+                        mbar_expect_tx(&q_full[g], 128 * 128);
+                        tma_load_2d(qbuf + g * 128 * 128, &tmap_q, h * DH, s * N + qt * 128, &q_full[g]);
+                    }
+                    for (int j = 0; j < nkb; ++j) {
+                        for (int g = 0; g < 2; ++g) {
+                            const int i = i0 + g;
+                            if (i >= n_mine) break;
+                            const int id = (int)blockIdx.x + i * (int)gridDim.x;
+                            const int sh = id / nqt, s = sh / H, h = sh % H;
+                            mbar_wait(&kv_empty[stage], phase ^ 1);
+                            mbar_expect_tx(&kv_full[stage], KV_STAGE_BYTES);
+                            uint8_t* kb = kvbuf + stage * KV_STAGE_BYTES;
+                            tma_load_2d(kb, &tmap_kv, d + h * DH, s * N + j * KVB, &kv_full[stage]);
+                            tma_load_2d(kb + KVB * 128, &tmap_kv, 2 * d + h * DH, s * N + j * KVB, &kv_full[stage]);
+                            if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ---- MMA issuer (warp-uniform control flow, elect.sync issue) ----
+            const uint32_t idesc_s = attn_idesc(128, KVB, F16, false), idesc_o = attn_idesc(128, DH, F16, true);
+            int s_stage = 0; uint32_t s_phase = 0;         // cursor of the next S to issue in the K/V ring
+            int p_stage = 0;                               // cursor of the next PV
+            uint32_t n_blk[2] = {0u, 0u};                  // blocks issued so far per group (parities of bar_s / bar_p / bar_o)
+            for (int i0 = 0; i0 < n_mine; i0 += 2) {
+                const int npres = (i0 + 1 < n_mine) ? 2 : 1;
+                for (int g = 0; g < npres; ++g) {
+                    const int i = i0 + g;
+                    mbar_wait(&q_full[g], (uint32_t)((i >> 1) & 1));
+                    if (i >= 2) mbar_wait(&bar_tfree[g], (uint32_t)(((i >> 1) - 1) & 1));     // the previous item's O has left this TMEM half
+                }
+                for (int j = 0; j < nkb; ++j) {
+                    for (int g = 0; g < npres; ++g) {
+                        const uint32_t thalf = tmem_base + g * 256;
+                        mbar_wait(&kv_full[s_stage], s_phase);
+                        if (j > 0) mbar_wait(&bar_o[g], (n_blk[g] - 1) & 1u);                   // PV_{j-1} done: P_{j-1} consumed, O consistent
+                        tc_fence_after();
+                        const uint64_t qd = smem_desc_sw128(smem_u32(qbuf + g * 128 * 128));
+                        const uint64_t kd = smem_desc_sw128(smem_u32(kvbuf + s_stage * KV_STAGE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < DH / 16; ++k) umma_ss_elect(thalf, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+                        umma_commit_elect(&bar_s[g]);
+                        if (++s_stage == KV_STAGES) { s_stage = 0; s_phase ^= 1; }
+                    }
+                    for (int g = 0; g < npres; ++g) {
+                        const uint32_t thalf = tmem_base + g * 256;
+                        mbar_wait(&bar_p[g], n_blk[g] & 1u);
+                        tc_fence_after();
+                        const uint64_t vd = smem_desc_sw128(smem_u32(kvbuf + p_stage * KV_STAGE_BYTES + KVB * 128));
+#pragma unroll
+                        for (int ks = 0; ks < KVB / 16; ++ks)
+                            umma_ts_elect(thalf + O_COL, thalf + ks * 8, vd + (uint64_t)(ks * 128), idesc_o, (j | ks) != 0);
+                        umma_commit_elect(&bar_o[g]);
+                        umma_commit_elect(&kv_empty[p_stage]);                                // the ring stage may be refilled
+                        if (++p_stage == KV_STAGES) p_stage = 0;
+                        ++n_blk[g];
+                    }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        // ---- softmax group g ----
+        const int g = (warp - 4) >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
+        const int rd_row = lane >> 3, rd_ch = lane & 7;
+        const int step2 = 2 * (int)gridDim.x;
+        const int step_qt = step2 % nqt, step_sh = step2 / nqt, step_h = step_sh % H, step_s = step_sh / H;
+        const int id0 = (int)blockIdx.x + g * (int)gridDim.x;
+        int qt = id0 % nqt, h = (id0 / nqt) % H, s = (id0 / nqt) / H;
+        uint32_t blk = 0;                                              // blocks processed by this group (barrier parities)
+        uint8_t* Qs = qbuf + g * 128 * 128;
+        for (int i = g; i < n_mine; i += 2) {
+            const int grow = qt * 128 + row;
+            const bool warp_active = qt * 128 + q * 32 < N;
+            const bool cls_thread = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0 && lane == 0;
+            float* cls_out = ((probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0) ? probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N : nullptr;
+            float m_run = -INFINITY, l = 0.f, p_last = 0.f;
+            float m_blk[8];                                            // the CLS row's max at each block (probe rescaling)
+            for (int j = 0; j < nkb; ++j, ++blk) {
+                mbar_wait(&bar_s[g], blk & 1u);
+                tc_fence_after();
+                if (warp_active) {
+                    const int n_eff = N - j * KVB;                     // valid keys of this block (>= 1; > 128 for interior blocks)
+                    uint32_t r[8][16];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) tmem_ld_32x16(trow + u * 16, r[u]);
+                    tmem_ld_wait();
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) chunk_max<true>(r[u], u, n_eff, m0, m1, m2, m3);
+                    const float m_new = fmaxf(m_run, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                    const float alpha = fast_exp2((m_run - m_new) * scale_log2);       // 0 for the first block (m_run = -inf)
+                    const float mneg = -m_new * scale_log2;
+                    float l0 = 0.f, l1 = 0.f, pl = 0.f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        chunk_exp<T16, true>(r[u], u, n_eff, scale_log2, mneg, trow, cls_out ? cls_out + j * KVB : nullptr, lane == 0, l0, l1, pl);
+                    if (j == nkb - 1) p_last = pl;
+                    l = fmaf(l, alpha, l0 + l1);
+                    m_run = m_new;
+                    if (cls_thread) m_blk[j & 7] = m_new;
+                    if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
+                        // O *= alpha (PV_{j-1} is complete: S_j was only issued after it)
+                        uint32_t o[4][16];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) tmem_ld_32x16(trow + O_COL + c * 16, o[c]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            uint32_t w8[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(__uint_as_float(o[c >> 1][(c & 1) * 8 + e]) * alpha);
+                            tmem_st_32x8(trow + O_COL + c * 8, w8);
+                        }
+                    }
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_p[g]);
+            }
+            // ---- the item's O is complete after the last PV ----
+            mbar_wait(&bar_o[g], (blk - 1) & 1u);
+            tc_fence_after();
+            const float inv = __frcp_rn(warp_active ? l : 1.f);
+            uint32_t o[4][16];
+            if (warp_active) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tmem_ld_32x16(trow + O_COL + c * 16, o[c]);
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tfree[g]);
+            if (warp_active) {
+                if (probe_mode == PROBE_TEXT_COL && grow < probe_P) probe_out[((int64_t)s * H + h) * probe_P + grow] = p_last * inv;
+                if (cls_thread)
+                    for (int key = 0; key < N; ++key)
+                        cls_out[key] *= fast_exp2((m_blk[(key / KVB) & 7] - m_run) * scale_log2) * inv;      // own earlier writes
+                const uint32_t stage = smem_u32(Qs) + (uint32_t)(q * 32) * 128u;      // the Q tile is dead: every S of the item is done
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t* rr = &o[c >> 1][(c & 1) * 8];
+                    const uint32_t x0 = pack2<T16>(__uint_as_float(rr[0]) * inv, __uint_as_float(rr[1]) * inv);
+                    const uint32_t x1 = pack2<T16>(__uint_as_float(rr[2]) * inv, __uint_as_float(rr[3]) * inv);
+                    const uint32_t x2 = pack2<T16>(__uint_as_float(rr[4]) * inv, __uint_as_float(rr[5]) * inv);
+                    const uint32_t x3 = pack2<T16>(__uint_as_float(rr[6]) * inv, __uint_as_float(rr[7]) * inv);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)lane * 128u + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4)),
+                                 "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");
+                }
+                __syncwarp();
+                uint8_t* gbase = reinterpret_cast<uint8_t*>(out_) + (((int64_t)s * N + qt * 128 + q * 32) * d + h * DH) * 2 + rd_ch * 16;
+                const int rows_left = N - (qt * 128 + q * 32);
+                uint4 x[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rd_row;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[it].x), "=r"(x[it].y), "=r"(x[it].z), "=r"(x[it].w)
+                                 : "r"(stage + (uint32_t)rr * 128u + (((uint32_t)rd_ch ^ ((uint32_t)rr & 7u)) << 4)) : "memory");
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rd_row;
+                    if (rr < rows_left) *reinterpret_cast<uint4*>(gbase + (int64_t)rr * d * 2) = x[it];
+                }
+                fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_free[g]);
+            qt += step_qt;
+            if (qt >= nqt) { qt -= nqt; ++h; }
+            h += step_h;
+            if (h >= H) { h -= H; ++s; }
+            s += step_s;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 #ifdef TAPCLIP_ATTN_TRACE
@@ -604,10 +864,10 @@ extern "C" __attribute__((visibility("default"))) int tapclip_debug_attn_trace(l
 }
 #endif
 
-bool attention_fwd_tc_supported(int dt, int N) { return (dt == DT_BF16 || dt == DT_F16) && N >= 1 && N <= 256; }
+bool attention_fwd_tc_supported(int dt, int N) { return (dt == DT_BF16 || dt == DT_F16) && N >= 1 && N <= 1024; }
 
 void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream) {
-    TC_CHECK(attention_fwd_tc_supported(dt, N), "tcgen05 attention supports 16-bit inputs and N <= 256");
+    TC_CHECK(attention_fwd_tc_supported(dt, N), "tcgen05 attention supports 16-bit inputs and N <= 1024");
 
     const int d = H * DH;
     const int nkp = (int)round_up(N, 16);
@@ -615,8 +875,26 @@ void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
     const bool f16 = dt == DT_F16;
     const CUtensorMapDataType tdt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const CUtensorMap& tq = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, 128, 64);
-    const CUtensorMap& tkv = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, nkp, 64);
     const float sl2 = 0.125f * 1.4426950408889634f;
+    if (nkp > 256) {
+        // flash-style kernel: 128-key blocks through a TMA ring
+        const CUtensorMap& tkb = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, KVB, 64);
+        static bool conf3[2] = {false, false};
+        if (!conf3[f16]) {
+            if (f16) TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN3_SMEM));
+            else TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN3_SMEM));
+            conf3[f16] = true;
+        }
+        static int num_sms3 = 0;
+        if (num_sms3 == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms3, cudaDevAttrMultiProcessorCount, dev)); }
+        const int n_items = S * H * nqt;
+        const unsigned grid3 = (unsigned)std::min(n_items, num_sms3);
+        if (f16) launch_pdl(attn_fwd_tc_kv_kernel<true>, grid3, ATTN2_THREADS, ATTN3_SMEM, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        else launch_pdl(attn_fwd_tc_kv_kernel<false>, grid3, ATTN2_THREADS, ATTN3_SMEM, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        TC_LAUNCH_CHECK();
+        return;
+    }
+    const CUtensorMap& tkv = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, nkp, 64);
     if (nkp <= 208) {
         // persistent pipelined kernel: 3 operand slots of (Q 16 KB + K + V) fit in shared memory
         const size_t smem2 = NSLOT * (128 * 128 + 2 * (size_t)nkp * 128) + 128 + 1024;   // + barriers/TMEM slot, alignment slack

@@ -86,7 +86,8 @@ def test_attention_fwd_and_probes(S, N, H, dtype):
     assert (attr - torch.softmax(ref_raw, -1)).abs().max().item() < tol_p
 
 
-@pytest.mark.parametrize("S,N,H", [(86, 197, 6), (128, 93, 8), (100, 50, 12), (70, 208, 8), (90, 129, 6), (140, 64, 8)])
+@pytest.mark.parametrize("S,N,H", [(86, 197, 6), (128, 93, 8), (100, 50, 12), (70, 208, 8), (90, 129, 6), (140, 64, 8),
+                                   (20, 577, 12), (40, 300, 10), (9, 1000, 16), (44, 257, 8)])   # N > 256: the flash-style KV-loop kernel
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 def test_attention_fwd_tcgen05_persistent_kernel(S, N, H, dtype):
     """Shapes with >= 1024 (sequence, head, q-tile) items take the persistent tcgen05 kernel (attention_tc.cu) in all three

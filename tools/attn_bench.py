@@ -5,7 +5,7 @@ import torch
 from tapclip_b200 import _lib
 lib = _lib.load()
 reps = 20
-for tag, S, N, H in [("vision B=128", 128, 197, 12), ("text C=65", 65, 93, 8), ("vision B=256", 256, 197, 12)]:
+for tag, S, N, H in [("vision B=128", 128, 197, 12), ("text C=65", 65, 93, 8), ("vision B=256", 256, 197, 12), ("ViT-L/14@336 B=64", 64, 577, 16)]:
     d = H * 64
     qkv = torch.randn(S * N, 3 * d, device="cuda").bfloat16()
     out = torch.empty(S * N, d, device="cuda", dtype=torch.bfloat16)
