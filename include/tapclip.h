@@ -166,6 +166,17 @@ TAPCLIP_API int tapclip_op_attention(const void* qkv, void* out, int32_t dtype, 
                          float* probe_out, int32_t probe_P, int64_t probe_seq_stride, void* stream);
 TAPCLIP_API int tapclip_op_attention_bwd(const void* qkv, const void* d_out, void* dqkv, int32_t dtype, int32_t S, int32_t N, int32_t H,
                              void* stream);
+/* Attention-rollout extension (image side; not in the reference, BASELINE north_star / configs[3]).
+ * tapclip_op_attention_lse: lse [S,H,N] = log2 sum_j 2^(c q_i.k_j), c = log2(e)/8, the softmax statistics of a packed qkv;
+ *      attn_out NULL: the statistics kernel alone; attn_out [S*N, H*64]: the attention forward itself, emitting lse from its
+ *      softmax registers where the selected kernel can (as the engine runs it when the rollout is requested).
+ * tapclip_op_rollout_step:  one layer of the CLS-row propagation r_out = 0.5 r_in + (0.5/H) sum_h r_in^T softmax(Q_h K_h^T / 8),
+ *      probabilities recomputed from qkv and lse (no N x N map); r_in NULL = e_0 (first call, LAST layer); last != 0 (FIRST
+ *      layer) drops the CLS column: r_out is [S, N-1], otherwise [S, N]. */
+TAPCLIP_API int tapclip_op_attention_lse(const void* qkv, void* attn_out, float* lse, int32_t dtype, int32_t S, int32_t N, int32_t H,
+                             void* stream);
+TAPCLIP_API int tapclip_op_rollout_step(const void* qkv, const float* lse, const float* r_in, float* r_out, int32_t dtype, int32_t S,
+                            int32_t N, int32_t H, int32_t last, void* stream);
 TAPCLIP_API int tapclip_op_attribution(const float* probe, float* raw, float* attr, int32_t C, int32_t H, int32_t P, void* stream);
 TAPCLIP_API int tapclip_op_cast(const float* src, void* dst, int32_t dst_dtype, int64_t n, void* stream);
 

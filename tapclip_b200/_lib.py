@@ -56,6 +56,8 @@ PROTOTYPES = {
     "tapclip_op_layernorm_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp]),
     "tapclip_op_attention": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i64, _vp]),
     "tapclip_op_attention_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tapclip_op_attention_lse": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tapclip_op_rollout_step": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tapclip_op_attribution": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "tapclip_op_cast": (C.c_int, [_vp, _vp, _i32, _i64, _vp]),
 }

@@ -358,7 +358,7 @@ template <bool F16, int NCH>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, void* __restrict__ out_,
                     int N, int H, int nkp, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out,
-                    int probe_P, int64_t probe_seq_stride) {
+                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out) {
     using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -525,6 +525,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     for (int v = 0; v < NTAIL; ++v) chunk_exp<T16, true>(t[v], NRES + v, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
                 }
                 l = l0 + l1;
+                if (lse_out && grow < N) lse_out[((int64_t)s * H + h) * N + grow] = log2f(l) - mneg;     // rollout statistics
                 tmem_st_wait();
             }
             TRACE(5);
@@ -616,7 +617,7 @@ template <bool F16>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, void* __restrict__ out_,
                       int N, int H, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out, int probe_P,
-                      int64_t probe_seq_stride) {
+                      int64_t probe_seq_stride, float* __restrict__ lse_out) {
     using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -810,6 +811,7 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             if (lane == 0) mbar_arrive(&bar_tfree[g]);
             if (warp_active) {
                 if (probe_mode == PROBE_TEXT_COL && grow < probe_P) probe_out[((int64_t)s * H + h) * probe_P + grow] = p_last * inv;
+                if (lse_out && grow < N) lse_out[((int64_t)s * H + h) * N + grow] = fmaf(m_run, scale_log2, log2f(l));   // rollout statistics
                 if (cls_thread)
                     for (int key = 0; key < N; ++key)
                         cls_out[key] *= fast_exp2((m_blk[(key / KVB) & 7] - m_run) * scale_log2) * inv;      // own earlier writes
@@ -866,7 +868,7 @@ extern "C" __attribute__((visibility("default"))) int tapclip_debug_attn_trace(l
 
 bool attention_fwd_tc_supported(int dt, int N) { return (dt == DT_BF16 || dt == DT_F16) && N >= 1 && N <= 1024; }
 
-void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream) {
+bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream) {
     TC_CHECK(attention_fwd_tc_supported(dt, N), "tcgen05 attention supports 16-bit inputs and N <= 1024");
 
     const int d = H * DH;
@@ -889,10 +891,10 @@ void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         if (num_sms3 == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms3, cudaDevAttrMultiProcessorCount, dev)); }
         const int n_items = S * H * nqt;
         const unsigned grid3 = (unsigned)std::min(n_items, num_sms3);
-        if (f16) launch_pdl(attn_fwd_tc_kv_kernel<true>, grid3, ATTN2_THREADS, ATTN3_SMEM, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
-        else launch_pdl(attn_fwd_tc_kv_kernel<false>, grid3, ATTN2_THREADS, ATTN3_SMEM, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+        if (f16) launch_pdl(attn_fwd_tc_kv_kernel<true>, grid3, ATTN2_THREADS, ATTN3_SMEM, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
+        else launch_pdl(attn_fwd_tc_kv_kernel<false>, grid3, ATTN2_THREADS, ATTN3_SMEM, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
         TC_LAUNCH_CHECK();
-        return;
+        return true;
     }
     const CUtensorMap& tkv = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, nkp, 64);
     if (nkp <= 208) {
@@ -909,14 +911,14 @@ void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
                 TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
                 configured = smem2;
             }
-            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
+            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
         };
         static size_t conf2[2][3] = {{0, 0, 0}, {0, 0, 0}};
         if (nch <= 4) { if (f16) go(attn_fwd_tc2_kernel<true, 4>, conf2[1][0]); else go(attn_fwd_tc2_kernel<false, 4>, conf2[0][0]); }
         else if (nch <= 8) { if (f16) go(attn_fwd_tc2_kernel<true, 8>, conf2[1][1]); else go(attn_fwd_tc2_kernel<false, 8>, conf2[0][1]); }
         else { if (f16) go(attn_fwd_tc2_kernel<true, 13>, conf2[1][2]); else go(attn_fwd_tc2_kernel<false, 13>, conf2[0][2]); }
         TC_LAUNCH_CHECK();
-        return;
+        return true;
     }
     const size_t smem = 128 * 128 + 2 * (size_t)nkp * 128 + 64 + 1024;
     static size_t conf[2] = {0, 0};
@@ -929,6 +931,7 @@ void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
     if (f16) launch_pdl(attn_fwd_tc_kernel<true>, grid, ATTN_THREADS, smem, stream, tq, tkv, out, N, H, nkp, nqt, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
     else launch_pdl(attn_fwd_tc_kernel<false>, grid, ATTN_THREADS, smem, stream, tq, tkv, out, N, H, nkp, nqt, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
     TC_LAUNCH_CHECK();
+    return false;                                              // this variant does not emit probe.lse_out
 }
 
 }  // namespace tapclip

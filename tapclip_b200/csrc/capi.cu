@@ -196,6 +196,26 @@ TAPCLIP_API int tapclip_op_attention_bwd(const void* qkv, const void* d_out, voi
     TC_API_END
 }
 
+TAPCLIP_API int tapclip_op_attention_lse(const void* qkv, void* attn_out, float* lse, int32_t dtype, int32_t S_, int32_t N, int32_t H,
+                             void* stream) {
+    TC_API_BEGIN
+    if (attn_out) {
+        AttnProbe p;
+        p.lse_out = lse;
+        attention_fwd(qkv, attn_out, dtype, S_, N, H, p, S(stream));
+    } else {
+        attention_lse(qkv, lse, dtype, S_, N, H, S(stream));
+    }
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_rollout_step(const void* qkv, const float* lse, const float* r_in, float* r_out, int32_t dtype, int32_t S_,
+                            int32_t N, int32_t H, int32_t last, void* stream) {
+    TC_API_BEGIN
+    rollout_step(qkv, lse, r_in, r_out, dtype, S_, N, H, last != 0, S(stream));
+    TC_API_END
+}
+
 TAPCLIP_API int tapclip_op_attribution(const float* probe, float* raw, float* attr, int32_t C, int32_t H, int32_t P, void* stream) {
     TC_API_BEGIN
     attribution_reduce(probe, raw, attr, C, H, P, S(stream));

@@ -93,7 +93,7 @@ Engine::~Engine() {
 }
 
 std::vector<DevBuf*> Engine::all_bufs() {
-    return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled, &v_abar,
+    return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled, &v_roll_qkv, &v_lse, &v_roll,
             &t_x, &t_ln, &t_qkv, &t_attn, &t_h, &t_pooled, &t_feat, &t_tfeat, &t_inv_norm, &t_probe, &t_attr, &t_attr_raw,
             &t_save_x, &t_save_qkv, &t_save_h, &b_dx, &b_dxc, &b_dh, &b_dln, &b_dattn, &b_dqkv, &b_dfeat, &b_dfeatc, &b_dpool,
             &s_rows, &s_cls, &e_eot, &e_pool};
@@ -324,7 +324,7 @@ bool Engine::gemm_ln(const void* a, const void* w, const float* bias, const floa
 // out-projection also emits ln_2(x) and its c_proj emits the NEXT block's ln_1(x) (+ the copies the backward pass needs), so
 // a block whose predecessor did that (`ln1_ready`) starts directly with its QKV GEMM.
 bool Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
-                           DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar,
+                           DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, void* rollout_qkv,
                            int live_row, const BlockWeights* next, bool ln1_ready) {
     const int64_t M = (int64_t)S * N;
     float* sx0 = nullptr; float* sx1 = nullptr; void* sqkv = qkv.p; void* shpre = nullptr;
@@ -334,10 +334,10 @@ bool Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
         sqkv = (uint8_t*)t_save_qkv.p + (int64_t)save_slot * M * 3 * d * esz;
         shpre = (uint8_t*)t_save_h.p + (int64_t)save_slot * M * 4 * d * esz;
     }
+    if (rollout_qkv) sqkv = rollout_qkv;                       // rollout extension: this layer's Q and K are re-read by rollout_step
     if (!ln1_ready) { layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, dt, sx0, M, d, st); ++launches; }
     gemm(ln.p, b.w_qkv, b.b_qkv, sqkv, nullptr, M, 3 * d, d, EPI_BF16, ACT_NONE, dt, st);
     attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
-    if (abar) { attention_headmean(sqkv, abar, dt, S, N, H, st); ++launches; }      // rollout extension: head-mean map of this layer
     if (probs_only) return false;
     if (live_row >= 0) {
         // Dead-row elimination: after the LAST block only token `live_row` of every sequence is read (ln_post(x[:,0])
@@ -382,7 +382,13 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
     v_attn.ensure(M * d * esz);
     v_h.ensure(M * 4 * d * esz);
     v_pooled.ensure((int64_t)B * d * esz);
-    if (out_rollout) v_abar.ensure((size_t)L * B * N * N * sizeof(float));     // [L, B, N, N] head-mean maps (rollout extension only)
+    if (out_rollout) {
+        // rollout extension: every layer's packed qkv and softmax statistics are kept, the CLS row is propagated from the last
+        // layer to the first after the tower (rollout.cu); no N x N map exists anywhere
+        v_roll_qkv.ensure((size_t)L * M * 3 * d * esz);
+        v_lse.ensure((size_t)L * B * H * N * sizeof(float));
+        v_roll.ensure((size_t)2 * B * N * sizeof(float));
+    }
 
     patchify(images, v_patches.p, vdt, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
     gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, vdt, st);
@@ -396,14 +402,25 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
             probe.seq_stride = (int64_t)L * H * N;
         }
         if (l == L - 1 && dead_rows) probe.live_q_rows = 1;
+        if (out_rollout) probe.lse_out = (float*)v_lse.p + (int64_t)l * B * H * N;
         ln_ready = block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st,
-                                 out_rollout ? (float*)v_abar.p + (int64_t)l * B * N * N : nullptr,
+                                 out_rollout ? (uint8_t*)v_roll_qkv.p + (int64_t)l * M * 3 * d * esz : nullptr,
                                  (l == L - 1 && dead_rows) ? 0 : -1,                   // only the CLS row feeds ln_post
                                  l + 1 < L ? &vis[l + 1] : nullptr, ln_ready);
     }
     layernorm_fwd((const float*)v_x.p, (int64_t)N * d, ln_post_g, ln_post_b, v_pooled.p, vdt, nullptr, B, d, st); ++launches;
     gemm(v_pooled.p, w_vproj, nullptr, out_feat, nullptr, B, E, d, EPI_F32, ACT_NONE, vdt, st);
-    if (out_rollout) { attention_rollout((const float*)v_abar.p, out_rollout, B, N, L, st); ++launches; }
+    if (out_rollout) {
+        // r_L = e_0;  r_{l} = 0.5 r_{l+1} + 0.5 r_{l+1}^T mean_h P_l;  out = r_0 without the CLS column.  At the last layer only
+        // r_0 != 0, so the statistics of its dead query rows (live_q_rows) are never read.
+        for (int l = L - 1; l >= 0; --l) {
+            const float* r_in = (l == L - 1) ? nullptr : (const float*)v_roll.p + (int64_t)((l + 1) & 1) * B * N;
+            float* r_out = (l == 0) ? out_rollout : (float*)v_roll.p + (int64_t)(l & 1) * B * N;
+            rollout_step((const uint8_t*)v_roll_qkv.p + (int64_t)l * M * 3 * d * esz, (const float*)v_lse.p + (int64_t)l * B * H * N,
+                         r_in, r_out, vdt, B, N, H, l == 0, st);
+            ++launches;
+        }
+    }
 }
 
 // ---- text side (rows A2, A6-A10) ----------------------------------------------------------------------

@@ -42,7 +42,7 @@ struct Engine {
     std::vector<BlockWeights> vis, txt;
 
     // workspaces (grow-only)
-    DevBuf v_patches, v_patch_out, v_x, v_ln, v_qkv, v_attn, v_h, v_pooled, v_abar;
+    DevBuf v_patches, v_patch_out, v_x, v_ln, v_qkv, v_attn, v_h, v_pooled, v_roll_qkv, v_lse, v_roll;
     DevBuf t_x, t_ln, t_qkv, t_attn, t_h, t_pooled, t_feat, t_tfeat, t_inv_norm, t_probe, t_attr, t_attr_raw;
     DevBuf t_save_x, t_save_qkv, t_save_h;
     DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
@@ -74,7 +74,7 @@ struct Engine {
     void attn_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
     void attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st);
     bool block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
-                       DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, float* abar = nullptr,
+                       DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, void* rollout_qkv = nullptr,
                        int live_row = -1, const BlockWeights* next = nullptr, bool ln1_ready = false);
     // residual GEMM with the following LayerNorm fused into its epilogue (gemm_ln.cu) when the shape allows it
     bool gemm_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x, void* ln_out,

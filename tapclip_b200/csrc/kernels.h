@@ -36,19 +36,26 @@ struct AttnProbe {
     bool causal = false;         // key j visible to query i only if j <= i (standard CLIP text tower, encode_text)
     int live_q_rows = 0;         // > 0: only query rows [0, live_q_rows) are consumed downstream (last block: the CLS row); the
                                  // tcgen05 kernel then skips whole 128-row query tiles past them, other rows of `out` are unspecified
+    float* lse_out = nullptr;    // rollout extension: [S,H,N] softmax statistics log2 sum_j 2^(c q_i.k_j), c = log2(e)/8, of every
+                                 // computed query row (non-causal only); rows past live_q_rows may be left unwritten
 };
 // qkv [S*N, 3*H*64] (packed in_proj output, activation type) -> out [S*N, H*64]; softmax(QK^T/8)V, no mask.
 // bf16 / fp16: mma.sync tensor-core flash kernel; fp32: SIMT kernel.  Probabilities asked for by `probe` are
 // emitted from the softmax registers; the N x N map is never written.
 void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe,
                    cudaStream_t stream);
-// tcgen05 version of attention_fwd for 16-bit inputs and N <= 256 (attention_tc.cu); same contract
+// tcgen05 version of attention_fwd for 16-bit inputs (attention_tc.cu); same contract, except that probe.lse_out is only
+// written by the variants that return true (attention_fwd completes it with attention_lse otherwise)
 bool attention_fwd_tc_supported(int dt, int N);
-void attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream);
-// rollout extension: abar [S, N, N] = head-mean attention probabilities of one layer; attention_rollout propagates the CLS
-// row through all L stored layers (abar_all [L, B, N, N]) and writes out [B, N-1] (CLS -> patch relevance)
-void attention_headmean(const void* qkv, float* abar, int dt, int S, int N, int H, cudaStream_t stream);
-void attention_rollout(const float* abar_all, float* out, int B, int N, int L, cudaStream_t stream);
+bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t stream);
+// rollout extension (rollout.cu): attention_lse writes the softmax statistics lse [S,H,N] of a packed qkv (see
+// AttnProbe::lse_out); rollout_step propagates the CLS row of the attention rollout through ONE layer,
+//   r_out[s,j] = 0.5 r_in[s,j] + (0.5/H) sum_h sum_i r_in[s,i] softmax_j(q_i.k_j/8),
+// recomputing the probabilities from qkv and lse (no N x N map in memory).  r_in = nullptr: e_0 (start, at the LAST layer);
+// last = true (the FIRST layer): the CLS column is dropped, r_out is [S, N-1].
+void attention_lse(const void* qkv, float* lse, int dt, int S, int N, int H, cudaStream_t stream);
+void rollout_step(const void* qkv, const float* lse, const float* r_in, float* r_out, int dt, int S, int N, int H, bool last,
+                  cudaStream_t stream);
 // dqkv [S*N, 3*H*64] from d_out [S*N, H*64] and the saved qkv (probabilities recomputed). N <= 128.
 // qkv may be fp16 (mixed mode) while gradients are bf16; fp32 mode: everything fp32.
 void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, int grad_dt, int S, int N, int H,

@@ -138,3 +138,45 @@ def test_attention_bwd(S, N, H, dtype):
     o.backward(do.float())
     tol = 2e-5 if dtype == "fp32" else 3e-2
     assert (dqkv.float() - x.grad).abs().max().item() < tol * max(1.0, x.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("S,N,H", [(3, 197, 12), (2, 577, 16), (5, 50, 12), (2, 17, 4), (3, 130, 2),      # mma.sync / SIMT statistics
+                                   (90, 197, 12), (40, 577, 16), (44, 257, 8)])                          # tcgen05 forward kernels
+@pytest.mark.parametrize("dtype", ["bf16", "fp16", "fp32"])
+def test_rollout_step_and_softmax_statistics(S, N, H, dtype):
+    """Rollout extension (rollout.cu): the softmax statistics from the stand-alone kernel and from the attention forward
+    (emitted by the persistent / KV-loop tcgen05 kernels, completed by the statistics kernel elsewhere), and one layer of
+    the CLS-row propagation r_out = 0.5 r + 0.5 mean_h r^T P_h against torch fp32 on the same (rounded) qkv."""
+    L, lib = _lib()
+    d = H * 64
+    g = torch.Generator(device="cuda").manual_seed(7 * S + N + H)
+    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[dtype]
+    qkv = (torch.randn(S * N, 3 * d, device="cuda", generator=g) * 1.5).to(tdt)
+    q, k, _ = qkv.float().view(S, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    scores = q @ k.transpose(-1, -2) / 8.0                                    # [S,H,N,N]
+    lse_ref = torch.logsumexp(scores, dim=-1) / math.log(2.0)
+    p = torch.softmax(scores, dim=-1)
+    lse = torch.full((S, H, N), float("nan"), device="cuda")
+    L.check(lib.tapclip_op_attention_lse(L.ptr(qkv), None, L.ptr(lse), L.DTYPE[dtype], S, N, H, L.stream_ptr()))
+    out = torch.empty(S * N, d, device="cuda", dtype=tdt)
+    lse_f = torch.full((S, H, N), float("nan"), device="cuda")
+    L.check(lib.tapclip_op_attention_lse(L.ptr(qkv), L.ptr(out), L.ptr(lse_f), L.DTYPE[dtype], S, N, H, L.stream_ptr()))
+    torch.cuda.synchronize()
+    tol_l = 2e-5 if dtype == "fp32" else 2e-4                                  # absolute, log2 units (16-bit: fp32 accumulation order)
+    assert (lse - lse_ref).abs().max().item() < tol_l
+    assert (lse_f - lse_ref).abs().max().item() < tol_l
+    ref_o, _ = _ref_attention(qkv, S, N, H)
+    assert (out.float() - ref_o).abs().max().item() < {"bf16": 2e-2, "fp16": 3e-3, "fp32": 2e-5}[dtype]
+    # first step (r = e_0), a middle step (dense positive r with exact zeros in it), last step (CLS column dropped)
+    r_mid = torch.rand(S, N, device="cuda", generator=g) * 0.01
+    r_mid[:, 3] = 0.0
+    for r_in, last in [(None, False), (r_mid, False), (r_mid, True)]:
+        r = r_mid if r_in is not None else torch.zeros(S, N, device="cuda").index_fill_(1, torch.tensor([0], device="cuda"), 1.0)
+        ref = 0.5 * r + 0.5 * torch.einsum("si,shij->sj", r, p) / H
+        if last:
+            ref = ref[:, 1:]
+        r_out = torch.full_like(ref, float("nan"))
+        L.check(lib.tapclip_op_rollout_step(L.ptr(qkv), L.ptr(lse_f), L.ptr(r_in), L.ptr(r_out), L.DTYPE[dtype], S, N, H, int(last), L.stream_ptr()))
+        torch.cuda.synchronize()
+        rel = ((r_out - ref).abs() / ref.abs().clamp_min(1e-12)).max().item()
+        assert rel < (2e-5 if dtype == "fp32" else 5e-4), (rel, last)
