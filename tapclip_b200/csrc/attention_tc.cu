@@ -322,9 +322,11 @@ constexpr int POLY_EVERY = 0;          // n > 0: every n-th exponential of the p
                                        // Measured (ViT-B/16 layer, B=128): 0 -> 62 us, 3 -> 77 us: the pass is latency/issue-bound, not MUFU-bound
 
 // exp2, row-sum, 16-bit pack and write-back of P chunk u (TMEM columns [8u, 8u+8) of the row); probe bookkeeping
-template <typename T16, bool MAYBE_MASKED>
+// CLS = float* : the CLS row's unnormalised p goes to global memory (scalar stores, any alignment);
+// CLS = uint32_t: to a 16-float-aligned shared-memory staging row (address; 0 = none) with four vector stores
+template <typename T16, bool MAYBE_MASKED, typename CLS>
 __device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N, float scale_log2, float mneg, uint32_t trow,
-                                          float* cls_out, bool cls_lane, float& l0, float& l1, float& p_last) {
+                                          CLS cls_out, bool cls_lane, float& l0, float& l1, float& p_last) {
     float pv[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -338,10 +340,19 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N,
             if (u * 16 + j == N - 1) p_last = pv[j];
         }
     }
-    if (cls_out != nullptr && cls_lane) {
+    if constexpr (std::is_same<CLS, uint32_t>::value) {
+        if (cls_out != 0u && cls_lane) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (u * 16 + j < N) cls_out[u * 16 + j] = pv[j];
+            for (int v = 0; v < 4; ++v)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cls_out + (uint32_t)(u * 16 + v * 4) * 4u), "f"(pv[4 * v]),
+                             "f"(pv[4 * v + 1]), "f"(pv[4 * v + 2]), "f"(pv[4 * v + 3]) : "memory");
+        }
+    } else {
+        if (cls_out != nullptr && cls_lane) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (u * 16 + j < N) cls_out[u * 16 + j] = pv[j];
+        }
     }
     uint32_t pk[8];
 #pragma unroll
@@ -354,6 +365,7 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N,
 
 // NCH = compile-time number of 16-key chunks the softmax handles (>= NKP/16: chunks past NKP are fully masked), so that every
 // register array below is indexed with constants; chunks below FIRST_MASKABLE are valid for every N this instance serves.
+constexpr int CLS_STAGE2 = 208;        // floats per group: the persistent kernel serves N <= 208
 template <bool F16, int NCH>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, void* __restrict__ out_,
@@ -371,6 +383,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint64_t* bar_tfree = bars + 9;       // [2] O read out of TMEM by the group's 4 warps: the TMEM half may take the next S
     uint64_t* bar_free = bars + 11;       // [2] O stored: the operand slot (its Q tile doubles as store staging) may be refilled
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    float* cls_stage = reinterpret_cast<float*>(smem + NSLOT * slot_bytes + 128);   // [2 groups][CLS_STAGE2] unnormalised CLS-row p
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int d = H * DH;
@@ -469,7 +482,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const int grow = qt * 128 + row;
             const bool warp_active = qt * 128 + q * 32 < N;            // else: all 32 rows of this warp are padding
             const bool cls_warp = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0;
-            float* cls_out = cls_warp ? probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N : nullptr;
+            // CLS probe: lane 0 (query row 0) stages its unnormalised probabilities in shared memory during the exp2 pass; the
+            // whole warp normalises them and writes the row to global memory with coalesced stores once l is known
+            const uint32_t cls_out = cls_warp ? smem_u32(cls_stage + g * CLS_STAGE2) : 0u;
 #ifdef TAPCLIP_ATTN_TRACE
             long long* tr = (blockIdx.x == 0 && lane == 0 && q == 0 && (i >> 1) < 16) ? g_attn_trace + (g * 16 + (i >> 1)) * 16 : nullptr;
 #endif
@@ -535,8 +550,13 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const float inv = __frcp_rn(l);
             if (warp_active) {
                 if (probe_mode == PROBE_TEXT_COL && grow < probe_P) probe_out[((int64_t)s * H + h) * probe_P + grow] = p_last * inv;
-                if (cls_warp && lane == 0)
-                    for (int key = 0; key < N; ++key) cls_out[key] *= inv;      // own earlier writes
+                if (cls_warp) {
+                    __syncwarp();                                          // lane 0's staged row is visible to the warp
+                    const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
+                    float* cls_gl = probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N;
+                    for (int key = lane; key < N; key += 32) cls_gl[key] = cls_stage[g * CLS_STAGE2 + key] * inv0;
+                    __syncwarp();                                          // staging may be overwritten by the group's next item
+                }
             }
             TRACE(7);
             mbar_wait(&bar_o[g], par);
@@ -611,7 +631,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 constexpr int KVB = 128;               // keys per block
 constexpr int KV_STAGES = 5;
 constexpr int KV_STAGE_BYTES = 2 * KVB * 128;
-constexpr int ATTN3_SMEM = 2 * 128 * 128 + KV_STAGES * KV_STAGE_BYTES + 256 + 1024;
+constexpr int ATTN3_SMEM = 2 * 128 * 128 + KV_STAGES * KV_STAGE_BYTES + 256 + 1024;   // 194.25 KB with the reserved KB: the 196 KB carve-out
+constexpr int CLS_STAGE3 = 1024;       // CLS probe launches only: [2 groups][1024] floats of staging behind the barriers (N <= 1024);
+constexpr int ATTN3_SMEM_CLS = ATTN3_SMEM + 2 * CLS_STAGE3 * 4;   // measured at N = 577: +7 % without a probe (next carve-out step), so opt-in
 
 template <bool F16>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
@@ -633,6 +655,7 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint64_t* bar_o = bar_s + 4;          // [2]
     uint64_t* bar_tfree = bar_s + 6;      // [2] count 4: O of the finished item has left TMEM
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
+    float* cls_stage = reinterpret_cast<float*>(kvbuf + KV_STAGES * KV_STAGE_BYTES + 256);   // only present (and touched) with PROBE_CLS_ROW
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int d = H * DH;
@@ -749,10 +772,13 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         for (int i = g; i < n_mine; i += 2) {
             const int grow = qt * 128 + row;
             const bool warp_active = qt * 128 + q * 32 < N;
-            const bool cls_thread = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0 && lane == 0;
-            float* cls_out = ((probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0) ? probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N : nullptr;
+            const bool cls_warp = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0;
+            const bool cls_thread = cls_warp && lane == 0;
+            // CLS probe: lane 0 stages p (relative to each block's running max) in shared memory during the pass; the whole warp
+            // rescales, normalises and stores the row coalesced at the end of the item
+            const uint32_t cls_out = cls_warp ? smem_u32(cls_stage + g * CLS_STAGE3) : 0u;
             float m_run = -INFINITY, l = 0.f, p_last = 0.f;
-            float m_blk[8];                                            // the CLS row's max at each block (probe rescaling)
+            float m_blk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // the CLS row's max at each block (probe rescaling)
             for (int j = 0; j < nkb; ++j, ++blk) {
                 mbar_wait(&bar_s[g], blk & 1u);
                 tc_fence_after();
@@ -771,7 +797,7 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     float l0 = 0.f, l1 = 0.f, pl = 0.f;
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        chunk_exp<T16, true>(r[u], u, n_eff, scale_log2, mneg, trow, cls_out ? cls_out + j * KVB : nullptr, lane == 0, l0, l1, pl);
+                        chunk_exp<T16, true>(r[u], u, n_eff, scale_log2, mneg, trow, cls_out ? cls_out + (uint32_t)(j * KVB) * 4u : 0u, lane == 0, l0, l1, pl);
                     if (j == nkb - 1) p_last = pl;
                     l = fmaf(l, alpha, l0 + l1);
                     m_run = m_new;
@@ -812,9 +838,19 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             if (warp_active) {
                 if (probe_mode == PROBE_TEXT_COL && grow < probe_P) probe_out[((int64_t)s * H + h) * probe_P + grow] = p_last * inv;
                 if (lse_out && grow < N) lse_out[((int64_t)s * H + h) * N + grow] = fmaf(m_run, scale_log2, log2f(l));   // rollout statistics
-                if (cls_thread)
-                    for (int key = 0; key < N; ++key)
-                        cls_out[key] *= fast_exp2((m_blk[(key / KVB) & 7] - m_run) * scale_log2) * inv;      // own earlier writes
+                if (cls_warp) {
+                    __syncwarp();                                      // lane 0's staged row is visible to the warp
+                    const float inv0 = __shfl_sync(0xffffffffu, inv, 0), m0 = __shfl_sync(0xffffffffu, m_run, 0);
+                    float fb[8];                                       // per key block: 2^((m_block - m_final) c) / l
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) fb[b] = fast_exp2((__shfl_sync(0xffffffffu, m_blk[b], 0) - m0) * scale_log2) * inv0;
+                    float* cls_gl = probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N;
+#pragma unroll
+                    for (int b = 0; b < 8; ++b)
+                        if (b < nkb)
+                            for (int key = b * KVB + lane; key < min(N, (b + 1) * KVB); key += 32) cls_gl[key] = cls_stage[g * CLS_STAGE3 + key] * fb[b];
+                    __syncwarp();                                      // staging may be overwritten by the group's next item
+                }
                 const uint32_t stage = smem_u32(Qs) + (uint32_t)(q * 32) * 128u;      // the Q tile is dead: every S of the item is done
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -883,23 +919,24 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         const CUtensorMap& tkb = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, KVB, 64);
         static bool conf3[2] = {false, false};
         if (!conf3[f16]) {
-            if (f16) TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN3_SMEM));
-            else TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN3_SMEM));
+            if (f16) TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN3_SMEM_CLS));
+            else TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN3_SMEM_CLS));
             conf3[f16] = true;
         }
+        const size_t smem3 = probe.mode == PROBE_CLS_ROW ? ATTN3_SMEM_CLS : ATTN3_SMEM;
         static int num_sms3 = 0;
         if (num_sms3 == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms3, cudaDevAttrMultiProcessorCount, dev)); }
         const int n_items = S * H * nqt;
         const unsigned grid3 = (unsigned)std::min(n_items, num_sms3);
-        if (f16) launch_pdl(attn_fwd_tc_kv_kernel<true>, grid3, ATTN2_THREADS, ATTN3_SMEM, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
-        else launch_pdl(attn_fwd_tc_kv_kernel<false>, grid3, ATTN2_THREADS, ATTN3_SMEM, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
+        if (f16) launch_pdl(attn_fwd_tc_kv_kernel<true>, grid3, ATTN2_THREADS, smem3, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
+        else launch_pdl(attn_fwd_tc_kv_kernel<false>, grid3, ATTN2_THREADS, smem3, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
         TC_LAUNCH_CHECK();
         return true;
     }
     const CUtensorMap& tkv = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, nkp, 64);
     if (nkp <= 208) {
         // persistent pipelined kernel: 3 operand slots of (Q 16 KB + K + V) fit in shared memory
-        const size_t smem2 = NSLOT * (128 * 128 + 2 * (size_t)nkp * 128) + 128 + 1024;   // + barriers/TMEM slot, alignment slack
+        const size_t smem2 = NSLOT * (128 * 128 + 2 * (size_t)nkp * 128) + 128 + 2 * CLS_STAGE2 * sizeof(float) + 1024;   // + barriers/TMEM slot, CLS staging, alignment slack
         static int num_sms = 0;
         if (num_sms == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
         const int n_items = S * H * nqt;

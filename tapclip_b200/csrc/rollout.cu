@@ -11,7 +11,7 @@
 // the head-mean map's four QK^T passes plus a write and a read of B*N*N floats (16 GB at ViT-L/14@336, B=512, 24 layers).
 // r_i is folded into the exponent: r_i * 2^(x - lse_i) = 2^(x - (lse_i - log2 r_i)); r_i = 0 gives +inf and a zero term.
 //
-//  * rollout_step_mma_kernel  16-bit Q/K: S^T = K Q^T on mma.sync m16n8k16; a CTA owns up to 128 keys of one image (16 per
+//  * rollout_step_mma_kernel  16-bit Q/K: S^T = K Q^T on mma.sync m16n8k16; a CTA owns up to 256 keys of one image (32 per
 //                             warp), loops over heads and 32-query steps; no atomics, deterministic.
 //  * rollout_step_simt_kernel fp32 parity mode (one warp per key).
 //  * attn_lse_mma_kernel / attn_lse_simt_kernel  the statistics alone, for forward kernels that do not emit them.
@@ -60,6 +60,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // r_out[s, key - skip] = 0.5 * r_in[s, key] + (0.5/H) * sum_h sum_i r_in[s, i] * 2^(c q_i.k_key - lse[s,h,i])
 // r_in == nullptr: r_in = e_0 (the CLS row of the identity).  skip = 1 on the last step drops the CLS column.
+// A warp owns 32 keys (two 16-row A fragments kept in registers for the head), so every ldmatrix of a Q fragment feeds
+// four MMAs: the shared-memory pipe was the busiest unit (59 %) with 16 keys per warp.
+constexpr int RS_KEYS = 32;            // keys per warp
+
 template <typename T>
 __global__ void __launch_bounds__(256, 2)
 rollout_step_mma_kernel(const T* __restrict__ qkv, const float* __restrict__ lse, const float* __restrict__ r_in,
@@ -68,8 +72,8 @@ rollout_step_mma_kernel(const T* __restrict__ qkv, const float* __restrict__ lse
     extern __shared__ __align__(128) uint8_t smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x, d = H * DH;
-    const int kt = nwarps * 16, k0 = blockIdx.y * kt;
+    const int s = blockIdx.x, d = H * DH;                     // (image-major launch order measured faster than tile-major: 1.53 vs 1.65 ms)
+    const int kt = nwarps * RS_KEYS, k0 = blockIdx.y * kt;
     uint8_t* Ks = smem;                                       // [kt][128 B]    this CTA's keys of the current head
     uint8_t* Qs = Ks + kt * 128;                              // [npad][128 B]  every query of the current head
     float* lr = reinterpret_cast<float*>(Qs + npad * 128);    // [npad] log2 r_in (head independent)
@@ -80,7 +84,9 @@ rollout_step_mma_kernel(const T* __restrict__ qkv, const float* __restrict__ lse
         if (i < N) v = r_in ? log2f(r_in[(int64_t)s * N + i]) : (i == 0 ? 0.f : -INFINITY);
         lr[i] = v;
     }
-    float acc0 = 0.f, acc1 = 0.f;
+    float acc[2][2][2];                                       // [key fragment][row half][partial sum]
+#pragma unroll
+    for (int f = 0; f < 2; ++f) { acc[f][0][0] = acc[f][0][1] = acc[f][1][0] = acc[f][1][1] = 0.f; }
     for (int h = 0; h < H; ++h) {
         __syncthreads();                                      // previous head's tiles are no longer read; lr is visible
         const T* base = qkv + (int64_t)s * N * 3 * d + h * DH;
@@ -92,37 +98,62 @@ rollout_step_mma_kernel(const T* __restrict__ qkv, const float* __restrict__ lse
             lw[i] = (i < N && lr[i] != -INFINITY) ? lse_h[i] - lr[i] : INFINITY;     // r_i = 0: the row's statistics may be unwritten
         cp_async_wait<0>();
         __syncthreads();
-        if (k0 + warp * 16 >= N) continue;                    // warp-uniform; the barriers above are still reached
-        uint32_t kf[4][4];
+        if (k0 + warp * RS_KEYS >= N) continue;               // warp-uniform; the barriers above are still reached
+        uint32_t kf[2][4][4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const int row = warp * 16 + (mat & 1) * 8 + l7, ch = ks * 2 + (mat >> 1);
-            ldmatrix_x4(kf[ks], smem_u32(Ks + row * 128 + ((ch ^ (row & 7)) << 4)));
-        }
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int row = warp * RS_KEYS + f * 16 + (mat & 1) * 8 + l7, ch = ks * 2 + (mat >> 1);
+                ldmatrix_x4(kf[f][ks], smem_u32(Ks + row * 128 + ((ch ^ (row & 7)) << 4)));
+            }
         for (int qc = 0; qc < npad; qc += QC) {
-            float sc[4][4];
-            tile_16x32<T>(sc, kf, Qs, qc, mat, l7);
+            float sc[2][4][4];
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { sc[f][i][0] = sc[f][i][1] = sc[f][i][2] = sc[f][i][3] = 0.f; }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int nbp = 0; nbp < 2; ++nbp) {
+                    const int row = qc + (nbp * 2 + (mat >> 1)) * 8 + l7, ch = ks * 2 + (mat & 1);
+                    uint32_t b[4];
+                    ldmatrix_x4(b, smem_u32(Qs + row * 128 + ((ch ^ (row & 7)) << 4)));
+#pragma unroll
+                    for (int f = 0; f < 2; ++f) {
+                        mma_16816<T>(sc[f][nbp * 2], kf[f][ks], b[0], b[1]);
+                        mma_16816<T>(sc[f][nbp * 2 + 1], kf[f][ks], b[2], b[3]);
+                    }
+                }
+            }
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
                 const float2 w = *reinterpret_cast<const float2*>(lw + qc + nb * 8 + tq * 2);
-                acc0 += ex2_approx(fmaf(sc[nb][0], SCALE_LOG2, -w.x)) + ex2_approx(fmaf(sc[nb][1], SCALE_LOG2, -w.y));
-                acc1 += ex2_approx(fmaf(sc[nb][2], SCALE_LOG2, -w.x)) + ex2_approx(fmaf(sc[nb][3], SCALE_LOG2, -w.y));
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    acc[f][0][0] += ex2_approx(fmaf(sc[f][nb][0], SCALE_LOG2, -w.x));
+                    acc[f][0][1] += ex2_approx(fmaf(sc[f][nb][1], SCALE_LOG2, -w.y));
+                    acc[f][1][0] += ex2_approx(fmaf(sc[f][nb][2], SCALE_LOG2, -w.x));
+                    acc[f][1][1] += ex2_approx(fmaf(sc[f][nb][3], SCALE_LOG2, -w.y));
+                }
             }
         }
     }
-    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-    if (tq == 0) {
-        const float wh = 0.5f / (float)H;
+    const float wh = 0.5f / (float)H;
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            const int key = k0 + warp * 16 + g + half * 8;
-            if (key < N && key >= skip) {
+            float a = acc[f][half][0] + acc[f][half][1];
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            const int key = k0 + warp * RS_KEYS + f * 16 + g + half * 8;
+            if (tq == 0 && key < N && key >= skip) {
                 const float rk = r_in ? r_in[(int64_t)s * N + key] : (key == 0 ? 1.f : 0.f);
-                r_out[(int64_t)s * (N - skip) + key - skip] = fmaf(wh, half ? acc1 : acc0, 0.5f * rk);
+                r_out[(int64_t)s * (N - skip) + key - skip] = fmaf(wh, a, 0.5f * rk);
             }
         }
-    }
 }
 
 // fp32 parity mode: one warp per key, lanes over the queries
@@ -288,9 +319,10 @@ void rollout_step(const void* qkv, const float* lse, const float* r_in, float* r
     TC_CHECK(N >= 2 && H >= 1 && lse && r_out, "bad rollout_step arguments");
     const int skip = last ? 1 : 0;
     if (dt == DT_BF16 || dt == DT_F16) {
-        int ntiles;
-        const int nwarps = warps_for(N, ntiles), npad = (int)round_up(N, QC);
-        const size_t smem = (size_t)(nwarps * 16 + npad) * 128 + (size_t)2 * npad * sizeof(float);
+        // 32-key blocks split evenly over the fewest CTAs of at most 8 warps
+        const int nkb = (int)ceil_div(N, RS_KEYS), ntiles = (int)ceil_div(nkb, 8), nwarps = (int)ceil_div(nkb, ntiles);
+        const int npad = (int)round_up(N, QC);
+        const size_t smem = (size_t)(nwarps * RS_KEYS + npad) * 128 + (size_t)2 * npad * sizeof(float);
         TC_CHECK(smem <= 227 * 1024, "sequence length %d too long for the rollout kernel", N);
         static size_t conf[2] = {0, 0};
         const int which = dt == DT_F16;

@@ -31,11 +31,13 @@ def run(S, N, H, reps=10):
         return sorted(ts)[len(ts) // 2]
 
     t_fwd = timed(lambda: _lib.check(lib.tapclip_op_attention(_lib.ptr(qkv), _lib.ptr(out), 1, S, N, H, 0, None, 0, 0, _lib.stream_ptr())))
+    rows = torch.empty(S, H, N, device="cuda")
+    t_fwd_cls = timed(lambda: _lib.check(lib.tapclip_op_attention(_lib.ptr(qkv), _lib.ptr(out), 1, S, N, H, 2, _lib.ptr(rows), 0, H * N, _lib.stream_ptr())))
     t_fwd_lse = timed(lambda: _lib.check(lib.tapclip_op_attention_lse(_lib.ptr(qkv), _lib.ptr(out), _lib.ptr(lse), 1, S, N, H, _lib.stream_ptr())))
     t_lse = timed(lambda: _lib.check(lib.tapclip_op_attention_lse(_lib.ptr(qkv), None, _lib.ptr(lse), 1, S, N, H, _lib.stream_ptr())))
     t_step = timed(lambda: _lib.check(lib.tapclip_op_rollout_step(_lib.ptr(qkv), _lib.ptr(lse), _lib.ptr(r_in), _lib.ptr(r_out), 1, S, N, H, 0, _lib.stream_ptr())))
     n_exp = S * H * N * N
-    print(f"S={S} N={N} H={H}: attention fwd {t_fwd:.3f} ms, fwd+lse {t_fwd_lse:.3f} ms, statistics alone {t_lse:.3f} ms, "
+    print(f"S={S} N={N} H={H}: attention fwd {t_fwd:.3f} ms, fwd+CLS probe {t_fwd_cls:.3f} ms, fwd+lse {t_fwd_lse:.3f} ms, statistics alone {t_lse:.3f} ms, "
           f"rollout step {t_step:.3f} ms ({n_exp / t_step * 1e-9:.2f} T exp2/s, {2 * n_exp * 64 / t_step * 1e-9:.0f} TFLOP/s QK^T)")
 
 
