@@ -56,6 +56,10 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
 void attention_lse(const void* qkv, float* lse, int dt, int S, int N, int H, cudaStream_t stream);
 void rollout_step(const void* qkv, const float* lse, const float* r_in, float* r_out, int dt, int S, int N, int H, bool last,
                   cudaStream_t stream);
+// tcgen05 version for long 16-bit sequences (rollout_tc.cu); rollout_step dispatches to it (TAPCLIP_ROLLOUT_IMPL=1: mma.sync)
+bool rollout_step_tc_supported(int dt, int N);
+void rollout_step_tc(const void* qkv, const float* lse, const float* r_in, float* r_out, int dt, int S, int N, int H, bool last,
+                     cudaStream_t stream);
 // dqkv [S*N, 3*H*64] from d_out [S*N, H*64] and the saved qkv (probabilities recomputed). N <= 128.
 // qkv may be fp16 (mixed mode) while gradients are bf16; fp32 mode: everything fp32.
 void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, int grad_dt, int S, int N, int H,

@@ -16,6 +16,7 @@
 //  * rollout_step_simt_kernel fp32 parity mode (one warp per key).
 //  * attn_lse_mma_kernel / attn_lse_simt_kernel  the statistics alone, for forward kernels that do not emit them.
 #include "kernels.h"
+#include <cstdlib>
 
 namespace tapclip {
 namespace {
@@ -318,6 +319,11 @@ void rollout_step(const void* qkv, const float* lse, const float* r_in, float* r
     if (S == 0) return;
     TC_CHECK(N >= 2 && H >= 1 && lse && r_out, "bad rollout_step arguments");
     const int skip = last ? 1 : 0;
+    static const int impl = getenv("TAPCLIP_ROLLOUT_IMPL") ? atoi(getenv("TAPCLIP_ROLLOUT_IMPL")) : 0;   // 0 auto, 1 mma.sync, 2 tcgen05
+    if (impl != 1 && rollout_step_tc_supported(dt, N) && (impl == 2 || (int64_t)S * ceil_div(N, 128) >= 148)) {
+        rollout_step_tc(qkv, lse, r_in, r_out, dt, S, N, H, last, stream);
+        return;
+    }
     if (dt == DT_BF16 || dt == DT_F16) {
         // 32-key blocks split evenly over the fewest CTAs of at most 8 warps
         const int nkb = (int)ceil_div(N, RS_KEYS), ntiles = (int)ceil_div(nkb, 8), nwarps = (int)ceil_div(nkb, ntiles);

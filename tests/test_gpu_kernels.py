@@ -141,12 +141,15 @@ def test_attention_bwd(S, N, H, dtype):
 
 
 @pytest.mark.parametrize("S,N,H", [(3, 197, 12), (2, 577, 16), (5, 50, 12), (2, 17, 4), (3, 130, 2),      # mma.sync / SIMT statistics
-                                   (90, 197, 12), (40, 577, 16), (44, 257, 8)])                          # tcgen05 forward kernels
+                                   (90, 197, 12), (40, 577, 16), (44, 257, 8),                           # tcgen05 forward kernels
+                                   (50, 257, 8), (30, 700, 4)])                                          # + tcgen05 rollout step (N > 256, >= 148 CTAs)
 @pytest.mark.parametrize("dtype", ["bf16", "fp16", "fp32"])
 def test_rollout_step_and_softmax_statistics(S, N, H, dtype):
     """Rollout extension (rollout.cu): the softmax statistics from the stand-alone kernel and from the attention forward
     (emitted by the persistent / KV-loop tcgen05 kernels, completed by the statistics kernel elsewhere), and one layer of
     the CLS-row propagation r_out = 0.5 r + 0.5 mean_h r^T P_h against torch fp32 on the same (rounded) qkv."""
+    if dtype == "fp32" and N > 608:
+        pytest.skip("fp32 parity-mode attention kernels serve N <= 608")
     L, lib = _lib()
     d = H * 64
     g = torch.Generator(device="cuda").manual_seed(7 * S + N + H)
