@@ -224,7 +224,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-            printf("tapclip: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+            printf("tapclip: mbarrier wait timed out (block %d thread %d parity %u, barrier at shared offset %u)\n", blockIdx.x, threadIdx.x, parity, smem_u32(bar));
             __trap();
         }
     }
