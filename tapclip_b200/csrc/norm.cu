@@ -115,7 +115,8 @@ assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restr
         }
 }
 
-template <typename T>
+// NV = float4 per lane the instance holds (4: d <= 512, the text tower - half the registers, twice the resident warps; 8: d <= 1024)
+template <typename T, int NV>
 __global__ void __launch_bounds__(WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      float* dx_acc, T* dx_cast, int64_t rows, int d, int64_t dx_row_stride) {
@@ -123,18 +124,25 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, nv = d >> 7;
-    float4 v[MAXV], g[MAXV];
+    // All three operand rows (x, dy, the dx accumulator) are requested before the first reduction: the rows fill one wave of
+    // CTAs, so the kernel's duration is the latency chain of a single warp (three dependent round trips before this).
+    float4 v[NV], g[NV], a[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
+    for (int i = 0; i < NV; ++i)
         if (i < nv) {
-            v[i] = *reinterpret_cast<const float4*>(x + row * d + (i * 32 + lane) * 4);
-            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            const int c = (i * 32 + lane) * 4;
+            v[i] = *reinterpret_cast<const float4*>(x + row * d + c);
+            g[i] = *reinterpret_cast<const float4*>(dy + row * d + c);
+            a[i] = *reinterpret_cast<const float4*>(dx_acc + row * dx_row_stride + c);
         }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (i < nv) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) / (float)d;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
+    for (int i = 0; i < NV; ++i)
         if (i < nv) {
             v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
             q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
@@ -143,28 +151,26 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     // g = dy * gamma ; xhat = (x-mean)*rstd ; dx = rstd * (g - mean(g) - xhat*mean(g*xhat))
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
+    for (int i = 0; i < NV; ++i)
         if (i < nv) {
             const int c = (i * 32 + lane) * 4;
-            const float4 dyv = *reinterpret_cast<const float4*>(dy + row * d + c);
             const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
-            g[i].x = dyv.x * gm.x; g[i].y = dyv.y * gm.y; g[i].z = dyv.z * gm.z; g[i].w = dyv.w * gm.w;
+            g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
             v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;
             sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
             sgx += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
         }
     const float mg = warp_sum(sg) / (float)d, mgx = warp_sum(sgx) / (float)d;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i)
+    for (int i = 0; i < NV; ++i)
         if (i < nv) {
             const int c = (i * 32 + lane) * 4;
-            float4 a = *reinterpret_cast<const float4*>(dx_acc + row * dx_row_stride + c);
-            a.x += rstd * (g[i].x - mg - v[i].x * mgx);
-            a.y += rstd * (g[i].y - mg - v[i].y * mgx);
-            a.z += rstd * (g[i].z - mg - v[i].z * mgx);
-            a.w += rstd * (g[i].w - mg - v[i].w * mgx);
-            *reinterpret_cast<float4*>(dx_acc + row * dx_row_stride + c) = a;
-            if (dx_cast) store4<T>(dx_cast + row * dx_row_stride + c, a);
+            a[i].x += rstd * (g[i].x - mg - v[i].x * mgx);
+            a[i].y += rstd * (g[i].y - mg - v[i].y * mgx);
+            a[i].z += rstd * (g[i].z - mg - v[i].z * mgx);
+            a[i].w += rstd * (g[i].w - mg - v[i].w * mgx);
+            *reinterpret_cast<float4*>(dx_acc + row * dx_row_stride + c) = a[i];
+            if (dx_cast) store4<T>(dx_cast + row * dx_row_stride + c, a[i]);
         }
 }
 
@@ -255,8 +261,14 @@ void layernorm_bwd(const float* dy, const float* x, const float* gamma, float* d
     TC_CHECK(cast_dt != DT_F16, "gradients are never fp16");
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (cast_dt == DT_BF16) launch_pdl(layernorm_bwd_kernel<bf16>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d, dx_row_stride ? dx_row_stride : (int64_t)d);
-    else launch_pdl(layernorm_bwd_kernel<float>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (float*)dx_cast, rows, d, dx_row_stride ? dx_row_stride : (int64_t)d);
+    const int64_t ld = dx_row_stride ? dx_row_stride : (int64_t)d;
+    if (d <= 512) {
+        if (cast_dt == DT_BF16) launch_pdl(layernorm_bwd_kernel<bf16, 4>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d, ld);
+        else launch_pdl(layernorm_bwd_kernel<float, 4>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (float*)dx_cast, rows, d, ld);
+    } else {
+        if (cast_dt == DT_BF16) launch_pdl(layernorm_bwd_kernel<bf16, MAXV>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (bf16*)dx_cast, rows, d, ld);
+        else launch_pdl(layernorm_bwd_kernel<float, MAXV>, grid, WARPS * 32, 0, stream, dy, x, gamma, dx_acc, (float*)dx_cast, rows, d, ld);
+    }
     TC_LAUNCH_CHECK();
 }
 
