@@ -30,7 +30,8 @@ struct GemmArgs {
 
 // Cached TMA descriptor of a 2-D row-major tensor [rows, cols] (leading dimension ld, elements of elem_bytes), 128B-swizzled
 // boxes of box_rows x box_cols (box_cols * elem_bytes must be 128).  Shared by the GEMM and the tcgen05 attention kernel.
-const CUtensorMap& make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+// Returned BY VALUE (128 bytes): a caller may hold two descriptors at once, and the cache evicts everything when it is full.
+CUtensorMap make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
                              int box_rows, int box_cols);
 
 // tcgen05/TMEM/TMA path: A and W bf16 (or fp16, g.dt); out = same 16-bit type (EPI_BF16) or f32

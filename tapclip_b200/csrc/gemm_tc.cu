@@ -393,7 +393,7 @@ struct TmapKey {
 };
 std::map<TmapKey, CUtensorMap> g_tmap_cache;
 
-const CUtensorMap& make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
+CUtensorMap make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
                              int box_rows, int box_cols) {
     const TmapKey key{ptr, (int)dt, rows, cols, ld, box_rows, box_cols};
     auto it = g_tmap_cache.find(key);
