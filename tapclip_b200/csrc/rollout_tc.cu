@@ -5,14 +5,15 @@
 // queries that the propagation needs stays inside one thread (no shuffles, no shared-memory reduction), and the tensor
 // work leaves the legacy HMMA path that bounded the mma.sync kernel together with the MUFU pipe.
 //
-// One CTA per (image, 128-key tile), 12 warps:
+// One CTA per (image, 128-key tile), 20 warps:
 //   warp 0      TMA: per head the K tile [128 x 64] and all Q rows [npad x 64] as 32-row 128B-swizzled boxes, 2 head stages
-//   warp 1      tcgen05.mma issuer: per head and 256-query block  D[128 x wb] = K_tile . Q_block^T  (M=128, N=wb, K=64) into
-//               the TMEM half of the block's parity; tcgen05.commit releases the head's stage when its MMAs are done
+//   warp 1      tcgen05.mma issuer: per head and 128-query block  D[128 x wb] = K_tile . Q_block^T  (M=128, N=wb, K=64) into
+//               the TMEM column quarter blk % 4; tcgen05.commit releases the head's stage when its MMAs are done
 //   warps 2-3   lw[h][i] = lse[s,h,i] - log2 r_in[s,i] for the next head (double buffered): r_i is folded into the exponent
-//   warps 4-11  two groups of four warps (one TMEM lane quarter each); group g drains the blocks of parity g:
-//               tcgen05.ld 32 columns -> 2^(c x - lw) -> per-thread sum; the halves alternate, so MMA and drain overlap
-// The two groups' partial sums of a key are combined through shared memory at the end; no atomics, deterministic.
+//   warps 4-19  four groups of four warps (one TMEM lane quarter each); group g drains the blocks with blk % 4 == g:
+//               tcgen05.ld 32 columns -> 2^(c x - lw) -> per-thread sum; four warps per scheduler keep the MUFU pipe fed while
+//               other groups wait for their next block (two groups of 256-column blocks: 1.28 ms at B=512, N=577)
+// The groups' partial sums of a key are combined through shared memory at the end; no atomics, deterministic.
 #include "gemm.h"
 #include "kernels.h"
 #include <cstdlib>
@@ -21,9 +22,10 @@ namespace tapclip {
 namespace {
 
 constexpr int DH = 64;
-constexpr int RT_THREADS = 384;
+constexpr int RT_NG = 4;               // drain groups = TMEM column quarters
+constexpr int RT_THREADS = 128 + RT_NG * 128;
 constexpr int RT_KEYS = 128;           // keys per CTA = TMEM lanes
-constexpr int RT_QB = 256;             // queries per MMA block = columns of one TMEM half
+constexpr int RT_QB = 512 / RT_NG;     // queries per MMA block = columns of one group's TMEM region
 constexpr int RT_NST = 2;              // head stages of K/Q in shared memory
 constexpr float SCALE_LOG2 = 0.125f * 1.4426950408889634f;
 
@@ -49,33 +51,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool F16>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rollout_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ lse, const float* __restrict__ r_in,
-                       float* __restrict__ r_out, int S, int N, int H, int npad, int skip, int tile_major) {
+                       float* __restrict__ r_out, int S, int N, int H, int npad, int skip, int tile_major, int kpc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int stage_bytes = (RT_KEYS + npad) * 128;           // K tile, then the Q rows (a multiple of 1024: npad % 32 == 0)
+    // kpc = key tiles per CTA (1 or 2): with two, the head's Q rows are fetched once for 256 keys (L2 -> SM traffic -1/3 at N = 577)
+    const int stage_bytes = (kpc * RT_KEYS + npad) * 128;     // K tile(s), then the Q rows (a multiple of 1024: npad % 32 == 0)
     float* lr = reinterpret_cast<float*>(smem + RT_NST * stage_bytes);   // [npad] log2 r_in
     float* lw = lr + npad;                                    // [2][npad]
-    float* comb = lw + 2 * npad;                              // [128] group 1's partial sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(comb + RT_KEYS);
+    float* comb = lr;                                         // [RT_NG - 1][2][128] partial sums, over lr / lw once every drain is done
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lw + 2 * npad);
     uint64_t* full = bars;                // [RT_NST] TMA transaction barriers
     uint64_t* empty = bars + RT_NST;      // [RT_NST] the head's MMAs are complete
-    uint64_t* bar_s = empty + RT_NST;     // [2] block in TMEM half g is complete
-    uint64_t* tfree = bar_s + 2;          // [2] count 4: the group has drained its half
-    uint64_t* lw_full = tfree + 2;        // [2] count 2
-    uint64_t* lw_empty = lw_full + 2;     // [2] count 8
+    uint64_t* bar_s = empty + RT_NST;     // [RT_NG] block in TMEM region g is complete
+    uint64_t* tfree = bar_s + RT_NG;      // [RT_NG] count 4: the group has drained its region
+    uint64_t* lw_full = tfree + RT_NG;    // [2] count 2
+    uint64_t* lw_empty = lw_full + 2;     // [2] count 4 * RT_NG: every drain warp, once per head
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lw_empty + 2);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int ntl = (N + RT_KEYS - 1) / RT_KEYS;
-    const int s = tile_major ? blockIdx.x / ntl : blockIdx.x % S;
-    const int k0 = (tile_major ? blockIdx.x % ntl : blockIdx.x / S) * RT_KEYS;
+    const int ntl = (N + RT_KEYS - 1) / RT_KEYS, npi = (ntl + kpc - 1) / kpc;     // key tiles / CTAs per image
+    const int s = tile_major ? blockIdx.x / npi : blockIdx.x % S;
+    const int t0 = (tile_major ? blockIdx.x % npi : blockIdx.x / S) * kpc;
+    const int nkt = min(kpc, ntl - t0), k0 = t0 * RT_KEYS;                        // this CTA's key tiles [t0, t0 + nkt)
     const int d = H * DH;
-    const int nb = (npad + RT_QB - 1) / RT_QB;                // query blocks per head (>= 2: checked by the launcher)
+    const int nb = (npad + RT_QB - 1) / RT_QB;                // query blocks per head (>= 3: checked by the launcher)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
         for (int i = 0; i < RT_NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&tfree[i], 4); mbar_init(&lw_full[i], 2); mbar_init(&lw_empty[i], 8); }
+        for (int i = 0; i < RT_NG; ++i) { mbar_init(&bar_s[i], 1); mbar_init(&tfree[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&lw_full[i], 2); mbar_init(&lw_empty[i], 4 * RT_NG); }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
@@ -99,9 +104,9 @@ rollout_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
                 const int st = h % RT_NST;
                 if (h >= RT_NST) mbar_wait(&empty[st], (uint32_t)((h / RT_NST - 1) & 1));
                 uint8_t* base = smem + st * stage_bytes;
-                mbar_expect_tx(&full[st], (uint32_t)stage_bytes);
-                for (int r = 0; r < RT_KEYS / 32; ++r) tma_load_2d(base + r * 32 * 128, &tmap, d + h * DH, s * N + k0 + r * 32, &full[st]);
-                for (int r = 0; r < npad / 32; ++r) tma_load_2d(base + (RT_KEYS + r * 32) * 128, &tmap, h * DH, s * N + r * 32, &full[st]);
+                mbar_expect_tx(&full[st], (uint32_t)((nkt * RT_KEYS + npad) * 128));
+                for (int r = 0; r < nkt * RT_KEYS / 32; ++r) tma_load_2d(base + r * 32 * 128, &tmap, d + h * DH, s * N + k0 + r * 32, &full[st]);
+                for (int r = 0; r < npad / 32; ++r) tma_load_2d(base + (kpc * RT_KEYS + r * 32) * 128, &tmap, h * DH, s * N + r * 32, &full[st]);
             }
         }
     } else if (warp == 1) {
@@ -112,16 +117,18 @@ rollout_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
             mbar_wait(&full[st], (uint32_t)((h / RT_NST) & 1));
             tc_fence_after();
             const uint32_t kaddr = smem_u32(smem + st * stage_bytes);
-            const uint64_t kd = desc_sw128(kaddr);
-            for (int qb = 0; qb < nb; ++qb, ++blk) {
-                const int g = blk & 1, use = blk >> 1;
-                if (use >= 1) { mbar_wait(&tfree[g], (uint32_t)((use - 1) & 1)); tc_fence_after(); }
-                const int wb = min(RT_QB, npad - qb * RT_QB);
-                const uint64_t qd = desc_sw128(kaddr + (uint32_t)(RT_KEYS + qb * RT_QB) * 128u);
-                const uint32_t idesc = idesc_kmajor(RT_KEYS, wb, F16);
+            for (int kt = 0; kt < nkt; ++kt) {
+                const uint64_t kd = desc_sw128(kaddr + (uint32_t)(kt * RT_KEYS) * 128u);
+                for (int qb = 0; qb < nb; ++qb, ++blk) {
+                    const int g = blk % RT_NG, use = blk / RT_NG;
+                    if (use >= 1) { mbar_wait(&tfree[g], (uint32_t)((use - 1) & 1)); tc_fence_after(); }
+                    const int wb = min(RT_QB, npad - qb * RT_QB);
+                    const uint64_t qd = desc_sw128(kaddr + (uint32_t)(kpc * RT_KEYS + qb * RT_QB) * 128u);
+                    const uint32_t idesc = idesc_kmajor(RT_KEYS, wb, F16);
 #pragma unroll
-                for (int k = 0; k < DH / 16; ++k) umma_ss_elect(tmem_base + g * RT_QB, kd + 2 * k, qd + 2 * k, idesc, k != 0);
-                umma_commit_elect(&bar_s[g]);
+                    for (int k = 0; k < DH / 16; ++k) umma_ss_elect(tmem_base + g * RT_QB, kd + 2 * k, qd + 2 * k, idesc, k != 0);
+                    umma_commit_elect(&bar_s[g]);
+                }
             }
             umma_commit_elect(&empty[st]);                    // every MMA that reads this stage has completed
         }
@@ -139,9 +146,10 @@ rollout_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
         }
     } else {
         // ---- drain group g: keys = TMEM lanes, queries = columns ----
-        const int g = (warp - 4) >> 2, q = warp & 3;
+        const int g = (warp - 4) >> 2, q = warp & 3;                        // a group's four warps cover the four TMEM lane quarters
         const uint32_t trow = tmem_base + g * RT_QB + ((uint32_t)(q * 32) << 16);
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;             // of the block being drained
+        float acc_kt[2] = {0.f, 0.f};                                       // per key tile, over heads and query blocks
         auto drain32 = [&](const uint32_t (&x)[32], const float* lwp) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -155,8 +163,9 @@ rollout_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
         int blk = 0, use = 0;
         for (int h = 0; h < H; ++h) {
             bool have_lw = false;
+            for (int kt = 0; kt < nkt; ++kt)
             for (int qb = 0; qb < nb; ++qb, ++blk) {
-                if ((blk & 1) != g) continue;
+                if (blk % RT_NG != g) continue;
                 if (!have_lw) { mbar_wait(&lw_full[h & 1], (uint32_t)((h >> 1) & 1)); have_lw = true; }
                 mbar_wait(&bar_s[g], (uint32_t)(use & 1));
                 tc_fence_after();
@@ -179,19 +188,30 @@ rollout_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tfree[g]);
                 ++use;
+                const float sblk = (acc0 + acc1) + (acc2 + acc3);
+                acc0 = acc1 = acc2 = acc3 = 0.f;
+                if (kt == 0) acc_kt[0] += sblk; else acc_kt[1] += sblk;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&lw_empty[h & 1]);
         }
-        float acc = (acc0 + acc1) + (acc2 + acc3);
-        if (g == 1) comb[q * 32 + lane] = acc;
-        asm volatile("bar.sync 1, 256;" ::: "memory");                     // the eight drain warps
+        asm volatile("bar.sync 1, %0;" ::"n"(RT_NG * 128) : "memory");     // every drain warp is done with lw (and the producers with lr)
+        if (g > 0) {
+            comb[((g - 1) * 2 + 0) * RT_KEYS + q * 32 + lane] = acc_kt[0];
+            comb[((g - 1) * 2 + 1) * RT_KEYS + q * 32 + lane] = acc_kt[1];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(RT_NG * 128) : "memory");
         if (g == 0) {
-            acc += comb[q * 32 + lane];
-            const int key = k0 + q * 32 + lane;
-            if (key < N && key >= skip) {
-                const float rk = r_in ? r_in[(int64_t)s * N + key] : (key == 0 ? 1.f : 0.f);
-                r_out[(int64_t)s * (N - skip) + key - skip] = fmaf(0.5f / (float)H, acc, 0.5f * rk);
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                float acc = acc_kt[kt];
+#pragma unroll
+                for (int o = 0; o < RT_NG - 1; ++o) acc += comb[(o * 2 + kt) * RT_KEYS + q * 32 + lane];
+                const int key = k0 + kt * RT_KEYS + q * 32 + lane;
+                if (kt < nkt && key < N && key >= skip) {
+                    const float rk = r_in ? r_in[(int64_t)s * N + key] : (key == 0 ? 1.f : 0.f);
+                    r_out[(int64_t)s * (N - skip) + key - skip] = fmaf(0.5f / (float)H, acc, 0.5f * rk);
+                }
             }
         }
     }
@@ -201,15 +221,16 @@ rollout_step_tc_kernel(const __grid_constant__ CUtensorMap tmap, const float* __
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-size_t rollout_tc_smem(int npad) {
-    return (size_t)RT_NST * (RT_KEYS + npad) * 128 + (size_t)3 * npad * sizeof(float) + RT_KEYS * sizeof(float) + 128 + 1024;
+size_t rollout_tc_smem(int npad, int kpc) {
+    return (size_t)RT_NST * (kpc * RT_KEYS + npad) * 128 + (size_t)3 * npad * sizeof(float) + 256 + 1024;
 }
 
 }  // namespace
 
 bool rollout_step_tc_supported(int dt, int N) {
     const int npad = (int)round_up(N, 32);
-    return (dt == DT_BF16 || dt == DT_F16) && npad > RT_QB && rollout_tc_smem(npad) <= 227 * 1024;
+    // >= 3 query blocks per head: no drain group is without a block in two consecutive heads (lw_empty hand-off, see the kernel)
+    return (dt == DT_BF16 || dt == DT_F16) && npad > 256 && rollout_tc_smem(npad, 1) <= 227 * 1024;
 }
 
 void rollout_step_tc(const void* qkv, const float* lse, const float* r_in, float* r_out, int dt, int S, int N, int H, bool last,
@@ -219,19 +240,22 @@ void rollout_step_tc(const void* qkv, const float* lse, const float* r_in, float
     const bool f16 = dt == DT_F16;
     const CUtensorMap& tm = make_tmap(qkv, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (int64_t)S * N, 3 * d,
                                       3 * d, 32, 64);
-    const size_t smem = rollout_tc_smem(npad);
+    const int ntl = (int)ceil_div(N, RT_KEYS);
+    static const int kpc_env = getenv("TAPCLIP_ROLLOUT_KPC") ? atoi(getenv("TAPCLIP_ROLLOUT_KPC")) : 0;   // measurement switch: 1 | 2
+    const int kpc = (kpc_env != 1 && ntl >= 2 && rollout_tc_smem(npad, 2) <= 227 * 1024) ? 2 : 1;      // key tiles per CTA
+    const size_t smem = rollout_tc_smem(npad, kpc);
     static size_t conf[2] = {0, 0};
     if (smem > conf[f16]) {
         if (f16) TC_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else TC_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conf[f16] = smem;
     }
-    const unsigned grid = (unsigned)(S * (int)ceil_div(N, RT_KEYS));
+    const unsigned grid = (unsigned)(S * (int)ceil_div(ntl, kpc));
     // tile-major launch order: the key tiles of an image run at the same time and share its Q rows in L2 (1.28 vs 1.52 ms at
     // B=512, N=577: image-major re-reads every row from HBM, 3.8 GB per launch, as 128-byte pieces)
     static const int tile_major = getenv("TAPCLIP_ROLLOUT_ORDER") ? atoi(getenv("TAPCLIP_ROLLOUT_ORDER")) : 1;
-    if (f16) launch_pdl(rollout_step_tc_kernel<true>, grid, RT_THREADS, smem, stream, tm, lse, r_in, r_out, S, N, H, npad, last ? 1 : 0, tile_major);
-    else launch_pdl(rollout_step_tc_kernel<false>, grid, RT_THREADS, smem, stream, tm, lse, r_in, r_out, S, N, H, npad, last ? 1 : 0, tile_major);
+    if (f16) launch_pdl(rollout_step_tc_kernel<true>, grid, RT_THREADS, smem, stream, tm, lse, r_in, r_out, S, N, H, npad, last ? 1 : 0, tile_major, kpc);
+    else launch_pdl(rollout_step_tc_kernel<false>, grid, RT_THREADS, smem, stream, tm, lse, r_in, r_out, S, N, H, npad, last ? 1 : 0, tile_major, kpc);
     TC_LAUNCH_CHECK();
 }
 
