@@ -370,12 +370,21 @@ template <bool F16, int NCH>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, void* __restrict__ out_,
                     int N, int H, int nkp, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out,
-                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out) {
+                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out, int pair) {
     using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int slot_bytes = 128 * 128 + 2 * nkp * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSLOT * slot_bytes);
+    // Operand slots.  pair = 0: NSLOT slots of [Q 16 KB | K | V], item i in slot i % NSLOT.
+    // pair = 1 (two q-tiles per head, 128 < N <= 208): the scheduling unit is a head, its q-tiles are items 2p and 2p+1 (one per
+    // softmax group) and share ONE slot [Q0 | Q1 | K | V] (slot p % 2): K and V cross L2 -> shared memory once per head.  All
+    // three tcgen05 attention-side kernels were found sitting at ~3 TB/s of TMA loads; this removes 38 % of them here.
+    const int q_bytes = pair ? 2 * 128 * 128 : 128 * 128;
+    const int slot_bytes = q_bytes + 2 * nkp * 128;
+    const int nslot = pair ? 2 : NSLOT;
+    auto slot_of = [&](int i) { return pair ? ((i >> 1) & 1) : (i % NSLOT); };
+    auto q_off = [&](int i) { return pair ? (i & 1) * 128 * 128 : 0; };
+    auto load_parity = [&](int i) { return (uint32_t)((pair ? (i >> 2) : (i / NSLOT)) & 1); };
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nslot * slot_bytes);
     uint64_t* bar_load = bars;            // [3] TMA transaction barriers, one per operand slot
     uint64_t* bar_s = bars + 3;           // [2] S = QK^T complete (per group / TMEM half)
     uint64_t* bar_p = bars + 5;           // [2] P written to TMEM by the group's 4 warps
@@ -383,11 +392,13 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint64_t* bar_tfree = bars + 9;       // [2] O read out of TMEM by the group's 4 warps: the TMEM half may take the next S
     uint64_t* bar_free = bars + 11;       // [2] O stored: the operand slot (its Q tile doubles as store staging) may be refilled
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    float* cls_stage = reinterpret_cast<float*>(smem + NSLOT * slot_bytes + 128);   // [2 groups][CLS_STAGE2] unnormalised CLS-row p
+    float* cls_stage = reinterpret_cast<float*>(smem + nslot * slot_bytes + 128);   // [2 groups][CLS_STAGE2] unnormalised CLS-row p
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int d = H * DH;
-    const int n_mine = (n_items > (int)blockIdx.x) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // n_items counts scheduling units: items, or heads (= two items) in pair mode
+    const int n_units = (n_items > (int)blockIdx.x) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_mine = pair ? 2 * n_units : n_units;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -414,7 +425,20 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 4 x 40 + 8 x 232 = 12 x 168
         if (warp == 0) {
             // ---- loader ----
-            if (lane == 0) {
+            if (lane == 0 && pair) {
+                for (int p = 0; p < n_units; ++p) {
+                    // slot p%2 was last used by head p-2: both of its items must have stored their O
+                    if (p >= 2) { mbar_wait(&bar_free[0], (uint32_t)((p - 2) & 1)); mbar_wait(&bar_free[1], (uint32_t)((p - 2) & 1)); }
+                    const int sh = (int)blockIdx.x + p * (int)gridDim.x, s = sh / H, h = sh % H;
+                    uint8_t* Qs = smem + (p & 1) * slot_bytes;
+                    uint64_t* bl = &bar_load[p & 1];
+                    mbar_expect_tx(bl, (uint32_t)slot_bytes);
+                    tma_load_2d(Qs, &tmap_q, h * DH, s * N, bl);
+                    tma_load_2d(Qs + 128 * 128, &tmap_q, h * DH, s * N + 128, bl);
+                    tma_load_2d(Qs + q_bytes, &tmap_kv, d + h * DH, s * N, bl);
+                    tma_load_2d(Qs + q_bytes + nkp * 128, &tmap_kv, 2 * d + h * DH, s * N, bl);
+                }
+            } else if (lane == 0) {
                 for (int i = 0; i < n_mine; ++i) {
                     // slot i%3 was last used by item i-3: operands dead after PV(i-3), staging (Q area) dead once its O is stored
                     if (i >= NSLOT) mbar_wait(&bar_free[(i - NSLOT) & 1], (uint32_t)(((i - NSLOT) >> 1) & 1));
@@ -434,12 +458,12 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const int nks = nkp / 16;
             auto issue_s = [&](int i) {
                 const int hf = i & 1;
-                uint8_t* Qs = smem + (i % NSLOT) * slot_bytes;
-                mbar_wait(&bar_load[i % NSLOT], (uint32_t)((i / NSLOT) & 1));
+                uint8_t* slot = smem + slot_of(i) * slot_bytes;
+                mbar_wait(&bar_load[slot_of(i)], load_parity(i));
                 if (i >= 2) mbar_wait(&bar_tfree[hf], (uint32_t)(((i >> 1) - 1) & 1));     // O(i-2) has left this TMEM half
                 tc_fence_after();
                 const uint32_t thalf = tmem_base + hf * 256;
-                const uint64_t qd = smem_desc_sw128(smem_u32(Qs)), kd = smem_desc_sw128(smem_u32(Qs + 128 * 128));
+                const uint64_t qd = smem_desc_sw128(smem_u32(slot + q_off(i))), kd = smem_desc_sw128(smem_u32(slot + q_bytes));
 #pragma unroll
                 for (int k = 0; k < DH / 16; ++k) umma_ss_elect(thalf, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
                 umma_commit_elect(&bar_s[hf]);
@@ -449,7 +473,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const uint32_t thalf = tmem_base + hf * 256;
                 mbar_wait(&bar_p[hf], (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
-                const uint64_t vd = smem_desc_sw128(smem_u32(smem + (j % NSLOT) * slot_bytes + 128 * 128 + nkp * 128));
+                const uint64_t vd = smem_desc_sw128(smem_u32(smem + slot_of(j) * slot_bytes + q_bytes + nkp * 128));
 #pragma unroll
                 for (int ks = 0; ks < 13; ++ks)                        // NKP <= 208: at most 13 k-steps
                     if (ks < nks) umma_ts_elect(thalf + O_COL, thalf + ks * 8, vd + (uint64_t)(ks * 128), idesc_o, ks != 0);
@@ -472,13 +496,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
         const int rd_row = lane >> 3, rd_ch = lane & 7;                // store mapping: 8 lanes cover one 128-byte row segment
         // (q-tile, head, sequence) of the group's current item, advanced incrementally (no divisions inside the loop)
+        // pair mode: the group keeps q-tile g and walks the CTA's heads; otherwise item ids b + i * grid, i = g, g + 2, ...
         const int step2 = 2 * (int)gridDim.x;
-        const int step_qt = step2 % nqt, step_sh = step2 / nqt, step_h = step_sh % H, step_s = step_sh / H;
+        const int step_qt = pair ? 0 : step2 % nqt, step_sh = pair ? (int)gridDim.x : step2 / nqt, step_h = step_sh % H, step_s = step_sh / H;
         const int id0 = (int)blockIdx.x + g * (int)gridDim.x;
-        int qt = id0 % nqt, h = (id0 / nqt) % H, s = (id0 / nqt) / H;
+        int qt = pair ? g : id0 % nqt, h = pair ? (int)blockIdx.x % H : (id0 / nqt) % H, s = pair ? (int)blockIdx.x / H : (id0 / nqt) / H;
         for (int i = g; i < n_mine; i += 2) {
             const uint32_t par = (uint32_t)((i >> 1) & 1);
-            uint8_t* Qs = smem + (i % NSLOT) * slot_bytes;
+            uint8_t* Qs = smem + slot_of(i) * slot_bytes + q_off(i);
             const int grow = qt * 128 + row;
             const bool warp_active = qt * 128 + q * 32 < N;            // else: all 32 rows of this warp are padding
             const bool cls_warp = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0;
@@ -935,11 +960,15 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
     }
     const CUtensorMap& tkv = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, nkp, 64);
     if (nkp <= 208) {
-        // persistent pipelined kernel: 3 operand slots of (Q 16 KB + K + V) fit in shared memory
-        const size_t smem2 = NSLOT * (128 * 128 + 2 * (size_t)nkp * 128) + 128 + 2 * CLS_STAGE2 * sizeof(float) + 1024;   // + barriers/TMEM slot, CLS staging, alignment slack
+        // persistent pipelined kernel: 3 operand slots of (Q 16 KB + K + V) fit in shared memory; with two q-tiles per head
+        // (pair mode) 2 slots of (Q0 + Q1 + K + V), so that a head's K and V are loaded once
+        static const int pair_env = getenv("TAPCLIP_ATTN_PAIR") ? atoi(getenv("TAPCLIP_ATTN_PAIR")) : 1;    // 0: measurement switch
+        const int pair = (nqt == 2 && pair_env != 0) ? 1 : 0;
+        const size_t slots = pair ? 2 * (2 * 128 * 128 + 2 * (size_t)nkp * 128) : NSLOT * (128 * 128 + 2 * (size_t)nkp * 128);
+        const size_t smem2 = slots + 128 + 2 * CLS_STAGE2 * sizeof(float) + 1024;   // + barriers/TMEM slot, CLS staging, alignment slack
         static int num_sms = 0;
         if (num_sms == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
-        const int n_items = S * H * nqt;
+        const int n_items = pair ? S * H : S * H * nqt;        // scheduling units
         const unsigned grid2 = (unsigned)std::min(n_items, num_sms);
         // softmax chunk count instance: 4 (N <= 64, ViT-B/32), 8 (N <= 128, the text tower), 13 (N <= 208, ViT-B/16)
         const int nch = nkp / 16;
@@ -948,7 +977,7 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
                 TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
                 configured = smem2;
             }
-            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
+            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair);
         };
         static size_t conf2[2][3] = {{0, 0, 0}, {0, 0, 0}};
         if (nch <= 4) { if (f16) go(attn_fwd_tc2_kernel<true, 4>, conf2[1][0]); else go(attn_fwd_tc2_kernel<false, 4>, conf2[0][0]); }
