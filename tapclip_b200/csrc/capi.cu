@@ -17,7 +17,7 @@ static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s)
 extern "C" {
 
 TAPCLIP_API const char* tapclip_last_error(void) { return get_error(); }
-TAPCLIP_API const char* tapclip_version(void) { return "tapclip-b200 0.1 (sm_100a: tcgen05/TMEM/TMA GEMM, mma.sync attention)"; }
+TAPCLIP_API const char* tapclip_version(void) { return "tapclip-b200 0.1 (sm_100a: tcgen05/TMEM/TMA GEMM, attention and rollout)"; }
 
 TAPCLIP_API int tapclip_create(const tapclip_config* cfg, tapclip_handle* out) {
     TC_API_BEGIN
