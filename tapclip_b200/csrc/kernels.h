@@ -58,6 +58,7 @@ void rollout_step(const void* qkv, const float* lse, const float* r_in, float* r
                   cudaStream_t stream);
 // tcgen05 version for long 16-bit sequences (rollout_tc.cu); rollout_step dispatches to it (TAPCLIP_ROLLOUT_IMPL=1: mma.sync)
 bool rollout_step_tc_supported(int dt, int N);
+int rollout_step_tc_ctas(int S, int N);            // CTAs the tcgen05 kernel would launch
 void rollout_step_tc(const void* qkv, const float* lse, const float* r_in, float* r_out, int dt, int S, int N, int H, bool last,
                      cudaStream_t stream);
 // dqkv [S*N, 3*H*64] from d_out [S*N, H*64] and the saved qkv (probabilities recomputed). N <= 128.

@@ -320,7 +320,8 @@ void rollout_step(const void* qkv, const float* lse, const float* r_in, float* r
     TC_CHECK(N >= 2 && H >= 1 && lse && r_out, "bad rollout_step arguments");
     const int skip = last ? 1 : 0;
     static const int impl = getenv("TAPCLIP_ROLLOUT_IMPL") ? atoi(getenv("TAPCLIP_ROLLOUT_IMPL")) : 0;   // 0 auto, 1 mma.sync, 2 tcgen05
-    if (impl != 1 && rollout_step_tc_supported(dt, N) && (impl == 2 || (int64_t)S * ceil_div(N, 128) >= 148)) {
+    // tcgen05 kernel when its (image, key-tile group) CTAs fill at least ~2/3 of the SMs
+    if (impl != 1 && rollout_step_tc_supported(dt, N) && (impl == 2 || rollout_step_tc_ctas(S, N) >= 96)) {
         rollout_step_tc(qkv, lse, r_in, r_out, dt, S, N, H, last, stream);
         return;
     }

@@ -227,22 +227,31 @@ size_t rollout_tc_smem(int npad, int kpc) {
 
 }  // namespace
 
-bool rollout_step_tc_supported(int dt, int N) {
-    const int npad = (int)round_up(N, 32);
-    // >= 3 query blocks per head: no drain group is without a block in two consecutive heads (lw_empty hand-off, see the kernel)
-    return (dt == DT_BF16 || dt == DT_F16) && npad > 256 && rollout_tc_smem(npad, 1) <= 227 * 1024;
+// key tiles per CTA: two when they fit (the Q rows of a head then serve 256 keys)
+int rollout_tc_kpc(int N) {
+    static const int kpc_env = getenv("TAPCLIP_ROLLOUT_KPC") ? atoi(getenv("TAPCLIP_ROLLOUT_KPC")) : 0;   // measurement switch: 1 | 2
+    const int npad = (int)round_up(N, 32), ntl = (int)ceil_div(N, RT_KEYS);
+    return (kpc_env != 1 && ntl >= 2 && rollout_tc_smem(npad, 2) <= 227 * 1024) ? 2 : 1;
 }
+
+bool rollout_step_tc_supported(int dt, int N) {
+    const int npad = (int)round_up(N, 32), ntl = (int)ceil_div(N, RT_KEYS), nb = (int)ceil_div(npad, RT_QB), kpc = rollout_tc_kpc(N);
+    // every CTA needs >= 3 (key tile, query block) MMA blocks per head: then no drain group is without a block in two consecutive
+    // heads (lw_empty hand-off, see the kernel).  The image's last CTA holds ntl % kpc key tiles when that is not zero.
+    const int min_tiles = (ntl % kpc) ? ntl % kpc : kpc;
+    return (dt == DT_BF16 || dt == DT_F16) && min_tiles * nb >= 3 && rollout_tc_smem(npad, kpc) <= 227 * 1024;
+}
+int rollout_step_tc_ctas(int S, int N) { return S * (int)ceil_div(ceil_div(N, RT_KEYS), rollout_tc_kpc(N)); }
 
 void rollout_step_tc(const void* qkv, const float* lse, const float* r_in, float* r_out, int dt, int S, int N, int H, bool last,
                      cudaStream_t stream) {
-    TC_CHECK(rollout_step_tc_supported(dt, N), "tcgen05 rollout step: 16-bit inputs, 256 < N <= ~700");
+    TC_CHECK(rollout_step_tc_supported(dt, N), "tcgen05 rollout step: 16-bit inputs, 128 < N <= ~700");
     const int d = H * DH, npad = (int)round_up(N, 32);
     const bool f16 = dt == DT_F16;
     const CUtensorMap& tm = make_tmap(qkv, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (int64_t)S * N, 3 * d,
                                       3 * d, 32, 64);
     const int ntl = (int)ceil_div(N, RT_KEYS);
-    static const int kpc_env = getenv("TAPCLIP_ROLLOUT_KPC") ? atoi(getenv("TAPCLIP_ROLLOUT_KPC")) : 0;   // measurement switch: 1 | 2
-    const int kpc = (kpc_env != 1 && ntl >= 2 && rollout_tc_smem(npad, 2) <= 227 * 1024) ? 2 : 1;      // key tiles per CTA
+    const int kpc = rollout_tc_kpc(N);
     const size_t smem = rollout_tc_smem(npad, kpc);
     static size_t conf[2] = {0, 0};
     if (smem > conf[f16]) {

@@ -142,7 +142,7 @@ def test_attention_bwd(S, N, H, dtype):
 
 @pytest.mark.parametrize("S,N,H", [(3, 197, 12), (2, 577, 16), (5, 50, 12), (2, 17, 4), (3, 130, 2),      # mma.sync / SIMT statistics
                                    (90, 197, 12), (40, 577, 16), (44, 257, 8),                           # tcgen05 forward kernels
-                                   (50, 257, 8), (30, 700, 4)])                                          # + tcgen05 rollout step (N > 256, >= 148 CTAs)
+                                   (50, 257, 8), (30, 700, 4), (100, 197, 12), (120, 130, 6)])           # + tcgen05 rollout step (N > 128, >= 96 CTAs)
 @pytest.mark.parametrize("dtype", ["bf16", "fp16", "fp32"])
 def test_rollout_step_and_softmax_statistics(S, N, H, dtype):
     """Rollout extension (rollout.cu): the softmax statistics from the stand-alone kernel and from the attention forward
