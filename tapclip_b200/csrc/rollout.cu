@@ -13,6 +13,8 @@
 //
 //  * rollout_step_mma_kernel  16-bit Q/K: S^T = K Q^T on mma.sync m16n8k16; a CTA owns up to 256 keys of one image (32 per
 //                             warp), loops over heads and 32-query steps; no atomics, deterministic.
+//                             Small problems and N <= 128; rollout_step() sends everything else to the tcgen05 kernel in
+//                             rollout_tc.cu (same contract).
 //  * rollout_step_simt_kernel fp32 parity mode (one warp per key).
 //  * attn_lse_mma_kernel / attn_lse_simt_kernel  the statistics alone, for forward kernels that do not emit them.
 #include "kernels.h"
