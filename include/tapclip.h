@@ -86,10 +86,12 @@ TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int3
  *   feature pass on [ctx*a | tok], last position, @ text_projection, L2-norm -> out_text_feat [C,E].
  *   mode 2 (ATTRIBUTION_ONLY): the INTENDED attribution pass alone (out_attr_raw / out_attr), no feature pass: used by the
  *   'gate' / 'residual' adjustors (prompt_adjustor.py:38-44), whose small networks run on the host side between the passes.
- * save_for_backward != 0 keeps the activations `tapclip_text_backward` needs. */
+ * save_for_backward != 0 keeps the activations `tapclip_text_backward` needs (ONE saved forward per handle: the next
+ * tapclip_text_forward / tapclip_encode_text replaces them).
+ * out_token (nullable): identifies the activations this call saved (0 if none); pass it to tapclip_text_backward. */
 TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const float* tok, int32_t C, int32_t P, int32_t mode,
                          int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat,
-                         void* stream);
+                         int64_t* out_token, void* stream);
 
 /* CLIPWrapper.encode_text (clip_wrapper.py:49-51 -> open_clip CLIP.encode_text; SURVEY 8f rank 1 — FullModel never calls
  * it): token_ids int64 [S, context_length] (device) -> out_feat [S,E] (NOT normalised): token + positional embedding,
@@ -111,8 +113,11 @@ TAPCLIP_API int tapclip_logits_backward(tapclip_handle h, const float* dlogits, 
 
 /* Row A13 (autograd of model_wrapper.py:68-75 down to prompt_learner.context_bank): d_text_feat [C,E]
  * -> out_dctx [C,P,D]; activation gradients only (frozen weights), attribution treated as constant.
- * Must follow a tapclip_text_forward(..., save_for_backward=1) with the same C, P. */
-TAPCLIP_API int tapclip_text_backward(tapclip_handle h, const float* d_text_feat, float* out_dctx, void* stream);
+ * Must follow a tapclip_text_forward(..., save_for_backward=1) with the same C, P.  token = the forward's out_token: if a
+ * later forward on this handle has replaced the saved activations the call FAILS (stale backward) instead of differentiating
+ * the wrong forward; token 0 skips that check.  C, P (> 0) are checked against the saved forward. */
+TAPCLIP_API int tapclip_text_backward(tapclip_handle h, const float* d_text_feat, float* out_dctx, int64_t token, int32_t C, int32_t P,
+                          void* stream);
 
 /* train.py:65-67,105: torch.optim.AdamW step fused over a flat fp32 bank of n elements. */
 TAPCLIP_API int tapclip_adamw_step(tapclip_handle h, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
@@ -135,11 +140,25 @@ TAPCLIP_API int tapclip_profile(tapclip_handle h, int32_t enable);
 TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
 
 /* ---- single-kernel entry points (used by the per-kernel parity tests and micro-benchmarks) -------- */
-/* Residual GEMM with a fused pre-LN epilogue (K1-LN, gemm_ln.cu): x[M,N] (fp32, in place) += A[M,K].W[N,K]^T + bias, then
- * ln_out[M,N] (16-bit, `dtype`) = LayerNorm(x; gamma, beta) and optionally x_copy[M,N] = x.  Replaces `x = x + f(...)` followed
- * by the next `ln_1` / `ln_2` of open_clip's residual blocks.  N in {512, 768, 1024}; dtype BF16 or FP16 (mixed-mode value 2). */
-TAPCLIP_API int tapclip_op_gemm_resid_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x,
-                             void* ln_out, float* x_copy, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream);
+/* The pre-LN residual block without LayerNorm kernels (north-star "fused ... pre-LN epilogues"): replaces `x = x + attn(ln_1(x))`,
+ * `x = x + mlp(ln_2(x))` of open_clip's ResidualAttentionBlock (invoked from models/model_wrapper.py:58,72 and
+ * models/clip_wrapper.py:47).
+ *   tapclip_op_gemm_resid : x_out[M,N] (fp32, ld_out) = x_in[M,N] (fp32, ld_in; may alias x_out) + A[M,K].W[N,K]^T + bias; optionally
+ *       xb[M,N] = x_out in the 16-bit `dtype` (dense) and stats[M][parts][2] = per-row partial (sum, sum of squares) of x_out,
+ *       parts = tapclip_op_gemm_stats_parts(N).  ld 0 = dense.
+ *   tapclip_op_gemm_fold  : out[M,N] (16-bit) = act(LayerNorm(x; gamma, beta).W^T + b) computed from the UN-normalised 16-bit rows xb,
+ *       their statistics partials and the folded operands (w_fold = W diag(gamma), fold_s[n] = sum_k w_fold[n,k], bias_fold = b + W beta):
+ *       LN(x) W^T + b = rstd (xb w_fold^T - mean fold_s) + bias_fold.  out_pre (nullable, needs act): pre-activation copy.
+ *   tapclip_op_fold_ln_weight / tapclip_op_row_stats_cast : build the folded operands / the (xb, stats) pair of arbitrary rows. */
+TAPCLIP_API int32_t tapclip_op_gemm_stats_parts(int64_t N);
+TAPCLIP_API int tapclip_op_gemm_resid(const void* a, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out,
+                          int64_t ld_out, void* xb, float* stats, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream);
+TAPCLIP_API int tapclip_op_gemm_fold(const void* xb, const float* stats, int32_t stats_parts, const void* w_fold, const float* bias_fold,
+                         const float* fold_s, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int32_t dtype, int32_t act,
+                         void* stream);
+TAPCLIP_API int tapclip_op_fold_ln_weight(const float* w, const float* bias, const float* gamma, const float* beta, void* w_fold,
+                              int32_t dtype, float* fold_s, float* bias_fold, int32_t N, int32_t K, void* stream);
+TAPCLIP_API int tapclip_op_row_stats_cast(const float* x, void* xb, int32_t dtype, float* stats, int64_t rows, int32_t d, void* stream);
 
 /* Image preprocessing on the device: what `CLIPWrapper.get_preprocess()` (models/clip_wrapper.py:64-65,
  * open_clip's inference transform, applied per image at dataset.py:31) does on the host with Pillow/torchvision:

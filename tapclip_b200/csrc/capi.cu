@@ -61,11 +61,13 @@ TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int3
 }
 
 TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const float* tok, int32_t C, int32_t P, int32_t mode,
-                         int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat, void* stream) {
+                         int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat, int64_t* out_token,
+                         void* stream) {
     TC_API_BEGIN
     NEED(h);
     TC_CHECK(C == 0 || (ctx != nullptr && tok != nullptr), "null argument");
-    h->impl.text_forward(ctx, tok, C, P, mode, save_for_backward != 0, out_attr_raw, out_attr, out_text_feat, S(stream));
+    const int64_t token = h->impl.text_forward(ctx, tok, C, P, mode, save_for_backward != 0, out_attr_raw, out_attr, out_text_feat, S(stream));
+    if (out_token) *out_token = token;
     TC_API_END
 }
 
@@ -96,11 +98,12 @@ TAPCLIP_API int tapclip_logits_backward(tapclip_handle h, const float* dlogits, 
     TC_API_END
 }
 
-TAPCLIP_API int tapclip_text_backward(tapclip_handle h, const float* d_text_feat, float* out_dctx, void* stream) {
+TAPCLIP_API int tapclip_text_backward(tapclip_handle h, const float* d_text_feat, float* out_dctx, int64_t token, int32_t C, int32_t P,
+                          void* stream) {
     TC_API_BEGIN
     NEED(h);
     TC_CHECK(d_text_feat && out_dctx, "null argument");
-    h->impl.text_backward(d_text_feat, out_dctx, S(stream));
+    h->impl.text_backward(d_text_feat, out_dctx, S(stream), token, C, P);
     TC_API_END
 }
 
@@ -147,13 +150,42 @@ TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias,
     TC_API_END
 }
 
-TAPCLIP_API int tapclip_op_gemm_resid_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x,
-                             void* ln_out, float* x_copy, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream) {
+TAPCLIP_API int32_t tapclip_op_gemm_stats_parts(int64_t N) { return gemm_stats_parts(N); }
+
+TAPCLIP_API int tapclip_op_gemm_resid(const void* a, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out,
+                          int64_t ld_out, void* xb, float* stats, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream) {
     TC_API_BEGIN
-    GemmLnArgs g;
-    g.a = a; g.w = w; g.bias = bias; g.gamma = gamma; g.beta = beta; g.x = x; g.ln_out = ln_out; g.x_copy = x_copy;
-    g.M = M; g.N = N; g.K = K; g.ldx = N; g.dt = dtype;
-    gemm_resid_ln(g, S(stream));
+    GemmArgs g;
+    g.a = a; g.w = w; g.bias = bias; g.out = x_out;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = ld_out ? ld_out : N; g.epi = EPI_F32_RESID; g.act = ACT_NONE; g.dt = dtype;
+    g.resid_in = x_in; g.ld_in = ld_in ? ld_in : N; g.xb = xb; g.stats_out = stats;
+    gemm_tc(g, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_gemm_fold(const void* xb, const float* stats, int32_t stats_parts, const void* w_fold, const float* bias_fold,
+                         const float* fold_s, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int32_t dtype, int32_t act,
+                         void* stream) {
+    TC_API_BEGIN
+    GemmArgs g;
+    g.a = xb; g.w = w_fold; g.bias = bias_fold; g.out = out; g.out_pre = out_pre;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = EPI_BF16; g.act = act; g.dt = dtype;
+    g.stats_in = stats; g.stats_parts = stats_parts; g.fold_s = fold_s;
+    TC_CHECK(stats != nullptr, "stats is required");
+    gemm_tc(g, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_fold_ln_weight(const float* w, const float* bias, const float* gamma, const float* beta, void* w_fold,
+                              int32_t dtype, float* fold_s, float* bias_fold, int32_t N, int32_t K, void* stream) {
+    TC_API_BEGIN
+    fold_ln_weight(w, bias, gamma, beta, w_fold, dtype, fold_s, bias_fold, N, K, S(stream));
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_op_row_stats_cast(const float* x, void* xb, int32_t dtype, float* stats, int64_t rows, int32_t d, void* stream) {
+    TC_API_BEGIN
+    row_stats_cast(x, xb, dtype, stats, rows, d, S(stream));
     TC_API_END
 }
 

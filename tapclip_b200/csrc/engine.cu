@@ -96,7 +96,7 @@ std::vector<DevBuf*> Engine::all_bufs() {
     return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled, &v_roll_qkv, &v_lse, &v_roll,
             &t_x, &t_ln, &t_qkv, &t_attn, &t_h, &t_pooled, &t_feat, &t_tfeat, &t_inv_norm, &t_probe, &t_attr, &t_attr_raw,
             &t_save_x, &t_save_qkv, &t_save_h, &b_dx, &b_dxc, &b_dh, &b_dln, &b_dattn, &b_dqkv, &b_dfeat, &b_dfeatc, &b_dpool,
-            &s_rows, &s_cls, &e_eot, &e_pool};
+            &s_rows, &s_cls, &e_eot, &e_pool, &v_xb, &v_stats, &v_xlive, &t_xb, &t_stats, &t_xlive};
 }
 
 int64_t Engine::workspace_bytes() {
@@ -187,19 +187,52 @@ void Engine::load_weight(const std::string& name, const float* data, int ndim, c
         w = store(name, data, N, K, K, false, is_vis ? vdt : tdt, st);
         if (need_t) wt = store(name + "#T", data, N, K, N, true, gdt, st);      // [K, N], gradient type
     };
-    if (leaf == "ln_1.weight") vec(b.ln1_g, d);
-    else if (leaf == "ln_1.bias") vec(b.ln1_b, d);
-    else if (leaf == "ln_2.weight") vec(b.ln2_g, d);
-    else if (leaf == "ln_2.bias") vec(b.ln2_b, d);
-    else if (leaf == "attn.in_proj_weight") mat(b.w_qkv, b.wt_qkv, 3 * d, d);
-    else if (leaf == "attn.in_proj_bias") vec(b.b_qkv, 3 * d);
+    const bool fold = cfg.dtype != DT_F32;                                       // 16-bit modes: LayerNorm folded into QKV / c_fc
+    auto keep_f32 = [&](float*& slot, int N, int K) { if (fold) slot = (float*)store(name + "#F32", data, N, K, K, false, DT_F32, st); };
+    const std::string prefix = (is_vis ? vp : tp) + std::to_string(layer) + ".";
+    const int odt = is_vis ? vdt : tdt;
+    int group = -1;                                                              // fold group this entry belongs to: 0 = ln_1 -> QKV, 1 = ln_2 -> c_fc
+    if (leaf == "ln_1.weight") { vec(b.ln1_g, d); group = 0; }
+    else if (leaf == "ln_1.bias") { vec(b.ln1_b, d); group = 0; }
+    else if (leaf == "ln_2.weight") { vec(b.ln2_g, d); group = 1; }
+    else if (leaf == "ln_2.bias") { vec(b.ln2_b, d); group = 1; }
+    else if (leaf == "attn.in_proj_weight") { mat(b.w_qkv, b.wt_qkv, 3 * d, d); keep_f32(b.f32_qkv, 3 * d, d); group = 0; }
+    else if (leaf == "attn.in_proj_bias") { vec(b.b_qkv, 3 * d); group = 0; }
     else if (leaf == "attn.out_proj.weight") mat(b.w_o, b.wt_o, d, d);
     else if (leaf == "attn.out_proj.bias") vec(b.b_o, d);
-    else if (leaf == "mlp.c_fc.weight") mat(b.w_fc, b.wt_fc, 4 * d, d);
-    else if (leaf == "mlp.c_fc.bias") vec(b.b_fc, 4 * d);
+    else if (leaf == "mlp.c_fc.weight") { mat(b.w_fc, b.wt_fc, 4 * d, d); keep_f32(b.f32_fc, 4 * d, d); group = 1; }
+    else if (leaf == "mlp.c_fc.bias") { vec(b.b_fc, 4 * d); group = 1; }
     else if (leaf == "mlp.c_proj.weight") mat(b.w_proj, b.wt_proj, d, 4 * d);
     else if (leaf == "mlp.c_proj.bias") vec(b.b_proj, d);
     else TC_CHECK(false, "unknown weight name '%s'", name.c_str());
+    if (fold && group >= 0) fold_group(b, group, prefix, d, odt, st);
+}
+
+// (Re)builds the folded operands of one LayerNorm -> Linear pair once its four tensors are present (on the loading stream: the
+// caller synchronises it before the first forward, engine.py load_state_dict).
+void Engine::fold_group(BlockWeights& b, int group, const std::string& prefix, int d, int dt, cudaStream_t st) {
+    const float* W = group == 0 ? b.f32_qkv : b.f32_fc;
+    const float* bias = group == 0 ? b.b_qkv : b.b_fc;
+    const float* gamma = group == 0 ? b.ln1_g : b.ln2_g;
+    const float* beta = group == 0 ? b.ln1_b : b.ln2_b;
+    if (!W || !bias || !gamma || !beta) return;
+    const int N = (group == 0 ? 3 : 4) * d, K = d;
+    const std::string key = prefix + (group == 0 ? "fold.qkv" : "fold.fc");
+    auto alloc = [&](const std::string& k, size_t bytes) {
+        auto it = weights.find(k);
+        if (it != weights.end()) return it->second;          // same shape as before: reuse
+        void* p = nullptr;
+        TC_CUDA(cudaMalloc(&p, bytes));
+        weights[k] = p;
+        return p;
+    };
+    void* wf = alloc(key + ".w", (size_t)N * K * dtype_size(dt));
+    float* fs = (float*)alloc(key + ".s", (size_t)N * 4);
+    float* fb = (float*)alloc(key + ".b", (size_t)N * 4);
+    fold_ln_weight(W, bias, gamma, beta, wf, dt, fs, fb, N, K, st);
+    ++launches;
+    if (group == 0) { b.wf_qkv = wf; b.fs_qkv = fs; b.fb_qkv = fb; }
+    else { b.wf_fc = wf; b.fs_fc = fs; b.fb_fc = fb; }
 }
 
 std::string Engine::missing_weights() const {
@@ -302,30 +335,41 @@ void Engine::attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int
     ++launches;
 }
 
-// one residual attention block on x [S*N, d] (fp32, updated in place).
-//   probe      : attention probe for this layer (or PROBE_NONE)
-//   stop_after_attention_probs : attribution pass, last block: only the probabilities are needed
-//   save       : keep x copies / qkv / h_pre for the backward pass (slot = layer)
-bool Engine::gemm_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x, void* ln_out,
-                     float* x_copy, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st) {
-    if (!gemm_resid_ln_supported(N, K, dt)) return false;
-    GemmLnArgs g;
-    g.a = a; g.w = w; g.bias = bias; g.gamma = gamma; g.beta = beta; g.x = x; g.ln_out = ln_out; g.x_copy = x_copy;
-    g.M = M; g.N = N; g.K = K; g.ldx = N; g.dt = dt;
-    ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, 5};
+void Engine::gemm_fold(const void* xb, const float* stats, int parts, const void* wf, const float* fb, const float* fs, void* out,
+                       void* out_pre, int64_t M, int64_t N, int64_t K, int act, int dt, cudaStream_t st) {
+    TC_CHECK(wf && fb && fs, "folded LayerNorm weights are missing (load ln_*, in_proj_* and c_fc.* of every block)");
+    GemmArgs g;
+    g.a = xb; g.w = wf; g.bias = fb; g.out = out; g.out_pre = out_pre;
+    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = EPI_BF16; g.act = act; g.dt = dt;
+    g.stats_in = stats; g.stats_parts = parts; g.fold_s = fs;
+    ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, 6};
     if (profiling) prof_begin(r, st);
-    gemm_resid_ln(g, st);
+    gemm_tc(g, st);
     if (profiling) prof_end(r, st);
     ++launches;
-    return true;
 }
 
-// `next` (the following block, or null) and `ln1_ready` drive the LayerNorm fusion: with fuse_ln on, this block's
-// out-projection also emits ln_2(x) and its c_proj emits the NEXT block's ln_1(x) (+ the copies the backward pass needs), so
-// a block whose predecessor did that (`ln1_ready`) starts directly with its QKV GEMM.
-bool Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
+void Engine::gemm_resid(const void* a, int64_t lda, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out,
+                        int64_t ldo, void* xb, float* stats, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st) {
+    GemmArgs g;
+    g.a = a; g.w = w; g.bias = bias; g.out = x_out;
+    g.M = M; g.N = N; g.K = K; g.lda = lda ? lda : K; g.ldw = K; g.ldo = ldo ? ldo : N; g.epi = EPI_F32_RESID; g.act = ACT_NONE; g.dt = dt;
+    g.resid_in = x_in; g.ld_in = ld_in ? ld_in : N; g.xb = xb; g.stats_out = stats;
+    ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, 7};
+    if (profiling) prof_begin(r, st);
+    gemm_tc(g, st);
+    if (profiling) prof_end(r, st);
+    ++launches;
+}
+
+// one residual attention block on x [S*N, d] (fp32, updated in place), LayerNorm as its own kernel (fp32 mode, encode_text,
+// TAPCLIP_FUSE_LN=0).
+//   probe      : attention probe for this layer (or PROBE_NONE)
+//   probs_only : attribution pass, last block: only the probabilities are needed
+//   save_slot  : keep x copies / qkv / h_pre for the backward pass (slot = layer)
+void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
                            DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, void* rollout_qkv,
-                           int live_row, const BlockWeights* next, bool ln1_ready) {
+                           int live_row) {
     const int64_t M = (int64_t)S * N;
     float* sx0 = nullptr; float* sx1 = nullptr; void* sqkv = qkv.p; void* shpre = nullptr;
     if (save_slot >= 0) {
@@ -335,10 +379,10 @@ bool Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
         shpre = (uint8_t*)t_save_h.p + (int64_t)save_slot * M * 4 * d * esz;
     }
     if (rollout_qkv) sqkv = rollout_qkv;                       // rollout extension: this layer's Q and K are re-read by rollout_step
-    if (!ln1_ready) { layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, dt, sx0, M, d, st); ++launches; }
+    layernorm_fwd(x, d, b.ln1_g, b.ln1_b, ln.p, dt, sx0, M, d, st); ++launches;
     gemm(ln.p, b.w_qkv, b.b_qkv, sqkv, nullptr, M, 3 * d, d, EPI_BF16, ACT_NONE, dt, st);
     attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
-    if (probs_only) return false;
+    if (probs_only) return;
     if (live_row >= 0) {
         // Dead-row elimination: after the LAST block only token `live_row` of every sequence is read (ln_post(x[:,0])
         // / pooling), and past the attention every row is independent.  The out-projection and the MLP therefore run on the
@@ -351,19 +395,53 @@ bool Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
         layernorm_fwd(xl, ld, b.ln2_g, b.ln2_b, ln.p, dt, sx1, S, d, st); ++launches;
         gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, S, 4 * d, d, EPI_BF16, cfg.act, dt, st);
         gemm(hbuf.p, b.w_proj, b.b_proj, xl, nullptr, S, d, 4 * d, EPI_F32_ADD, ACT_NONE, dt, st, DT_BF16, 0, ld);
-        return false;
+        return;
     }
-    const bool fuse = dt != DT_F32 && ((fuse_ln >= 1 && d == cfg.text_width && &ln == &t_ln) || (fuse_ln >= 2 && &ln == &v_ln));
-    if (!(fuse && gemm_ln(attn.p, b.w_o, b.b_o, b.ln2_g, b.ln2_b, x, ln.p, sx1, M, d, d, dt, st))) {
-        gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, dt, st);
-        layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, dt, sx1, M, d, st); ++launches;
-    }
+    gemm(attn.p, b.w_o, b.b_o, x, nullptr, M, d, d, EPI_F32_ADD, ACT_NONE, dt, st);
+    layernorm_fwd(x, d, b.ln2_g, b.ln2_b, ln.p, dt, sx1, M, d, st); ++launches;
     gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, M, 4 * d, d, EPI_BF16, cfg.act, dt, st);
-    float* next_sx0 = (save_slot >= 0 && next) ? (float*)t_save_x.p + (int64_t)(2 * (save_slot + 1)) * M * d : nullptr;
-    if (fuse && next && gemm_ln(hbuf.p, b.w_proj, b.b_proj, next->ln1_g, next->ln1_b, x, ln.p, next_sx0, M, d, 4 * d, dt, st))
-        return true;                                                    // ln.p = ln_1 of the next block, its saved input written
     gemm(hbuf.p, b.w_proj, b.b_proj, x, nullptr, M, d, 4 * d, EPI_F32_ADD, ACT_NONE, dt, st);
-    return false;
+}
+
+// The same block with no LayerNorm kernel (16-bit modes; see engine.h).  On entry xb / stats describe the rows at `x`.
+void Engine::block_forward_fused(const BlockWeights& b, float*& x, int& parts, float* scratch, int S, int N, int d, int H, int dt,
+                                 DevBuf& xb, DevBuf& stats, DevBuf& xlive, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf,
+                                 const AttnProbe& probe, bool probs_only, int save_slot, bool has_next, cudaStream_t st, void* rollout_qkv,
+                                 int live_row) {
+    const int64_t M = (int64_t)S * N;
+    float* sx1 = nullptr; float* next_sx0 = nullptr; void* sqkv = qkv.p; void* shpre = nullptr;
+    if (save_slot >= 0) {
+        // the residual stream itself hops through the save slots: slot 2l holds the input of ln_1 of layer l (written by the
+        // previous block's c_proj, or by the splice kernel for l = 0), slot 2l+1 the input of ln_2 (written by the out-projection)
+        sx1 = (float*)t_save_x.p + (int64_t)(2 * save_slot + 1) * M * d;
+        if (has_next) next_sx0 = (float*)t_save_x.p + (int64_t)(2 * save_slot + 2) * M * d;
+        sqkv = (uint8_t*)t_save_qkv.p + (int64_t)save_slot * M * 3 * d * esz;
+        shpre = (uint8_t*)t_save_h.p + (int64_t)save_slot * M * 4 * d * esz;
+    }
+    if (rollout_qkv) sqkv = rollout_qkv;
+    gemm_fold(xb.p, (const float*)stats.p, parts, b.wf_qkv, b.fb_qkv, b.fs_qkv, sqkv, nullptr, M, 3 * d, d, ACT_NONE, dt, st);
+    attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
+    if (probs_only) return;
+    if (live_row >= 0) {
+        // last block, dead-row form (see block_forward): the live rows leave the [S*N, d] stream here and continue as a compact
+        // [S, d] matrix; the out-projection reads row `live_row` of every sequence through its leading dimensions
+        const int64_t ld = (int64_t)N * d;
+        float* xl = (float*)xlive.p;
+        gemm_resid((const uint8_t*)attn.p + (int64_t)live_row * d * esz, ld, b.w_o, b.b_o, x + (int64_t)live_row * d, ld, xl, d, nullptr, nullptr,
+                   S, d, d, dt, st);
+        layernorm_fwd(xl, d, b.ln2_g, b.ln2_b, ln.p, dt, sx1, S, d, st); ++launches;
+        gemm(ln.p, b.w_fc, b.b_fc, hbuf.p, shpre, S, 4 * d, d, EPI_BF16, cfg.act, dt, st);
+        gemm(hbuf.p, b.w_proj, b.b_proj, xl, nullptr, S, d, 4 * d, EPI_F32_ADD, ACT_NONE, dt, st);
+        x = xl;
+        return;
+    }
+    float* x1 = sx1 ? sx1 : x;
+    gemm_resid(attn.p, 0, b.w_o, b.b_o, x, d, x1, d, xb.p, (float*)stats.p, M, d, d, dt, st);
+    parts = gemm_stats_parts(d);
+    gemm_fold(xb.p, (const float*)stats.p, parts, b.wf_fc, b.fb_fc, b.fs_fc, hbuf.p, shpre, M, 4 * d, d, cfg.act, dt, st);
+    float* x2 = next_sx0 ? next_sx0 : (save_slot >= 0 ? scratch : x1);
+    gemm_resid(hbuf.p, 0, b.w_proj, b.b_proj, x1, d, x2, d, xb.p, (float*)stats.p, M, d, 4 * d, dt, st);
+    x = x2;
 }
 
 // ---- image tower (row A4) ---------------------------------------------------------------------------
@@ -390,10 +468,19 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
         v_roll.ensure((size_t)2 * B * N * sizeof(float));
     }
 
+    const bool fused = use_fold(true);
+    if (fused) {
+        v_xb.ensure(M * d * esz);
+        v_stats.ensure((size_t)M * gemm_stats_parts(d) * 2 * sizeof(float));
+        v_xlive.ensure((size_t)B * d * sizeof(float));
+    }
     patchify(images, v_patches.p, vdt, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
     gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, vdt, st);
-    assemble_ln_pre((const float*)v_patch_out.p, cls_emb, pos_emb, ln_pre_g, ln_pre_b, (float*)v_x.p, B, N, d, st); ++launches;
-    bool ln_ready = false;
+    assemble_ln_pre((const float*)v_patch_out.p, cls_emb, pos_emb, ln_pre_g, ln_pre_b, (float*)v_x.p, B, N, d, st,
+                    fused ? v_xb.p : nullptr, fused ? (float*)v_stats.p : nullptr); ++launches;
+    float* xcur = (float*)v_x.p;                      // where the residual stream lives (fused path: may move to the compact live rows)
+    int64_t x_stride = (int64_t)N * d;                // distance between the CLS rows of consecutive images
+    int parts = 1;
     for (int l = 0; l < L; ++l) {
         AttnProbe probe;
         if (out_cls_rows) {
@@ -403,12 +490,17 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
         }
         if (l == L - 1 && dead_rows) probe.live_q_rows = 1;
         if (out_rollout) probe.lse_out = (float*)v_lse.p + (int64_t)l * B * H * N;
-        ln_ready = block_forward(vis[l], (float*)v_x.p, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st,
-                                 out_rollout ? (uint8_t*)v_roll_qkv.p + (int64_t)l * M * 3 * d * esz : nullptr,
-                                 (l == L - 1 && dead_rows) ? 0 : -1,                   // only the CLS row feeds ln_post
-                                 l + 1 < L ? &vis[l + 1] : nullptr, ln_ready);
+        void* roll_qkv = out_rollout ? (uint8_t*)v_roll_qkv.p + (int64_t)l * M * 3 * d * esz : nullptr;
+        const int live_row = (l == L - 1 && dead_rows) ? 0 : -1;                       // only the CLS row feeds ln_post
+        if (fused) {
+            block_forward_fused(vis[l], xcur, parts, (float*)v_x.p, B, N, d, H, vdt, v_xb, v_stats, v_xlive, v_ln, v_qkv, v_attn, v_h, probe,
+                                false, -1, l + 1 < L, st, roll_qkv, live_row);
+            if (live_row >= 0) x_stride = d;
+        } else {
+            block_forward(vis[l], xcur, B, N, d, H, vdt, v_ln, v_qkv, v_attn, v_h, probe, false, -1, st, roll_qkv, live_row);
+        }
     }
-    layernorm_fwd((const float*)v_x.p, (int64_t)N * d, ln_post_g, ln_post_b, v_pooled.p, vdt, nullptr, B, d, st); ++launches;
+    layernorm_fwd(xcur, x_stride, ln_post_g, ln_post_b, v_pooled.p, vdt, nullptr, B, d, st); ++launches;
     gemm(v_pooled.p, w_vproj, nullptr, out_feat, nullptr, B, E, d, EPI_F32, ACT_NONE, vdt, st);
     if (out_rollout) {
         // r_L = e_0;  r_{l} = 0.5 r_{l+1} + 0.5 r_{l+1}^T mean_h P_l;  out = r_0 without the CLS column.  At the last layer only
@@ -424,17 +516,18 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
 }
 
 // ---- text side (rows A2, A6-A10) ----------------------------------------------------------------------
-void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw,
-                          float* out_attr, float* out_text_feat, cudaStream_t st) {
+int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw,
+                             float* out_attr, float* out_text_feat, cudaStream_t st) {
     TC_CHECK(C >= 0 && P >= 1, "bad class count / prompt length");
     TC_CHECK(mode >= 0 && mode <= 2, "attribution mode must be 0 (literal), 1 (intended) or 2 (intended attribution pass only)");
     const bool attr_only = (mode == 2);
     if (attr_only) { mode = 1; TC_CHECK(!save, "the attribution-only pass keeps nothing for backward"); }
     saved.valid = false;
-    if (C == 0) return;
+    if (C == 0) return 0;
     const std::string miss = missing_weights();
     TC_CHECK(miss.empty(), "weights missing: %s", miss.c_str());
     const int D = cfg.text_width, H = cfg.text_heads, Lc = cfg.context_length, T = P + Lc, L = cfg.text_layers, E = cfg.embed_dim;
+    const bool fused = use_fold(false);
     const int64_t M = (int64_t)C * T;
     t_x.ensure(M * D * 4);
     t_ln.ensure(M * D * esz);
@@ -454,21 +547,43 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
         t_save_qkv.ensure((int64_t)L * M * 3 * D * esz);
         t_save_h.ensure((int64_t)L * M * 4 * D * esz);
     }
+    if (fused) {
+        t_xb.ensure(M * D * esz);
+        t_stats.ensure((size_t)M * gemm_stats_parts(D) * 2 * sizeof(float));
+        t_xlive.ensure((size_t)C * D * sizeof(float));
+    }
     float* x = (float*)t_x.p;
     const float* attr = nullptr;
+    // one pass of the text transformer over the prompts already spliced into `xp` (fused path: xp may be save slot 0)
+    auto run_blocks = [&](float* xp, bool attribution_pass, bool keep, float*& x_end, int64_t& pool_stride, int64_t& pool_offset) {
+        float* xc = xp;
+        int parts = 1;
+        pool_stride = T; pool_offset = T - 1;
+        if (fused) { row_stats_cast(xc, t_xb.p, tdt, (float*)t_stats.p, M, D, st); ++launches; }
+        for (int l = 0; l < L; ++l) {
+            AttnProbe probe;
+            const bool last = (l == L - 1);
+            if (attribution_pass && last) { probe.mode = PROBE_TEXT_COL; probe.out = (float*)t_probe.p; probe.P = P; }
+            // feature pass, last block: only position T-1 is pooled (model_wrapper.py:73) -> out-projection and MLP on C rows
+            const int live_row = (!attribution_pass && last && dead_rows) ? T - 1 : -1;
+            if (fused) {
+                block_forward_fused(txt[l], xc, parts, (float*)t_x.p, C, T, D, H, tdt, t_xb, t_stats, t_xlive, t_ln, t_qkv, t_attn, t_h, probe,
+                                    attribution_pass && last, keep ? l : -1, l + 1 < L, st, nullptr, live_row);
+                if (live_row >= 0) { pool_stride = 1; pool_offset = 0; }
+            } else {
+                block_forward(txt[l], xc, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, probe, attribution_pass && last, keep ? l : -1, st, nullptr,
+                              live_row);
+            }
+        }
+        x_end = xc;
+    };
+    float* x_end = nullptr; int64_t pool_stride = T, pool_offset = T - 1;
     if (mode == 1) {
         // attribution pass (rows A7/A8): un-adjusted prompt, probabilities of the last block only
         TC_CHECK(P <= 64, "prompt_len %d unsupported (<= 64)", P);
         t_probe.ensure((int64_t)C * H * P * 4);
         splice_prompts(ctx, tok, nullptr, 1, x, C, P, Lc, D, st); ++launches;
-        bool ln_ready = false;
-        for (int l = 0; l < L; ++l) {
-            AttnProbe probe;
-            const bool last = (l == L - 1);
-            if (last) { probe.mode = PROBE_TEXT_COL; probe.out = (float*)t_probe.p; probe.P = P; }
-            ln_ready = block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, probe, last, -1, st, nullptr, -1,
-                                     l + 1 < L ? &txt[l + 1] : nullptr, ln_ready);
-        }
+        run_blocks(x, true, false, x_end, pool_stride, pool_offset);
         attribution_reduce((const float*)t_probe.p, (float*)t_attr_raw.p, (float*)t_attr.p, C, H, P, st); ++launches;
         attr = (const float*)t_attr.p;
         if (out_attr_raw) TC_CUDA(cudaMemcpyAsync(out_attr_raw, t_attr_raw.p, (size_t)C * P * 4, cudaMemcpyDeviceToDevice, st));
@@ -478,21 +593,22 @@ void Engine::text_forward(const float* ctx, const float* tok, int C, int P, int 
         launch_pdl(fill_kernel, (unsigned)ceil_div(C, 256), 256, 0, st, out_attr, 1.0f, C);
         TC_LAUNCH_CHECK(); ++launches;
     }
-    if (attr_only) return;          // 'gate' / 'residual' adjustors: the host applies its small network to out_attr (prompt_adjustor.py:38-44)
-    // feature pass (rows A9/A10)
-    splice_prompts(ctx, tok, attr, PA, x, C, P, Lc, D, st); ++launches;
-    bool ln_ready2 = false;
-    for (int l = 0; l < L; ++l) {
-        AttnProbe none;
-        // last block: only position T-1 is pooled (model_wrapper.py:73) -> out-projection and MLP on C rows
-        ln_ready2 = block_forward(txt[l], x, C, T, D, H, tdt, t_ln, t_qkv, t_attn, t_h, none, false, save ? l : -1, st, nullptr,
-                                  (l == L - 1 && dead_rows) ? T - 1 : -1, l + 1 < L ? &txt[l + 1] : nullptr, ln_ready2);
-    }
-    gather_rows(x, t_pooled.p, tdt, C, T, T - 1, D, st); ++launches;
+    if (attr_only) return 0;        // 'gate' / 'residual' adjustors: the host applies its small network to out_attr (prompt_adjustor.py:38-44)
+    // feature pass (rows A9/A10).  Fused path with save: the spliced prompts are written straight into save slot 0 (the input of
+    // ln_1 of layer 0) and the residual stream hops through the save slots from there.
+    float* xp = (fused && save) ? (float*)t_save_x.p : x;
+    splice_prompts(ctx, tok, attr, PA, xp, C, P, Lc, D, st); ++launches;
+    run_blocks(xp, false, save, x_end, pool_stride, pool_offset);
+    gather_rows(x_end, t_pooled.p, tdt, C, pool_stride, pool_offset, D, st); ++launches;
     gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, tdt, st);
     l2norm_fwd((const float*)t_feat.p, (float*)t_tfeat.p, (float*)t_inv_norm.p, C, E, st); ++launches;
     if (out_text_feat) TC_CUDA(cudaMemcpyAsync(out_text_feat, t_tfeat.p, (size_t)C * E * 4, cudaMemcpyDeviceToDevice, st));
-    if (save) { saved.valid = true; saved.C = C; saved.P = P; saved.T = T; saved.PA = PA; saved.has_attr = (mode == 1); saved.dead_last = dead_rows; }
+    if (save) {
+        saved.valid = true; saved.C = C; saved.P = P; saved.T = T; saved.PA = PA; saved.has_attr = (mode == 1); saved.dead_last = dead_rows;
+        saved.token = ++forward_seq;
+        return saved.token;
+    }
+    return 0;
 }
 
 // ---- standard CLIP text path (CLIPWrapper.encode_text, clip_wrapper.py:49-51; never called by FullModel) ---------------
@@ -526,8 +642,13 @@ void Engine::encode_text(const int64_t* ids, int S, float* out_feat, cudaStream_
 }
 
 // ---- backward to ctx (row A13) ---------------------------------------------------------------------------
-void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st) {
-    TC_CHECK(saved.valid, "tapclip_text_backward needs a preceding tapclip_text_forward(save_for_backward=1)");
+void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st, int64_t token, int C_expect, int P_expect) {
+    TC_CHECK(saved.valid, "tapclip_text_backward needs a preceding tapclip_text_forward(save_for_backward=1) whose activations are still "
+                          "held (a later text_forward / encode_text on this handle replaces them)");
+    TC_CHECK(token == 0 || token == saved.token, "stale backward: the activations of forward #%lld were overwritten by forward #%lld on this handle "
+             "(one saved forward per handle: run backward before the next forward, or use one CLIPWrapper per model)", (long long)token, (long long)saved.token);
+    TC_CHECK((C_expect <= 0 || C_expect == saved.C) && (P_expect <= 0 || P_expect == saved.P), "backward for C=%d, P=%d but the saved forward had C=%d, P=%d",
+             C_expect, P_expect, saved.C, saved.P);
     const int C = saved.C, P = saved.P, T = saved.T;
     const int D = cfg.text_width, H = cfg.text_heads, L = cfg.text_layers, E = cfg.embed_dim;
     const int64_t M = (int64_t)C * T;

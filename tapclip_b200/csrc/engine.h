@@ -23,6 +23,11 @@ struct BlockWeights {
     float *b_qkv = nullptr, *b_o = nullptr, *b_fc = nullptr, *b_proj = nullptr;
     void *w_qkv = nullptr, *w_o = nullptr, *w_fc = nullptr, *w_proj = nullptr;        // [N,K], activation type
     void *wt_qkv = nullptr, *wt_o = nullptr, *wt_fc = nullptr, *wt_proj = nullptr;    // [K,N] dgrad operands (text tower)
+    // LayerNorm folded into the consumer GEMM (16-bit modes; gemm.h GemmArgs::stats_in): W' = W diag(gamma) in the operand type,
+    // s[n] = sum_k W'[n,k], b' = b + W beta; built from fp32 copies of W as soon as W, b, gamma and beta of a group are loaded
+    float *f32_qkv = nullptr, *f32_fc = nullptr;
+    void *wf_qkv = nullptr, *wf_fc = nullptr;
+    float *fs_qkv = nullptr, *fb_qkv = nullptr, *fs_fc = nullptr, *fb_fc = nullptr;
 };
 
 struct Engine {
@@ -44,10 +49,14 @@ struct Engine {
     // workspaces (grow-only)
     DevBuf v_patches, v_patch_out, v_x, v_ln, v_qkv, v_attn, v_h, v_pooled, v_roll_qkv, v_lse, v_roll;
     DevBuf t_x, t_ln, t_qkv, t_attn, t_h, t_pooled, t_feat, t_tfeat, t_inv_norm, t_probe, t_attr, t_attr_raw;
+    DevBuf v_xb, v_stats, v_xlive, t_xb, t_stats, t_xlive;      // folded-LayerNorm path: 16-bit residual copy, row statistics, live rows of the last block
     DevBuf t_save_x, t_save_qkv, t_save_h;
     DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
     DevBuf s_rows, s_cls, e_eot, e_pool;
-    struct { bool valid = false; int C = 0, P = 0, T = 0, PA = 1; bool has_attr = false; bool dead_last = false; } saved;
+    // activations kept by text_forward(save) for text_backward; `token` identifies the forward that wrote them (a later
+    // text_forward / encode_text on this handle overwrites the slot: its backward must then fail, not use the wrong tensors)
+    struct { bool valid = false; int C = 0, P = 0, T = 0, PA = 1; bool has_attr = false; bool dead_last = false; int64_t token = 0; } saved;
+    int64_t forward_seq = 0;
 
     // optional per-launch CUDA-event timing of the tensor-core kernels (bench.py roofline numbers)
     struct ProfRec { cudaEvent_t a, b; double flops; int kind; int64_t M, N, K; int epi; };
@@ -73,18 +82,30 @@ struct Engine {
               int act, int dt, cudaStream_t st, int aux_dt = DT_BF16, int64_t lda = 0, int64_t ldo = 0);   // lda/ldo 0 = dense
     void attn_fwd(const void* qkv, void* out, int dt, int S, int N, int H, const AttnProbe& probe, cudaStream_t st);
     void attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int N, int H, cudaStream_t st);
-    bool block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
+    void block_forward(const BlockWeights& b, float* x, int S, int N, int d, int H, int dt, DevBuf& ln, DevBuf& qkv, DevBuf& attn,
                        DevBuf& hbuf, const AttnProbe& probe, bool probs_only, int save_slot, cudaStream_t st, void* rollout_qkv = nullptr,
-                       int live_row = -1, const BlockWeights* next = nullptr, bool ln1_ready = false);
-    // residual GEMM with the following LayerNorm fused into its epilogue (gemm_ln.cu) when the shape allows it
-    bool gemm_ln(const void* a, const void* w, const float* bias, const float* gamma, const float* beta, float* x, void* ln_out,
-                 float* x_copy, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st);
-    // 0 = LayerNorm as its own kernel; 1 = fused into the residual GEMMs of the text tower; 2 = of both towers (TAPCLIP_FUSE_LN)
-    int fuse_ln = getenv("TAPCLIP_FUSE_LN") ? atoi(getenv("TAPCLIP_FUSE_LN")) : 0;
+                       int live_row = -1);
+    // The pre-LN block without LayerNorm kernels (north-star "pre-LN epilogue", gemm.h): the residual GEMMs (EPI_F32_RESID) emit the
+    // updated rows in 16 bits plus per-row (sum, sum of squares); the QKV / c_fc GEMMs consume them with LayerNorm folded into the
+    // weights.  `x` follows the residual stream (it hops through the save slots when save_slot >= 0; after a last block with
+    // live_row >= 0 it points at the compact [S, d] live rows); `parts` = statistics partials per row currently in `stats`.
+    void block_forward_fused(const BlockWeights& b, float*& x, int& parts, float* scratch, int S, int N, int d, int H, int dt, DevBuf& xb,
+                             DevBuf& stats, DevBuf& xlive, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf, const AttnProbe& probe,
+                             bool probs_only, int save_slot, bool has_next, cudaStream_t st, void* rollout_qkv = nullptr, int live_row = -1);
+    void gemm_fold(const void* xb, const float* stats, int parts, const void* wf, const float* fb, const float* fs, void* out, void* out_pre,
+                   int64_t M, int64_t N, int64_t K, int act, int dt, cudaStream_t st);
+    void gemm_resid(const void* a, int64_t lda, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out, int64_t ldo,
+                    void* xb, float* stats, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st);
+    void fold_group(BlockWeights& b, int group, const std::string& prefix, int d, int dt, cudaStream_t st);
+    // TAPCLIP_FUSE_LN: 0 = LayerNorm as its own kernel; 1 = folded into the GEMMs of the text tower; 2 = of both towers (default)
+    int fuse_ln = getenv("TAPCLIP_FUSE_LN") ? atoi(getenv("TAPCLIP_FUSE_LN")) : 2;
+    bool use_fold(bool vision) const { return cfg.dtype != DT_F32 && fuse_ln >= (vision ? 2 : 1); }
     void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, float* out_rollout, cudaStream_t st);
-    void text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
-                      float* out_text_feat, cudaStream_t st);
-    void text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st);
+    // returns the token of the saved activations (0 when nothing was saved)
+    int64_t text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
+                         float* out_text_feat, cudaStream_t st);
+    // token: as returned by the text_forward whose activations are to be used (0 = whatever was saved last); C, P: checked when > 0
+    void text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st, int64_t token = 0, int C = 0, int P = 0);
     void encode_text(const int64_t* ids, int S, float* out_feat, cudaStream_t st);
     void logits(const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels, int B, int C,
                 float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss, float* out_dlogits, cudaStream_t st);

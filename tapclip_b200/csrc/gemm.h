@@ -11,6 +11,10 @@ enum Epi : int {
     EPI_F32_ADD = 2,   // out (f32) += acc + bias        (residual stream update)
     EPI_BF16_ACTGRAD = 3,  // out (bf16) = (acc + bias) * act'(out_pre)   (dgrad through the MLP activation; out_pre is READ:
                            // the saved 16-bit pre-activations, type aux_dt, same [M,N] layout and leading dimension as out)
+    EPI_F32_RESID = 4,     // out (f32, ldo) = resid_in (f32, ld_in) + acc + bias: the residual update `x = x + f(...)` of a pre-LN
+                           // block, out of place (or in place: resid_in == out).  Optionally also emits what the NEXT LayerNorm
+                           // needs: xb = the updated rows in the 16-bit operand type (dense [M,N]) and stats_out = per-row partial
+                           // (sum, sum of squares) of the updated rows, one pair per (n-tile, epilogue-warp parity) -- see `fold`
 };
 
 struct GemmArgs {
@@ -26,7 +30,20 @@ struct GemmArgs {
     int block_n = 0;           // 0 = choose; 128 / 256 = 128 x block_n single-CTA tiles; 512 = 2-CTA pairs, 256 x 256 tiles
     int aux_dt = DT_BF16;      // EPI_BF16_ACTGRAD: type of the pre-activations behind out_pre (DT_BF16 or DT_F16)
     int dt = DT_BF16;          // tcgen05 path: 16-bit type of A, W and of the EPI_BF16 output (DT_BF16 or DT_F16)
+    // EPI_F32_RESID
+    const float* resid_in = nullptr;   // [M, N] fp32, leading dimension ld_in
+    int64_t ld_in = 0;
+    void* xb = nullptr;                // optional: 16-bit copy (type dt) of the updated rows, dense [M, N]
+    float* stats_out = nullptr;        // optional: [M][gemm_stats_parts(N)][2] partial (sum, sum of squares) of the updated rows
+    // LayerNorm folded into the GEMM (EPI_BF16 only): A holds the UN-normalised rows x in 16 bits, W the gamma-scaled weight
+    // W' = W * diag(gamma), bias the folded bias b' = b + W beta, fold_s[n] = sum_k W'[n,k]; with the row statistics
+    // (mean, rstd) recovered from stats_in the epilogue forms  LN(x) W^T + b = rstd * (x W'^T - mean * s) + b'.
+    const float* stats_in = nullptr;   // [M][stats_parts][2] partial (sum, sum of squares) over the K elements of each row of A
+    int stats_parts = 0;
+    const float* fold_s = nullptr;     // [N]
 };
+// number of (sum, sum of squares) partials per row an EPI_F32_RESID GEMM with N output columns writes (2 per n-tile)
+int gemm_stats_parts(int64_t N);
 
 // Cached TMA descriptor of a 2-D row-major tensor [rows, cols] (leading dimension ld, elements of elem_bytes), 128B-swizzled
 // boxes of box_rows x box_cols (box_cols * elem_bytes must be 128).  Shared by the GEMM and the tcgen05 attention kernel.
@@ -36,23 +53,6 @@ CUtensorMap make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, i
 
 // tcgen05/TMEM/TMA path: A and W bf16 (or fp16, g.dt); out = same 16-bit type (EPI_BF16) or f32
 void gemm_tc(const GemmArgs& g, cudaStream_t stream);
-
-// Residual GEMM with fused LayerNorm epilogue (gemm_ln.cu):  x[M,N] += A[M,K] . W[N,K]^T + bias;  ln_out = LayerNorm(x; gamma, beta)
-// in the 16-bit type `dt` (dense [M,N]);  x_copy (optional, dense fp32 [M,N]) = the updated x.  N = 512 / 768 / 1024.
-struct GemmLnArgs {
-    const void* a = nullptr;       // [M, K] 16-bit, dense
-    const void* w = nullptr;       // [N, K] 16-bit, dense
-    const float* bias = nullptr;   // [N] or null
-    const float* gamma = nullptr;  // [N] LayerNorm weight
-    const float* beta = nullptr;   // [N] LayerNorm bias
-    float* x = nullptr;            // [M, N] fp32 residual stream, leading dimension ldx, updated in place
-    void* ln_out = nullptr;        // [M, N] 16-bit
-    float* x_copy = nullptr;
-    int64_t M = 0, N = 0, K = 0, ldx = 0;
-    int dt = DT_BF16;
-};
-bool gemm_resid_ln_supported(int64_t N, int64_t K, int dt);
-void gemm_resid_ln(const GemmLnArgs& g, cudaStream_t stream);
 
 // fp32 SIMT path for the fp32 parity mode: A, W, out all f32; EPI_BF16 means "store in the activation
 // type" (f32 here) with the optional activation / pre-activation copy

@@ -13,6 +13,18 @@
 // Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  M/N/K tails are handled by TMA zero-fill on loads and clipping on stores.
 //
+// Tile order: static striding (tile = cta, cta + grid, ...) or, with a scheduler slot (GemmExtra::sched), DYNAMIC: the
+// producer lane draws tile indices from a global atomic counter and hands them to the MMA / epilogue warps through a
+// 4-deep shared-memory ring.  When another stream's kernels hold part of the SMs (the text tower runs beside the image
+// tower), late-starting CTAs then simply draw fewer tiles instead of leaving a static share for the end.
+//
+// LayerNorm never runs as its own kernel around these GEMMs (north-star "pre-LN epilogue"):
+//   EPI_F32_RESID  the residual update x_new = x_old + A W^T + b also writes x_new in the 16-bit operand type and per-row
+//                  partial (sum, sum of squares) of x_new (one pair per n-tile and epilogue-warp parity: written, never
+//                  accumulated, so there is no zeroing pass and the result is deterministic);
+//   FOLD           the consumer GEMM multiplies the UN-normalised 16-bit rows with W' = W diag(gamma) and applies
+//                  LN(x) W^T + b = rstd (x W'^T - mean s) + b'  per row in its epilogue (s = row sums of W', b' = b + W beta).
+//
 // Two tile shapes:
 //   CTA2 = false  cta_group::1, UMMA 128 x BLOCK_N x 16, one CTA per tile (48 KB of operands per k-block).
 //   CTA2 = true   cta_group::2, UMMA 256 x BLOCK_N x 16 issued by the leader of a 2-CTA cluster: each CTA holds its
@@ -43,8 +55,34 @@ template <int BLOCK_N, bool CTA2> struct Cfg {
     static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
     static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;            // 4 (48 KB), 6 (32 KB), 8 (24 KB)
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/ + 1024 /*align slack*/;
+    // barriers (ring, TMEM, scheduler ring) + scheduler tiles + TMEM slot: 256 B; bias tile and fold_s tile: 2 x BLOCK_N floats
+    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 2 * BLOCK_N * 4;
+    // the dynamic shared memory window starts 1024-byte aligned in practice (no static shared memory in this kernel); 768 B of
+    // slack cover any base that is at least 256-byte aligned, and the kernel traps if the carve-up would not fit
+    static constexpr int SMEM_BYTES = SMEM_USED + 768;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert((2 * STAGES + 4 + 2 * 4) * 8 + 4 * 4 + 4 <= 256, "barrier region");
 };
+constexpr int SCHED_DEPTH = 4;
+
+// per-launch extras of the residual / folded-LayerNorm epilogues and of the dynamic tile scheduler
+struct GemmExtra {
+    const float* resid_in; int ld_in;      // EPI_F32_RESID
+    void* xb; float* stats_out;
+    const float* stats_in; int stats_parts; const float* fold_s;      // FOLD
+    int* sched;                            // {next tile, finished CTAs} or null (static tile order)
+};
+
+// consumer side of the scheduler ring (whole warp): returns the next tile index (>= num_tiles: no more work)
+__device__ __forceinline__ int sched_fetch(uint64_t* full, uint64_t* empty, const int* ring, int& slot, uint32_t& phase) {
+    mbar_wait(&full[slot], phase);
+    int t = *reinterpret_cast<const volatile int*>(&ring[slot]);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    __syncwarp();
+    if (elect_one()) mbar_arrive(&empty[slot]);
+    if (++slot == SCHED_DEPTH) { slot = 0; phase ^= 1; }
+    return t;
+}
 
 // UMMA shared-memory descriptor: K-major operand, 128B swizzle, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -74,16 +112,18 @@ __device__ __forceinline__ uint32_t mul_act_grad(uint32_t x, uint32_t h, int h_f
     return pack2<T16>(xf.x * act_bwd_fast<ACT>(hf.x), xf.y * act_bwd_fast<ACT>(hf.y));
 }
 
-template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16, bool CTA2>
+template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16, bool CTA2, bool FOLD>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                void* out, void* out_pre, int ldo,
-               const float* __restrict__ bias, int M, int N, int K, int dbg, int aux_f16) {
+               const float* __restrict__ bias, int M, int N, int K, int dbg, int aux_f16, const GemmExtra ex) {
     using C = Cfg<BLOCK_N, CTA2>;
     constexpr bool ACTGRAD = (EPI == EPI_BF16_ACTGRAD);      // out = (acc + bias) * act'(aux), aux = out_pre pointer, same layout as out
+    constexpr bool RESID = (EPI == EPI_F32_RESID);           // out = resid_in + acc + bias (+ 16-bit copy + row statistics)
     constexpr bool OUT16 = (EPI == EPI_BF16) || ACTGRAD;
+    static_assert(!FOLD || EPI == EPI_BF16, "the folded-LayerNorm epilogue exists for 16-bit outputs only");
     using T16 = typename std::conditional<F16, f16, bf16>::type;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + C::STAGES * STAGE_A_BYTES;
@@ -93,8 +133,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* empty_bar = bars + C::STAGES;
     uint64_t* tmem_full = bars + 2 * C::STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* bias_s = reinterpret_cast<float*>(smem_epi + EPI_BYTES + 256);      // bias of the current tile, shared by the 4 epilogue warps
+    uint64_t* sched_full = tmem_empty + 2;
+    uint64_t* sched_empty = sched_full + SCHED_DEPTH;
+    int* sched_tile = reinterpret_cast<int*>(sched_empty + SCHED_DEPTH);
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(sched_tile + SCHED_DEPTH);
+    float* bias_s = reinterpret_cast<float*>(smem_epi + EPI_BYTES + 256);      // bias of the current tile, shared by the epilogue warps
+    float* fold_s_s = bias_s + BLOCK_N;                                        // FOLD: row sums of W' for the tile's columns
 
     // warp index (and below the TMEM base) come out of shuffles so that ptxas knows they are warp-uniform
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -106,12 +150,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int m_tiles = (M + UNIT_M - 1) / UNIT_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = m_tiles * n_tiles;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const bool dyn = !CTA2 && ex.sched != nullptr;            // dynamic tile order (kernel parameter: warp-uniform)
 
     if (warp == 0 && lane == 0) {
+        uint32_t dyn_bytes;
+        asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+        if ((uint32_t)(smem - smem_raw) + (uint32_t)C::SMEM_USED > dyn_bytes) {
+            printf("tapclip: gemm_tc_kernel shared-memory carve-up does not fit (base offset %u)\n", (uint32_t)(smem - smem_raw));
+            __trap();
+        }
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int i = 0; i < C::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CTA2 ? 2 * EPI_WARPS : EPI_WARPS); }
+        for (int i = 0; i < SCHED_DEPTH; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 1 + EPI_WARPS); }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
@@ -130,10 +182,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     pdl_wait();
 
     if (warp == 0) {
-        // ================================ TMA producer ================================
+        // ================================ TMA producer (+ tile scheduler) ================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = unit; tile < num_tiles; tile += num_units) {
+            int pslot = 0; uint32_t pphase = 0;
+            int tile = unit;
+            while (true) {
+                if (dyn) {                                  // hand the tile (or the end marker) to the MMA and epilogue warps
+                    mbar_wait(&sched_empty[pslot], pphase ^ 1);
+                    *reinterpret_cast<volatile int*>(&sched_tile[pslot]) = tile;
+                    mbar_arrive(&sched_full[pslot]);
+                    if (++pslot == SCHED_DEPTH) { pslot = 0; pphase ^= 1; }
+                }
+                if (tile >= num_tiles) break;
+                // the next tile is drawn now: the atomic's round trip hides behind this tile's loads
+                const int next = dyn ? num_units + atomicAdd(ex.sched, 1) : tile + num_units;
                 const int m0 = (tile / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M;
                 const int n0 = (tile % n_tiles) * BLOCK_N + (int)cta_rank * (CTA2 ? C::B_ROWS : 0);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -151,6 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+                tile = next;
             }
         }
     } else if (warp == 1) {
@@ -160,7 +224,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             constexpr uint32_t idesc = make_idesc(UNIT_M, BLOCK_N, F16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = unit; tile < num_tiles; tile += num_units) {
+            int cslot = 0; uint32_t cphase = 0;
+            int tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : unit;
+            while (tile < num_tiles) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -177,6 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 umma_commit_elect(&tmem_full[acc]);                 // accumulator ready for the epilogue warps
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : tile + num_units;
             }
         } else if (lane == 0 && cta_rank == 0) {
             constexpr uint32_t idesc = make_idesc(UNIT_M, BLOCK_N, F16);
@@ -204,7 +271,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ================================ epilogue warps ==============================
         // TMEM -> registers (one accumulator row per thread) -> bias/activation -> XOR-swizzled smem transpose ->
         // coalesced 16-byte global stores (each store instruction covers 4 rows x 128 B).  Stores are fire-and-forget:
-        // nothing in this loop waits on the memory system except the tcgen05.ld itself.
+        // nothing in this loop waits on the memory system except the tcgen05.ld itself (and, for EPI_F32_RESID, the old
+        // residual values, requested in the store mapping before the accumulator is read).
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int ew = warp - 2;
         const int chunk_par = ew >> 2;                       // this warp handles the chunks with (c & 1) == chunk_par
@@ -213,7 +281,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const uint32_t sw = (uint32_t)(lane & 7);
         const int rd_row = lane >> 3, rd_ch = lane & 7;      // read-back mapping: 8 lanes cover one 128-byte row
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = unit; tile < num_tiles; tile += num_units) {
+        int cslot = 0; uint32_t cphase = 0;
+        int tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : unit;
+        while (tile < num_tiles) {
             const int m0 = (tile / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
             if (bias != nullptr) {
                 // stage this tile's bias in smem while the MMAs of the tile are still running (a global load per
@@ -225,19 +295,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (col < N) b = __ldg(reinterpret_cast<const float4*>(bias + col));
                     *reinterpret_cast<float4*>(bias_s + et * 4) = b;
+                } else if (FOLD && et < BLOCK_N / 2) {
+                    const int e2 = et - BLOCK_N / 4, col = n0 + e2 * 4;
+                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (col < N) b = __ldg(reinterpret_cast<const float4*>(ex.fold_s + col));
+                    *reinterpret_cast<float4*>(fold_s_s + e2 * 4) = b;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            }
+            const int row0 = m0 + q * 32;
+            // FOLD: this thread's row statistics -> out = fa * acc + (fb * s[n] + b'[n]),  fa = rstd, fb = -mean * rstd
+            float fa = 1.f, fb = 0.f;
+            if constexpr (FOLD) {
+                const int row = row0 + lane;
+                float s1 = 0.f, s2 = 0.f;
+                if (row < M) {
+                    const float2* sp = reinterpret_cast<const float2*>(ex.stats_in) + (int64_t)row * ex.stats_parts;
+                    for (int p = 0; p < ex.stats_parts; ++p) { const float2 t = sp[p]; s1 += t.x; s2 += t.y; }
+                }
+                const float inv_k = 1.0f / (float)K;
+                const float mean = s1 * inv_k;
+                fa = rsqrtf(fmaxf(s2 * inv_k - mean * mean, 0.f) + 1e-5f);
+                fb = -mean * fa;
+            }
+            [[maybe_unused]] float rs[8], rq[8];             // RESID: (sum, sum of squares) of this warp's columns, rows it*4 + rd_row
+            if constexpr (RESID) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) { rs[it] = 0.f; rq[it] = 0.f; }
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
-            const int row0 = m0 + q * 32;
             constexpr int CH = OUT16 ? 64 : 32;  // columns per 128-byte staging row
             constexpr int OUT_ESZ = OUT16 ? 2 : 4;
             constexpr int NCHUNK = BLOCK_N / CH;
             constexpr int LAST_MINE = NCHUNK - 2;            // last chunk index (before adding chunk_par) of each warp
 #pragma unroll 1
             for (int c = chunk_par; c < NCHUNK; c += 2) {
+                const int col0 = n0 + c * CH;
+                const int gcol = col0 + rd_ch * (16 / OUT_ESZ);
+                [[maybe_unused]] float4 xo[8];               // RESID: old residual values in the store mapping
+                if constexpr (RESID) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + rd_row;
+                        xo[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row0 + r < M && gcol < N)
+                            xo[it] = *reinterpret_cast<const float4*>(ex.resid_in + (int64_t)(row0 + r) * ex.ld_in + gcol);
+                    }
+                }
                 float v[CH];
                 {
                     uint32_t r0[32];
@@ -259,8 +365,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     __syncwarp();
                     if (lane == 0) { if constexpr (CTA2) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0)); else mbar_arrive(&tmem_empty[acc]); }
                 }
-                const int col0 = n0 + c * CH;
-                if (bias != nullptr) {
+                if constexpr (FOLD) {
+#pragma unroll
+                    for (int j = 0; j < CH; j += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c * CH + j);   // smem broadcast
+                        const float4 s = *reinterpret_cast<const float4*>(fold_s_s + c * CH + j);
+                        v[j] = fmaf(fa, v[j], fmaf(fb, s.x, b.x)); v[j + 1] = fmaf(fa, v[j + 1], fmaf(fb, s.y, b.y));
+                        v[j + 2] = fmaf(fa, v[j + 2], fmaf(fb, s.z, b.z)); v[j + 3] = fmaf(fa, v[j + 3], fmaf(fb, s.w, b.w));
+                    }
+                } else if (bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < CH; j += 4) {
                         const float4 b = *reinterpret_cast<const float4*>(bias_s + c * CH + j);   // smem broadcast
@@ -309,9 +422,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     __syncwarp();
                     // staging -> global: lane (rd_row, rd_ch) moves 16 bytes; 8 lanes = one full 128-byte row segment
                     uint8_t* gbase = reinterpret_cast<uint8_t*>(is_pre ? out_pre : out);
-                    const int gcol = col0 + rd_ch * (16 / OUT_ESZ);
                     if (dbg != 1) {
-                        if constexpr (EPI == EPI_F32_ADD) {
+                        if constexpr (RESID) {
+                            // x_new = x_old + tile: plain store of the fp32 row, 8-byte store of its 16-bit copy, and the row's
+                            // (sum, sum of squares) over this chunk reduced across the 8 lanes that share the row
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int r = it * 4 + rd_row;
+                                float a0, a1, a2, a3;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                                             : "r"(sb + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
+                                float ps = 0.f, pq = 0.f;
+                                if (row0 + r < M && gcol < N) {
+                                    a0 += xo[it].x; a1 += xo[it].y; a2 += xo[it].z; a3 += xo[it].w;
+                                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + ((int64_t)(row0 + r) * ldo + gcol) * 4),
+                                                 "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+                                    if (ex.xb != nullptr)
+                                        asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint8_t*>(ex.xb) + ((int64_t)(row0 + r) * N + gcol) * 2),
+                                                     "r"(pack2<T16>(a0, a1)), "r"(pack2<T16>(a2, a3)) : "memory");
+                                    ps = (a0 + a1) + (a2 + a3);
+                                    pq = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                                }
+                                ps += __shfl_xor_sync(0xffffffffu, ps, 1); pq += __shfl_xor_sync(0xffffffffu, pq, 1);
+                                ps += __shfl_xor_sync(0xffffffffu, ps, 2); pq += __shfl_xor_sync(0xffffffffu, pq, 2);
+                                ps += __shfl_xor_sync(0xffffffffu, ps, 4); pq += __shfl_xor_sync(0xffffffffu, pq, 4);
+                                rs[it] += ps; rq[it] += pq;
+                            }
+                        } else if constexpr (EPI == EPI_F32_ADD) {
                             // residual update x += tile as fire-and-forget vector reductions (measured faster than a plain
                             // read-modify-write: 37 vs 54 us on the 25216x768x768 out-projection); every element has exactly
                             // one contributor, so the result is deterministic
@@ -344,7 +481,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     }
                 }
             }
+            if constexpr (RESID) {
+                // one (sum, sum of squares) pair per row, n-tile and warp parity: every slot has exactly one writer
+                if (ex.stats_out != nullptr && rd_ch == 0) {
+                    const int parts = 2 * n_tiles, part = 2 * (tile % n_tiles) + chunk_par;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row0 + it * 4 + rd_row;
+                        if (row < M) reinterpret_cast<float2*>(ex.stats_out)[(int64_t)row * parts + part] = make_float2(rs[it], rq[it]);
+                    }
+                }
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : tile + num_units;
         }
     }
 
@@ -355,6 +504,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 1) {
         if constexpr (CTA2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
         else tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+    if (dyn && threadIdx.x == 0) {
+        // the last CTA to leave re-arms the scheduler slot, so a captured launch can be replayed
+        __threadfence();
+        if (atomicAdd(ex.sched + 1, 1) == (int)gridDim.x - 1) { ex.sched[0] = 0; ex.sched[1] = 0; }
     }
 }
 
@@ -422,33 +576,62 @@ CUtensorMap encode_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes,
 
 namespace {
 
-int g_num_sms = 0;
-// TAPCLIP_GEMM_DEBUG (measurement only; results are WRONG when set): 1 = skip the epilogue's TMA stores, 2 = skip the epilogue body
+// per-device launch state (a process may drive several GPUs): SM count and the ring of scheduler slots
+struct DeviceState {
+    int num_sms = 0;
+    int* sched = nullptr;          // SCHED_SLOTS x {next tile, finished CTAs}; every slot re-arms itself (see the kernel's last lines)
+    uint32_t seq = 0;
+};
+constexpr int SCHED_SLOTS = 4096;
+DeviceState& device_state() {
+    static DeviceState st[64];
+    int dev;
+    TC_CUDA(cudaGetDevice(&dev));
+    TC_CHECK(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    DeviceState& d = st[dev];
+    if (d.num_sms == 0) TC_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    return d;
+}
+// TAPCLIP_GEMM_DEBUG (measurement only; results are WRONG when set): 1 = skip the epilogue's global stores, 2 = skip the epilogue body
 int g_debug = getenv("TAPCLIP_GEMM_DEBUG") ? atoi(getenv("TAPCLIP_GEMM_DEBUG")) : 0;
+// TAPCLIP_GEMM_SCHED: 1 = dynamic tile order (atomic counter), 0 = static striding
+int g_dynamic = getenv("TAPCLIP_GEMM_SCHED") ? atoi(getenv("TAPCLIP_GEMM_SCHED")) : 1;
 
-template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16, bool CTA2>
+int choose_block_n(int64_t N) { return (N % 256 == 0) ? 256 : 128; }
+
+template <int BLOCK_N, int EPI, int ACT, bool STORE_PRE, bool F16, bool CTA2, bool FOLD = false>
 void launch(const GemmArgs& g, cudaStream_t stream) {
     using C = Cfg<BLOCK_N, CTA2>;
-    auto kern = gemm_tc_kernel<BLOCK_N, EPI, ACT, STORE_PRE, F16, CTA2>;
+    auto kern = gemm_tc_kernel<BLOCK_N, EPI, ACT, STORE_PRE, F16, CTA2, FOLD>;
     constexpr CUtensorMapDataType DT16 = F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    static bool configured = false;
-    if (!configured) {
+    DeviceState& ds = device_state();
+    static bool configured[64] = {};
+    int dev;
+    TC_CUDA(cudaGetDevice(&dev));
+    if (!configured[dev]) {
         TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
-    if (g_num_sms == 0) {
-        int dev;
-        TC_CUDA(cudaGetDevice(&dev));
-        TC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        configured[dev] = true;
     }
     const CUtensorMap& ta = make_tmap(g.a, DT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K);
     const CUtensorMap& tb = make_tmap(g.w, DT16, 2, g.N, g.K, g.ldw, C::B_ROWS, BLOCK_K);
     const int out_esz = (EPI == EPI_BF16 || EPI == EPI_BF16_ACTGRAD) ? 2 : 4;
     TC_CHECK((reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && (g.ldo * out_esz) % 16 == 0, "GEMM output must be 16-byte aligned with a 16-byte row pitch");
     if (STORE_PRE || EPI == EPI_BF16_ACTGRAD) TC_CHECK((reinterpret_cast<uintptr_t>(g.out_pre) & 15) == 0, "GEMM pre-activation output must be 16-byte aligned");
+    GemmExtra ex = {};
+    if (EPI == EPI_F32_RESID) {
+        TC_CHECK(g.resid_in != nullptr && (reinterpret_cast<uintptr_t>(g.resid_in) & 15) == 0 && g.ld_in % 4 == 0, "residual input must be 16-byte aligned with a 16-byte row pitch");
+        TC_CHECK((reinterpret_cast<uintptr_t>(g.xb) & 7) == 0 && (reinterpret_cast<uintptr_t>(g.stats_out) & 7) == 0, "xb / stats_out must be 8-byte aligned");
+        ex.resid_in = g.resid_in; ex.ld_in = (int)g.ld_in; ex.xb = g.xb; ex.stats_out = g.stats_out;
+    }
+    if (FOLD) {
+        TC_CHECK(g.stats_in != nullptr && g.stats_parts >= 1 && g.fold_s != nullptr && g.bias != nullptr, "folded-LayerNorm GEMM needs stats_in, fold_s and the folded bias");
+        TC_CHECK((reinterpret_cast<uintptr_t>(g.stats_in) & 7) == 0 && (reinterpret_cast<uintptr_t>(g.fold_s) & 15) == 0, "stats_in / fold_s alignment");
+        ex.stats_in = g.stats_in; ex.stats_parts = g.stats_parts; ex.fold_s = g.fold_s;
+    }
+    if (g.bias) TC_CHECK((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "bias must be 16-byte aligned");
     if (CTA2) {
         const int64_t tiles = ceil_div(g.M, 2 * BLOCK_M) * ceil_div(g.N, BLOCK_N);
-        const int clusters = (int)std::min<int64_t>(tiles, g_num_sms / 2);
+        const int clusters = (int)std::min<int64_t>(tiles, ds.num_sms / 2);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * clusters);
         cfg.blockDim = dim3(NUM_THREADS);
@@ -460,11 +643,19 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        TC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug, (int)(g.aux_dt == DT_F16)));
+        TC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug, (int)(g.aux_dt == DT_F16), ex));
     } else {
         const int64_t tiles = ceil_div(g.M, BLOCK_M) * ceil_div(g.N, BLOCK_N);
-        const int grid = (int)std::min<int64_t>(tiles, g_num_sms);
-        launch_pdl(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug, (int)(g.aux_dt == DT_F16));
+        const int grid = (int)std::min<int64_t>(tiles, ds.num_sms);
+        if (g_dynamic && tiles > grid) {           // with one tile per CTA there is nothing to schedule
+            if (ds.sched == nullptr) {
+                TC_CUDA(cudaMalloc(&ds.sched, SCHED_SLOTS * 2 * sizeof(int)));
+                TC_CUDA(cudaMemset(ds.sched, 0, SCHED_SLOTS * 2 * sizeof(int)));
+                TC_CUDA(cudaDeviceSynchronize());
+            }
+            ex.sched = ds.sched + 2 * (ds.seq++ % SCHED_SLOTS);
+        }
+        launch_pdl(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, g.out, g.out_pre, (int)g.ldo, g.bias, (int)g.M, (int)g.N, (int)g.K, g_debug, (int)(g.aux_dt == DT_F16), ex);
     }
     TC_LAUNCH_CHECK();
 }
@@ -473,6 +664,10 @@ template <int BLOCK_N, bool F16, bool CTA2>
 void dispatch(const GemmArgs& g, cudaStream_t stream) {
     if (g.epi == EPI_F32) return launch<BLOCK_N, EPI_F32, ACT_NONE, false, F16, CTA2>(g, stream);
     if (g.epi == EPI_F32_ADD) return launch<BLOCK_N, EPI_F32_ADD, ACT_NONE, false, F16, CTA2>(g, stream);
+    if (g.epi == EPI_F32_RESID) {
+        if constexpr (!CTA2) return launch<BLOCK_N, EPI_F32_RESID, ACT_NONE, false, F16, CTA2>(g, stream);
+        TC_CHECK(false, "the residual epilogue runs on single-CTA tiles only");
+    }
     if (g.epi == EPI_BF16_ACTGRAD) {
         // dgrad through the MLP activation: out = (A W^T) * act'(out_pre); only the shapes the backward uses are built
         TC_CHECK(g.out_pre != nullptr && (g.aux_dt == DT_BF16 || g.aux_dt == DT_F16), "activation-gradient epilogue needs 16-bit pre-activations in out_pre");
@@ -484,6 +679,17 @@ void dispatch(const GemmArgs& g, cudaStream_t stream) {
     }
     TC_CHECK(g.epi == EPI_BF16, "unknown epilogue %d", g.epi);
     const bool pre = g.out_pre != nullptr;
+    if (g.stats_in != nullptr) {
+        // LayerNorm folded into the GEMM (see GemmArgs::stats_in)
+        if constexpr (!CTA2) {
+            if (g.act == ACT_NONE) { TC_CHECK(!pre, "out_pre needs an activation"); return launch<BLOCK_N, EPI_BF16, ACT_NONE, false, F16, CTA2, true>(g, stream); }
+            if (g.act == ACT_GELU_ERF) return pre ? launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, true, F16, CTA2, true>(g, stream)
+                                                  : launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, false, F16, CTA2, true>(g, stream);
+            if (g.act == ACT_QUICK_GELU) return pre ? launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, true, F16, CTA2, true>(g, stream)
+                                                    : launch<BLOCK_N, EPI_BF16, ACT_QUICK_GELU, false, F16, CTA2, true>(g, stream);
+        }
+        TC_CHECK(false, "folded-LayerNorm GEMM: unsupported activation %d / tile shape", g.act);
+    }
     if (g.act == ACT_NONE) { TC_CHECK(!pre, "out_pre needs an activation"); return launch<BLOCK_N, EPI_BF16, ACT_NONE, false, F16, CTA2>(g, stream); }
     if (g.act == ACT_GELU_ERF) return pre ? launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, true, F16, CTA2>(g, stream)
                                           : launch<BLOCK_N, EPI_BF16, ACT_GELU_ERF, false, F16, CTA2>(g, stream);
@@ -494,6 +700,8 @@ void dispatch(const GemmArgs& g, cudaStream_t stream) {
 
 }  // namespace
 
+int gemm_stats_parts(int64_t N) { return 2 * (int)ceil_div(N, choose_block_n(N)); }
+
 void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     TC_CHECK(g.M > 0 && g.N > 0 && g.K > 0, "empty GEMM %lldx%lldx%lld", (long long)g.M, (long long)g.N, (long long)g.K);
     TC_CHECK(g.K % 8 == 0 && g.N % 8 == 0, "tcgen05 GEMM needs K%%8==0 and N%%8==0 (K=%lld N=%lld)", (long long)g.K, (long long)g.N);
@@ -501,12 +709,17 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
     // block_n: 0 = choose; 128 / 256 = one CTA per 128 x block_n tile; 512 = 2-CTA pairs on 256 x 256 tiles
     int bn = g.block_n;
     static const int env_bn = getenv("TAPCLIP_GEMM_BN") ? atoi(getenv("TAPCLIP_GEMM_BN")) : 0;   // measurement override: 128 | 256 | 512
-    if (bn == 0 && env_bn != 0 && g.N % 256 == 0 && g.epi != EPI_BF16_ACTGRAD) bn = env_bn;
+    const bool fixed_shape = g.epi == EPI_F32_RESID || g.stats_in != nullptr;   // the statistics layout follows choose_block_n
+    if (bn == 0 && env_bn != 0 && g.N % 256 == 0 && g.epi != EPI_BF16_ACTGRAD && !fixed_shape) bn = env_bn;
+    if (g.epi == EPI_F32_RESID) {
+        TC_CHECK(bn == 0 || bn == choose_block_n(g.N), "the residual epilogue fixes the tile shape (statistics layout)");
+        bn = 0;
+    }
     if (bn == 0) {
         // Measured (tools/gemm_bench.py, B200): 128x256 single-CTA tiles are within 3 % of the 2-CTA 256x256 tiles on the
         // image-tower shapes (both ~0.95 of cuBLAS: the mainloop is not L2-feed-bound) and 10-15 % faster on the small
         // text-tower shapes, where a 2-CTA pair halves the number of schedulable units.
-        bn = (g.N % 256 == 0) ? 256 : 128;
+        bn = choose_block_n(g.N);
     }
     const bool f16 = g.dt == DT_F16;
     if (bn == 512) { if (f16) dispatch<256, true, true>(g, stream); else dispatch<256, false, true>(g, stream); }

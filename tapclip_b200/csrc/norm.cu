@@ -72,7 +72,7 @@ layernorm_fwd_kernel(const float* x, int64_t x_row_stride, const float* __restri
 __global__ void __launch_bounds__(WARPS * 32)
 assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls, const float* __restrict__ pos,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x, int64_t rows,
-                       int n_tokens, int d) {
+                       int n_tokens, int d, bf16* __restrict__ xb, float2* __restrict__ stats) {
     pdl_wait_and_trigger();
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -112,7 +112,45 @@ assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restr
             o.z = (v[i].z - mean) * rstd * g.z + bb.z;
             o.w = (v[i].w - mean) * rstd * g.w + bb.w;
             *reinterpret_cast<float4*>(x + row * d + c) = o;
+            v[i] = o;
         }
+    if (xb != nullptr) {
+        // what the first block's folded-LayerNorm QKV GEMM consumes (gemm.h, GemmArgs::stats_in): the row in 16 bits and its
+        // (sum, sum of squares) as a single partial
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (i < nv) {
+                store4<bf16>(xb + row * d + (i * 32 + lane) * 4, v[i]);
+                s1 += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+                s2 += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+            }
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0) stats[row] = make_float2(s1, s2);
+    }
+}
+
+// x [rows, d] fp32 -> xb = x in the 16-bit operand type, stats[row] = (sum, sum of squares): the inputs of a folded-LayerNorm GEMM
+// for a residual stream that was not produced by an EPI_F32_RESID GEMM (the spliced prompts of the text tower)
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32)
+row_stats_cast_kernel(const float* __restrict__ x, T* __restrict__ xb, float2* __restrict__ stats, int64_t rows, int d) {
+    pdl_wait_and_trigger();
+    const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31, nv = d >> 7;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            const int c = (i * 32 + lane) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(x + row * d + c);
+            store4<T>(xb + row * d + c, v);
+            s1 += (v.x + v.y) + (v.z + v.w);
+            s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) stats[row] = make_float2(s1, s2);
 }
 
 // NV = float4 per lane the instance holds (4: d <= 512, the text tower - half the registers, twice the resident warps; 8: d <= 1024)
@@ -230,6 +268,28 @@ l2norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xhat, c
         }
 }
 
+// LayerNorm folded into a Linear (gemm.h, GemmArgs::stats_in): one warp per output row n of W [N,K]:
+//   Wf[n,k] = T(W[n,k] * gamma[k]),  fs[n] = sum_k float(Wf[n,k])  (of the ROUNDED values: the mean term must cancel what the
+//   tensor cores accumulate),  fb[n] = bias[n] + sum_k W[n,k] * beta[k]
+template <typename T>
+__global__ void fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, T* __restrict__ Wf, float* __restrict__ fs, float* __restrict__ fb,
+                                      int N, int K) {
+    pdl_wait_and_trigger();
+    const int n = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float s = 0.f, bb = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = W[(int64_t)n * K + k];
+        const T wf = from_f32<T>(w * gamma[k]);
+        Wf[(int64_t)n * K + k] = wf;
+        s += to_f32<T>(wf);
+        bb += w * beta[k];
+    }
+    s = warp_sum(s); bb = warp_sum(bb);
+    if (lane == 0) { fs[n] = s; fb[n] = (bias ? bias[n] : 0.f) + bb; }
+}
+
 void check_d(int d) { TC_CHECK(d % 128 == 0 && d >= 128 && d <= 128 * MAXV, "row width %d unsupported (need d %% 128 == 0, d <= 1024)", d); }
 
 }  // namespace
@@ -246,12 +306,32 @@ void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, con
 }
 
 void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta, float* x,
-                     int B, int n_tokens, int d, cudaStream_t stream) {
+                     int B, int n_tokens, int d, cudaStream_t stream, void* xb, float* stats) {
     check_d(d);
     const int64_t rows = (int64_t)B * n_tokens;
     if (rows == 0) return;
+    TC_CHECK((xb == nullptr) == (stats == nullptr), "assemble_ln_pre: xb and stats go together");
     launch_pdl(assemble_ln_pre_kernel, (unsigned)ceil_div(rows, WARPS), WARPS * 32, 0, stream, patch_out, cls, pos, gamma, beta, x, rows,
-               n_tokens, d);
+               n_tokens, d, (bf16*)xb, (float2*)stats);
+    TC_LAUNCH_CHECK();
+}
+
+void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, void* Wf, int dt, float* fs, float* fb,
+                    int N, int K, cudaStream_t stream) {
+    TC_CHECK(dt == DT_BF16 || dt == DT_F16, "folded weights are 16-bit operands");
+    const unsigned grid = (unsigned)ceil_div((int64_t)N * 32, 256);
+    if (dt == DT_F16) launch_pdl(fold_ln_weight_kernel<f16>, grid, 256, 0, stream, W, bias, gamma, beta, (f16*)Wf, fs, fb, N, K);
+    else launch_pdl(fold_ln_weight_kernel<bf16>, grid, 256, 0, stream, W, bias, gamma, beta, (bf16*)Wf, fs, fb, N, K);
+    TC_LAUNCH_CHECK();
+}
+
+void row_stats_cast(const float* x, void* xb, int xb_dt, float* stats, int64_t rows, int d, cudaStream_t stream) {
+    check_d(d);
+    TC_CHECK(xb_dt == DT_BF16 || xb_dt == DT_F16, "row_stats_cast writes a 16-bit copy");
+    if (rows == 0) return;
+    const unsigned grid = (unsigned)ceil_div(rows, WARPS);
+    if (xb_dt == DT_BF16) launch_pdl(row_stats_cast_kernel<bf16>, grid, WARPS * 32, 0, stream, x, (bf16*)xb, (float2*)stats, rows, d);
+    else launch_pdl(row_stats_cast_kernel<f16>, grid, WARPS * 32, 0, stream, x, (f16*)xb, (float2*)stats, rows, d);
     TC_LAUNCH_CHECK();
 }
 

@@ -29,6 +29,8 @@ class Engine:
                                cfg.text_width, cfg.text_layers, cfg.text_heads, cfg.embed_dim, cfg.context_length,
                                _lib.ACT["quick_gelu" if cfg.quick_gelu else "gelu_erf"], _lib.DTYPE[dtype])
         self._h = C.c_void_p()
+        self.last_forward_token = 0
+        self.weight_generation = 0                       # bumped by load_state_dict: part of FullModel's text-feature cache key
         with torch.cuda.device(self.device):
             _lib.check(self.lib.tapclip_create(C.byref(c), C.byref(self._h)))
 
@@ -49,8 +51,9 @@ class Engine:
                 w = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
                 shape = (C.c_int64 * max(w.dim(), 1))(*w.shape)
                 _lib.check(self.lib.tapclip_load_weight(self._h, name.encode(), _lib.ptr(w), w.dim(), shape, _lib.stream_ptr()))
-            torch.cuda.current_stream().synchronize()      # staging copies `w` may be freed after this
+            torch.cuda.current_stream().synchronize()      # staging copies `w` may be freed after this; folded operands are built
             _lib.check(self.lib.tapclip_weights_complete(self._h))
+        self.weight_generation += 1
 
     # ---- hot path -------------------------------------------------------------------------------------
     def encode_image(self, images: torch.Tensor, want_cls_rows: bool = False, want_rollout: bool = False):
@@ -89,9 +92,11 @@ class Engine:
         attr = torch.empty(Cn, pa, device=ctx.device, dtype=torch.float32)
         raw = torch.empty(Cn, pa, device=ctx.device, dtype=torch.float32) if mode == "intended" else None
         feat = torch.empty(Cn, cfg.embed_dim, device=ctx.device, dtype=torch.float32)
+        token = C.c_int64(0)
         _lib.check(self.lib.tapclip_text_forward(self._h, _lib.ptr(ctx), _lib.ptr(tok), Cn, P, _lib.ATTR_MODE[mode],
                                                  1 if save_for_backward else 0, _lib.ptr(raw), _lib.ptr(attr), _lib.ptr(feat),
-                                                 _lib.stream_ptr()))
+                                                 C.byref(token), _lib.stream_ptr()))
+        self.last_forward_token = int(token.value)      # identifies the saved activations; text_backward(token=...) checks it
         return feat, attr, raw
 
     def text_attribution(self, ctx: torch.Tensor, tok: torch.Tensor):
@@ -104,7 +109,7 @@ class Engine:
         attr = torch.empty(Cn, P, device=ctx.device, dtype=torch.float32)
         raw = torch.empty(Cn, P, device=ctx.device, dtype=torch.float32)
         _lib.check(self.lib.tapclip_text_forward(self._h, _lib.ptr(ctx), _lib.ptr(tok), Cn, P, _lib.ATTR_MODE["attribution_only"], 0,
-                                                 _lib.ptr(raw), _lib.ptr(attr), None, _lib.stream_ptr()))
+                                                 _lib.ptr(raw), _lib.ptr(attr), None, None, _lib.stream_ptr()))
         return attr, raw
 
     def logits(self, img_feat, text_feat, logit_scale, labels=None, inv_batch_total=None):
@@ -134,10 +139,13 @@ class Engine:
                                                     _lib.stream_ptr()))
         return d_text, d_scale
 
-    def text_backward(self, d_text_feat, n_cls: int, prompt_len: int):
+    def text_backward(self, d_text_feat, n_cls: int, prompt_len: int, token: int = 0):
+        """``token``: ``last_forward_token`` of the forward being differentiated; a forward that ran on this engine since then
+        has replaced the saved activations, and the call raises instead of using them (0 = no check)."""
         _check_cuda_f32(d_text_feat, "d_text_feat")
         dctx = torch.empty(n_cls, prompt_len, self.cfg.text_width, device=d_text_feat.device, dtype=torch.float32)
-        _lib.check(self.lib.tapclip_text_backward(self._h, _lib.ptr(d_text_feat), _lib.ptr(dctx), _lib.stream_ptr()))
+        _lib.check(self.lib.tapclip_text_backward(self._h, _lib.ptr(d_text_feat), _lib.ptr(dctx), int(token), n_cls, prompt_len,
+                                                  _lib.stream_ptr()))
         return dctx
 
     def adamw_step(self, param, grad, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step):

@@ -17,6 +17,8 @@ all-reduced and the ctx gradients are all-gathered so that every replica holds t
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -71,6 +73,9 @@ class _TapClipFunction(torch.autograd.Function):
             model.last_attribution = attr_local
         ctx.model, ctx.shard, ctx.dims = model, shard, (n_cls, P, lo, hi)
         ctx.need_grad = need_grad
+        # the engine keeps ONE set of saved text activations: remember which forward wrote them, so a backward that comes after
+        # another forward on the same CLIPWrapper (two FullModels sharing it, two forwards before one backward) fails loudly
+        ctx.text_token = eng.last_forward_token if need_grad else 0
         ctx.save_for_backward(logits, dlogits_ce if dlogits_ce is not None else logits.new_empty(0), img_norm, logit_scale)
         ctx.has_ce = dlogits_ce is not None
         ctx.set_materialize_grads(False)
@@ -99,7 +104,7 @@ class _TapClipFunction(torch.autograd.Function):
         grads = [None] * n_cls
         if ctx.need_grad:
             d_local = d_text[lo:hi].contiguous()
-            dctx_local = eng.text_backward(d_local, hi - lo, P)                    # row A13
+            dctx_local = eng.text_backward(d_local, hi - lo, P, token=ctx.text_token)   # row A13
             dctx = all_gather_rows(dctx_local.view(hi - lo, -1), shard, n_cls).view(n_cls, P, -1)
             grads = [dctx] if ctx.adjusted else list(dctx.unbind(0))
         elif ctx.adjusted:
@@ -149,7 +154,10 @@ class FullModel(nn.Module):
         if not self.overlap_towers or device.type != "cuda":
             return None
         if self._side is None:
-            self._side = torch.cuda.Stream(device=device)
+            # TAPCLIP_TEXT_PRIO=1: the text tower's (small, dependent) kernels get the SMs first; the image tower's GEMMs draw their
+            # tiles dynamically (gemm_tc.cu) and take whatever is free
+            prio = -1 if os.environ.get("TAPCLIP_TEXT_PRIO", "0") == "1" else 0
+            self._side = torch.cuda.Stream(device=device, priority=prio)
         return self._side
 
     def _encode_image(self, images):
@@ -196,7 +204,8 @@ class FullModel(nn.Module):
         ctx_bank = pl.flat_ctx()
         use_cache = self.cache_text_features and not need_grad and not self.training
         if use_cache:
-            key = (ctx_bank.data_ptr(), tuple(p._version for p in pl.context_bank.values()), lo, hi, self.clip.attribution)
+            key = (ctx_bank.data_ptr(), tuple(p._version for p in pl.context_bank.values()), lo, hi, self.clip.attribution,
+                   self.clip.engine.weight_generation)
             if self._text_cache is not None and self._text_cache[0] == key:
                 return self._text_cache[1]
         out = self.clip.engine.text_forward(ctx_bank[lo:hi], pl.flat_tok()[lo:hi], self.clip.attribution, need_grad)

@@ -12,6 +12,8 @@ class FakeEngine:
         self.ow = oracle_wrapper
         self.launch_count = 0
         self._saved = None
+        self.last_forward_token = 0          # same contract as the real engine: one saved forward, identified by a token
+        self.weight_generation = 0
 
     def encode_image(self, images, want_cls_rows=False):
         with torch.no_grad():
@@ -47,6 +49,7 @@ class FakeEngine:
             feat = x[:, -1, :] @ self.ow.model.text_projection
             feat = feat / feat.norm(dim=-1, keepdim=True)
         self._saved = (leaf, feat) if save_for_backward else None
+        self.last_forward_token = self.last_forward_token + 1 if save_for_backward else 0
         return feat.detach(), attr, raw
 
     def logits(self, img_feat, text_feat, logit_scale, labels=None, inv_batch_total=None):
@@ -64,7 +67,9 @@ class FakeEngine:
         d_text = logit_scale.detach().exp() * dlogits.t() @ img_norm
         return d_text, (dlogits * logits).sum()
 
-    def text_backward(self, d_text_feat, n_cls, prompt_len):
+    def text_backward(self, d_text_feat, n_cls, prompt_len, token=0):
+        if self._saved is None or (token and token != self.last_forward_token):
+            raise RuntimeError("stale backward: the saved activations were replaced by a later forward")
         leaf, feat = self._saved
         (g,) = torch.autograd.grad(feat, leaf, d_text_feat)
         return g

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 LIB = os.path.join(ROOT, "build", "libtapclip_trace.so")
 SRC = os.path.join(ROOT, "tapclip_b200", "csrc")
 if len(sys.argv) > 1 and sys.argv[1] == "build":
-    srcs = "capi.cu engine.cu gemm_tc.cu gemm_ln.cu gemm_simt.cu norm.cu attention.cu elementwise.cu preprocess.cu".split()
+    srcs = "capi.cu engine.cu gemm_tc.cu gemm_simt.cu norm.cu attention.cu elementwise.cu preprocess.cu".split()
     objs = [os.path.join(ROOT, "build", "obj", s.replace(".cu", ".o")) for s in srcs]
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler",
                            "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-DTAPCLIP_ATTN_TRACE", "-I", os.path.join(ROOT, "include"),
