@@ -123,10 +123,14 @@ TAPCLIP_API int tapclip_text_backward(tapclip_handle h, const float* d_text_feat
 TAPCLIP_API int tapclip_adamw_step(tapclip_handle h, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                        float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
 
-/* utils/eval_metrics.py:19-29: argmax over classes into out_pred (int64 [B], nullable) and
- * atomically adds the number of (pred == label) to out_correct[0] (int32, nullable with labels). */
+/* utils/eval_metrics.py:19-29,58-63: argmax over classes into out_pred (int64 [B], nullable; first maximum wins, NaN counts as
+ * the maximum, as torch.argmax) and, with labels, the accuracy counters ACCUMULATED on the device (all int32, nullable):
+ * out_correct[0] += #(pred == label); out_class_total[t] += 1 and out_class_correct[t] += (pred == t) for every sample whose
+ * label t is in [0, C) ([C] arrays: the reference's per_class_total / per_class_correct dicts).  One device->host read per
+ * epoch replaces the reference's per-sample .item() calls. */
 TAPCLIP_API int tapclip_argmax_count(tapclip_handle h, const float* logits, const int64_t* labels, int32_t B, int32_t C,
-                         int64_t* out_pred, int32_t* out_correct, void* stream);
+                         int64_t* out_pred, int32_t* out_correct, int32_t* out_class_correct, int32_t* out_class_total,
+                         void* stream);
 
 /* Workspace bytes currently held by the handle (for memory accounting). */
 TAPCLIP_API int64_t tapclip_workspace_bytes(tapclip_handle h);

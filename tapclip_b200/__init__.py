@@ -8,6 +8,7 @@ is an error (no CPU / PyTorch fallback).
 from .attribution_monitor import AttributionMonitor
 from .clip_wrapper import CLIPWrapper
 from .configs import get_model_config
+from .eval_metrics import evaluate_accuracy, evaluate_per_class_accuracy
 from .model_wrapper import FullModel
 from .optim import FusedAdamW
 from .preprocess import GpuPreprocess
@@ -15,5 +16,5 @@ from .prompt_adjustor import PromptAdjustor
 from .prompt_learner import PromptLearner
 
 __all__ = ["CLIPWrapper", "FullModel", "PromptLearner", "AttributionMonitor", "PromptAdjustor", "FusedAdamW",
-           "GpuPreprocess", "get_model_config"]
+           "GpuPreprocess", "get_model_config", "evaluate_accuracy", "evaluate_per_class_accuracy"]
 __version__ = "0.1.0"

@@ -50,7 +50,7 @@ PROTOTYPES = {
     "tapclip_logits_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "tapclip_text_backward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "tapclip_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
-    "tapclip_argmax_count": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "tapclip_argmax_count": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "tapclip_workspace_bytes": (_i64, [_vp]),
     "tapclip_launch_count": (_i64, [_vp]),
     "tapclip_profile": (C.c_int, [_vp, _i32]),

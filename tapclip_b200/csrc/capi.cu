@@ -118,10 +118,12 @@ TAPCLIP_API int tapclip_adamw_step(tapclip_handle h, float* param, const float* 
 }
 
 TAPCLIP_API int tapclip_argmax_count(tapclip_handle h, const float* logits, const int64_t* labels, int32_t B, int32_t C, int64_t* out_pred,
-                         int32_t* out_correct, void* stream) {
+                         int32_t* out_correct, int32_t* out_class_correct, int32_t* out_class_total, void* stream) {
     TC_API_BEGIN
     NEED(h);
-    argmax_count(logits, labels, out_pred, out_correct, B, C, S(stream));
+    TC_CHECK(B == 0 || logits != nullptr, "null argument");
+    TC_CHECK(labels != nullptr || (out_correct == nullptr && out_class_correct == nullptr && out_class_total == nullptr), "counters need labels");
+    argmax_count(logits, labels, out_pred, out_correct, out_class_correct, out_class_total, B, C, S(stream));
     ++h->impl.launches;
     TC_API_END
 }

@@ -311,17 +311,19 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
-// utils/eval_metrics.py:19-29: argmax over classes (first max wins, as torch.argmax) + correct count
+// utils/eval_metrics.py:19-29,58-63: argmax over classes (first max wins, as torch.argmax; NaN counts as the maximum, as in
+// torch) + overall and per-class correct / total counters kept on the device (the reference pulls every sample to the host)
 __global__ void argmax_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int64_t* __restrict__ pred,
-                              int* __restrict__ correct, int B, int C) {
+                              int* __restrict__ correct, int* __restrict__ class_correct, int* __restrict__ class_total, int B, int C) {
     pdl_wait_and_trigger();
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
     const int lane = threadIdx.x & 31;
     float best = -INFINITY; int bi = 0x7fffffff;
     for (int c = lane; c < C; c += 32) {
-        const float v = logits[(int64_t)b * C + c];
-        if (v > best) { best = v; bi = c; }
+        float v = logits[(int64_t)b * C + c];
+        if (v != v) v = INFINITY;                     // torch.argmax treats NaN as the largest value (first one wins)
+        if (v > best || bi == 0x7fffffff) { best = v; bi = c; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -331,7 +333,15 @@ __global__ void argmax_kernel(const float* __restrict__ logits, const int64_t* _
     }
     if (lane == 0) {
         if (pred) pred[b] = bi;
-        if (labels && correct && labels[b] == bi) atomicAdd(correct, 1);
+        if (labels) {
+            const int64_t t = labels[b];
+            const bool hit = (t == bi);
+            if (correct && hit) atomicAdd(correct, 1);
+            if (t >= 0 && t < C) {                    // eval_metrics.py:26-29: per_class_total[t] += 1; per_class_correct[t] += (t == p)
+                if (class_total) atomicAdd(class_total + t, 1);
+                if (class_correct && hit) atomicAdd(class_correct + t, 1);
+            }
+        }
     }
 }
 
@@ -478,9 +488,10 @@ void adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float l
     TC_LAUNCH_CHECK();
 }
 
-void argmax_count(const float* logits, const int64_t* labels, int64_t* pred, int* correct, int B, int C, cudaStream_t stream) {
+void argmax_count(const float* logits, const int64_t* labels, int64_t* pred, int* correct, int* class_correct, int* class_total, int B,
+                  int C, cudaStream_t stream) {
     if (B == 0) return;
-    launch_pdl(argmax_kernel, (unsigned)ceil_div(B, 8), 256, 0, stream, logits, labels, pred, correct, B, C);
+    launch_pdl(argmax_kernel, (unsigned)ceil_div(B, 8), 256, 0, stream, logits, labels, pred, correct, class_correct, class_total, B, C);
     TC_LAUNCH_CHECK();
 }
 

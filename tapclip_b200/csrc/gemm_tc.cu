@@ -227,6 +227,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int cslot = 0; uint32_t cphase = 0;
             int tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : unit;
             while (tile < num_tiles) {
+                if constexpr (RESID) {
+                    // pull the tile's old residual rows into L2 now: the epilogue reads them one mainloop from here
+                    const int pm0 = (tile / n_tiles) * BLOCK_M, pn0 = (tile % n_tiles) * BLOCK_N;
+                    const uint32_t bytes = (uint32_t)min(BLOCK_N, N - pn0) * 4u;
+#pragma unroll
+                    for (int rr = 0; rr < BLOCK_M / 32; ++rr) {
+                        const int r = pm0 + rr * 32 + lane;
+                        if (r < M) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ex.resid_in + (int64_t)r * ex.ld_in + pn0), "r"(bytes) : "memory");
+                    }
+                }
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -285,6 +295,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         int tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : unit;
         while (tile < num_tiles) {
             const int m0 = (tile / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            const int row0 = m0 + q * 32;
+            [[maybe_unused]] float2 st[8];                   // FOLD: the row's first 8 statistics partials, in flight during the bias staging
+            if constexpr (FOLD) {
+                const int row = row0 + lane;
+                const float2* sp = reinterpret_cast<const float2*>(ex.stats_in) + (int64_t)row * ex.stats_parts;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    st[p] = make_float2(0.f, 0.f);
+                    if (row < M && p < ex.stats_parts) st[p] = sp[p];
+                }
+            }
             if (bias != nullptr) {
                 // stage this tile's bias in smem while the MMAs of the tile are still running (a global load per
                 // chunk inside the epilogue loop exposed its full latency: ncu long_scoreboard on the bias FADDs)
@@ -303,29 +324,123 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
             }
-            const int row0 = m0 + q * 32;
             // FOLD: this thread's row statistics -> out = fa * acc + (fb * s[n] + b'[n]),  fa = rstd, fb = -mean * rstd
             float fa = 1.f, fb = 0.f;
             if constexpr (FOLD) {
-                const int row = row0 + lane;
                 float s1 = 0.f, s2 = 0.f;
-                if (row < M) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) { s1 += st[p].x; s2 += st[p].y; }
+                const int row = row0 + lane;
+                for (int p0 = 8; p0 < ex.stats_parts; p0 += 8) {            // more than 8 partials: rows wider than 1024 / 128-wide tiles
                     const float2* sp = reinterpret_cast<const float2*>(ex.stats_in) + (int64_t)row * ex.stats_parts;
-                    for (int p = 0; p < ex.stats_parts; ++p) { const float2 t = sp[p]; s1 += t.x; s2 += t.y; }
+#pragma unroll
+                    for (int p = 0; p < 8; ++p)
+                        if (row < M && p0 + p < ex.stats_parts) { const float2 t = sp[p0 + p]; s1 += t.x; s2 += t.y; }
                 }
                 const float inv_k = 1.0f / (float)K;
                 const float mean = s1 * inv_k;
                 fa = rsqrtf(fmaxf(s2 * inv_k - mean * mean, 0.f) + 1e-5f);
                 fb = -mean * fa;
             }
-            [[maybe_unused]] float rs[8], rq[8];             // RESID: (sum, sum of squares) of this warp's columns, rows it*4 + rd_row
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
             if constexpr (RESID) {
+                // ---- x_new = x_old + A W^T + b, its 16-bit copy and its row statistics -------------------------------------------
+                // The old residual values are the only global READ of this epilogue; they are requested in the store mapping
+                // (lane (rd_row, rd_ch) owns 16 bytes of rows it*4 + rd_row) two chunks ahead: the first two chunks' values are in
+                // flight while this tile's MMAs still run (the MMA warp has pulled the tile's rows into L2 when it started the
+                // tile), chunk i+2 is requested when chunk i has been consumed.  The chunk loop is unrolled so that both
+                // lookahead buffers stay in registers.
+                constexpr int RCH = 32;                              // fp32 columns per 128-byte staging row
+                constexpr int NMINE = BLOCK_N / RCH / 2;             // chunks of this warp: c = chunk_par + 2 i
+                float4 xo[2][8];
+                float rs[8], rq[8];                                  // (sum, sum of squares) of this warp's columns, rows it*4 + rd_row
 #pragma unroll
                 for (int it = 0; it < 8; ++it) { rs[it] = 0.f; rq[it] = 0.f; }
+                auto request = [&](int i, float4 (&dst)[8]) {
+                    const int gc = n0 + (chunk_par + 2 * i) * RCH + rd_ch * 4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = row0 + it * 4 + rd_row;
+                        dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < M && gc < N) dst[it] = *reinterpret_cast<const float4*>(ex.resid_in + (int64_t)r * ex.ld_in + gc);
+                    }
+                };
+                request(0, xo[0]);
+                if constexpr (NMINE > 1) request(1, xo[1]);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+#pragma unroll
+                for (int i = 0; i < NMINE; ++i) {
+                    const int c = chunk_par + 2 * i;
+                    const int col0 = n0 + c * RCH, gcol = col0 + rd_ch * 4;
+                    float v[RCH];
+                    {
+                        uint32_t r0[32];
+                        tmem_ld_32x32(taddr + c * RCH, r0);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+                    }
+                    if (i == NMINE - 1) {                            // this warp's TMEM reads of the tile are done
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
+                    if (bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < RCH; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias_s + c * RCH + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    }
+                    __syncwarp();                                    // previous read-back of the staging buffer is complete
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + row_off + (((uint32_t)j ^ sw) << 4)),
+                                     "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])), "r"(__float_as_uint(v[4 * j + 2])),
+                                     "r"(__float_as_uint(v[4 * j + 3])) : "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + rd_row;
+                        float a0, a1, a2, a3;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                                     : "r"(stage_u32 + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
+                        float ps = 0.f, pq = 0.f;
+                        if (row0 + r < M && gcol < N && dbg == 0) {
+                            const float4 o = xo[i & 1][it];
+                            a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
+                            asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<uint8_t*>(out) + ((int64_t)(row0 + r) * ldo + gcol) * 4),
+                                         "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+                            if (ex.xb != nullptr)
+                                asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint8_t*>(ex.xb) + ((int64_t)(row0 + r) * N + gcol) * 2),
+                                             "r"(pack2<T16>(a0, a1)), "r"(pack2<T16>(a2, a3)) : "memory");
+                            ps = (a0 + a1) + (a2 + a3);
+                            pq = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                        }
+                        // the 8 lanes that share a row (consecutive lanes) reduce their partials
+                        ps += __shfl_xor_sync(0xffffffffu, ps, 1); pq += __shfl_xor_sync(0xffffffffu, pq, 1);
+                        ps += __shfl_xor_sync(0xffffffffu, ps, 2); pq += __shfl_xor_sync(0xffffffffu, pq, 2);
+                        ps += __shfl_xor_sync(0xffffffffu, ps, 4); pq += __shfl_xor_sync(0xffffffffu, pq, 4);
+                        rs[it] += ps; rq[it] += pq;
+                    }
+                    if (i + 2 < NMINE) request(i + 2, xo[i & 1]);
+                }
+                // one (sum, sum of squares) pair per row, n-tile and warp parity: every slot has exactly one writer
+                if (ex.stats_out != nullptr && rd_ch == 0) {
+                    const int parts = 2 * n_tiles, part = 2 * (tile % n_tiles) + chunk_par;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = row0 + it * 4 + rd_row;
+                        if (row < M) reinterpret_cast<float2*>(ex.stats_out)[(int64_t)row * parts + part] = make_float2(rs[it], rq[it]);
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : tile + num_units;
+                continue;
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
             constexpr int CH = OUT16 ? 64 : 32;  // columns per 128-byte staging row
             constexpr int OUT_ESZ = OUT16 ? 2 : 4;
             constexpr int NCHUNK = BLOCK_N / CH;
@@ -334,16 +449,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int c = chunk_par; c < NCHUNK; c += 2) {
                 const int col0 = n0 + c * CH;
                 const int gcol = col0 + rd_ch * (16 / OUT_ESZ);
-                [[maybe_unused]] float4 xo[8];               // RESID: old residual values in the store mapping
-                if constexpr (RESID) {
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int r = it * 4 + rd_row;
-                        xo[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row0 + r < M && gcol < N)
-                            xo[it] = *reinterpret_cast<const float4*>(ex.resid_in + (int64_t)(row0 + r) * ex.ld_in + gcol);
-                    }
-                }
                 float v[CH];
                 {
                     uint32_t r0[32];
@@ -423,32 +528,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     // staging -> global: lane (rd_row, rd_ch) moves 16 bytes; 8 lanes = one full 128-byte row segment
                     uint8_t* gbase = reinterpret_cast<uint8_t*>(is_pre ? out_pre : out);
                     if (dbg != 1) {
-                        if constexpr (RESID) {
-                            // x_new = x_old + tile: plain store of the fp32 row, 8-byte store of its 16-bit copy, and the row's
-                            // (sum, sum of squares) over this chunk reduced across the 8 lanes that share the row
-#pragma unroll
-                            for (int it = 0; it < 8; ++it) {
-                                const int r = it * 4 + rd_row;
-                                float a0, a1, a2, a3;
-                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
-                                             : "r"(sb + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
-                                float ps = 0.f, pq = 0.f;
-                                if (row0 + r < M && gcol < N) {
-                                    a0 += xo[it].x; a1 += xo[it].y; a2 += xo[it].z; a3 += xo[it].w;
-                                    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gbase + ((int64_t)(row0 + r) * ldo + gcol) * 4),
-                                                 "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
-                                    if (ex.xb != nullptr)
-                                        asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint8_t*>(ex.xb) + ((int64_t)(row0 + r) * N + gcol) * 2),
-                                                     "r"(pack2<T16>(a0, a1)), "r"(pack2<T16>(a2, a3)) : "memory");
-                                    ps = (a0 + a1) + (a2 + a3);
-                                    pq = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-                                }
-                                ps += __shfl_xor_sync(0xffffffffu, ps, 1); pq += __shfl_xor_sync(0xffffffffu, pq, 1);
-                                ps += __shfl_xor_sync(0xffffffffu, ps, 2); pq += __shfl_xor_sync(0xffffffffu, pq, 2);
-                                ps += __shfl_xor_sync(0xffffffffu, ps, 4); pq += __shfl_xor_sync(0xffffffffu, pq, 4);
-                                rs[it] += ps; rq[it] += pq;
-                            }
-                        } else if constexpr (EPI == EPI_F32_ADD) {
+                        if constexpr (EPI == EPI_F32_ADD) {
                             // residual update x += tile as fire-and-forget vector reductions (measured faster than a plain
                             // read-modify-write: 37 vs 54 us on the 25216x768x768 out-projection); every element has exactly
                             // one contributor, so the result is deterministic
@@ -478,17 +558,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                                  "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");   // streaming: keep A/W resident in L2
                             }
                         }
-                    }
-                }
-            }
-            if constexpr (RESID) {
-                // one (sum, sum of squares) pair per row, n-tile and warp parity: every slot has exactly one writer
-                if (ex.stats_out != nullptr && rd_ch == 0) {
-                    const int parts = 2 * n_tiles, part = 2 * (tile % n_tiles) + chunk_par;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = row0 + it * 4 + rd_row;
-                        if (row < M) reinterpret_cast<float2*>(ex.stats_out)[(int64_t)row * parts + part] = make_float2(rs[it], rq[it]);
                     }
                 }
             }
@@ -595,7 +664,7 @@ DeviceState& device_state() {
 // TAPCLIP_GEMM_DEBUG (measurement only; results are WRONG when set): 1 = skip the epilogue's global stores, 2 = skip the epilogue body
 int g_debug = getenv("TAPCLIP_GEMM_DEBUG") ? atoi(getenv("TAPCLIP_GEMM_DEBUG")) : 0;
 // TAPCLIP_GEMM_SCHED: 1 = dynamic tile order (atomic counter), 0 = static striding
-int g_dynamic = getenv("TAPCLIP_GEMM_SCHED") ? atoi(getenv("TAPCLIP_GEMM_SCHED")) : 1;
+int g_dynamic = getenv("TAPCLIP_GEMM_SCHED") ? atoi(getenv("TAPCLIP_GEMM_SCHED")) : 0;
 
 int choose_block_n(int64_t N) { return (N % 256 == 0) ? 256 : 128; }
 

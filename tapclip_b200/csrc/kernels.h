@@ -115,8 +115,10 @@ void logits_bwd(const float* dlogits, const float* logits, const float* img, con
 // p -= lr*(m_hat/(sqrt(v_hat)+eps) + wd*p)  — torch.optim.AdamW semantics, one fused pass over a flat bank
 void adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                 float wd, int step, cudaStream_t stream);
-// argmax over classes + count of argmax==label (utils/eval_metrics.py:19-29 without per-sample .item())
-void argmax_count(const float* logits, const int64_t* labels, int64_t* pred, int* correct, int B, int C, cudaStream_t stream);
+// argmax over classes + counters kept on the device (utils/eval_metrics.py:19-29,58-63 without per-sample .item()): correct[0] +=
+// #(argmax == label); class_total[t] += 1 and class_correct[t] += (argmax == t) for every sample with label t (int32 [C], nullable)
+void argmax_count(const float* logits, const int64_t* labels, int64_t* pred, int* correct, int* class_correct, int* class_total, int B,
+                  int C, cudaStream_t stream);
 
 // ---- preprocess.cu ---------------------------------------------------------------------------------
 // img [H, W, 3] uint8 RGB (device) -> out [3, R, R] fp32: bicubic resize of the shorter side to R (Pillow's antialiased

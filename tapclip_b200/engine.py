@@ -154,12 +154,27 @@ class Engine:
         _lib.check(self.lib.tapclip_adamw_step(self._h, _lib.ptr(param), _lib.ptr(grad), _lib.ptr(exp_avg), _lib.ptr(exp_avg_sq),
                                                param.numel(), lr, betas[0], betas[1], eps, weight_decay, step, _lib.stream_ptr()))
 
-    def argmax_count(self, logits, labels=None):
+    def argmax_count(self, logits, labels=None, counters=None):
+        """argmax over classes (+ accuracy counters).  ``counters``: optional ``(correct [1], class_correct [C], class_total [C])``
+        int32 CUDA tensors that are ACCUMULATED into across calls (eval_metrics.evaluate_accuracy keeps one set per epoch)."""
         B, Cn = logits.shape
         pred = torch.empty(B, device=logits.device, dtype=torch.int64)
-        correct = torch.zeros((), device=logits.device, dtype=torch.int32) if labels is not None else None
+        correct = cls_ok = cls_n = None
+        if labels is not None:
+            if labels.dtype != torch.int64 or not labels.is_cuda:
+                raise ValueError("labels must be an int64 CUDA tensor")
+            labels = labels.contiguous()
+            if counters is not None:
+                correct, cls_ok, cls_n = counters
+                for t in counters:
+                    if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous():
+                        raise ValueError("accuracy counters must be contiguous int32 CUDA tensors")
+                if cls_ok.numel() != Cn or cls_n.numel() != Cn:
+                    raise ValueError(f"per-class counters must have {Cn} entries")
+            else:
+                correct = torch.zeros((), device=logits.device, dtype=torch.int32)
         _lib.check(self.lib.tapclip_argmax_count(self._h, _lib.ptr(logits.contiguous()), _lib.ptr(labels), B, Cn, _lib.ptr(pred),
-                                                 _lib.ptr(correct), _lib.stream_ptr()))
+                                                 _lib.ptr(correct), _lib.ptr(cls_ok), _lib.ptr(cls_n), _lib.stream_ptr()))
         return pred, correct
 
     def profile(self, enable: bool):

@@ -115,6 +115,62 @@ def test_eval_text_feature_cache_and_argmax():
     assert torch.equal(pred, l1.argmax(1)) and correct.item() == (l1.argmax(1) == labels).sum().item()
 
 
+def test_evaluate_accuracy_with_device_side_per_class_counters(capsys):
+    """utils/eval_metrics.py:7-41,44-73 as a drop-in: same return values and report as the reference's host loop, with the
+    argmax and the overall / per-class counters kept on the device (one D2H per epoch)."""
+    import tapclip_b200 as tb
+    ow, om, clip, model = _mini(mode="intended", dtype="fp32")
+    C = 5
+    g = torch.Generator().manual_seed(3)
+    loader = [(torch.randn(n, 3, 64, 64, generator=g), torch.randint(0, C, (n,), generator=g)) for n in (7, 4, 1, 9)]
+    # the reference's loop (eval_metrics.py:14-29), restated on the host from this model's own logits
+    correct = total = 0
+    cls_ok, cls_n = [0] * C, [0] * C
+    model.eval()
+    with torch.no_grad():
+        for images, labels in loader:
+            preds = model(images.cuda())["logits"].argmax(1).cpu()
+            correct += int((preds == labels).sum()); total += labels.numel()
+            for t, p in zip(labels.tolist(), preds.tolist()):
+                cls_n[t] += 1; cls_ok[t] += int(t == p)
+    acc = tb.evaluate_accuracy(model, loader, "cuda")
+    report = capsys.readouterr().out
+    assert abs(acc - 100.0 * correct / total) < 1e-9
+    for c in range(C):
+        if cls_n[c]:
+            assert f" - Class {c:2d}: {100.0 * cls_ok[c] / cls_n[c]:.2f}% ({cls_ok[c]}/{cls_n[c]})" in report
+    per = tb.evaluate_per_class_accuracy(model, loader, "cuda", class_names=class_names(C))
+    assert per == {class_names(C)[c]: 100.0 * cls_ok[c] / cls_n[c] for c in range(C) if cls_n[c]}
+    assert tb.evaluate_accuracy(model, [], "cuda") == 0.0                      # empty loader (eval_metrics.py:31)
+    # counters accumulate across calls and ignore out-of-range labels for the per-class arrays
+    cnt = (torch.zeros(1, dtype=torch.int32, device="cuda"), torch.zeros(C, dtype=torch.int32, device="cuda"),
+           torch.zeros(C, dtype=torch.int32, device="cuda"))
+    logits = torch.randn(6, C, device="cuda")
+    logits[2, 3] = float("nan")                                               # torch.argmax: NaN is the maximum
+    lab = torch.tensor([0, 1, 3, 4, 2, 0], device="cuda")
+    for _ in range(2):
+        pred, _ = clip.engine.argmax_count(logits, lab, counters=cnt)
+    assert torch.equal(pred, logits.argmax(1))
+    assert cnt[0].item() == 2 * int((pred == lab).sum()) and cnt[2].sum().item() == 12
+
+
+def test_stale_backward_is_refused():
+    """One CLIPWrapper shared by two FullModels (train + EMA/teacher): the engine holds ONE set of saved text activations, so a
+    backward that follows another model's forward must fail loudly instead of differentiating the wrong forward."""
+    import tapclip_b200 as tb
+    ow, om, clip, model = _mini(mode="intended", dtype="fp32")
+    torch.manual_seed(5)
+    other = tb.FullModel(class_names(5), clip, prompt_len=model.prompt_len)
+    images, labels = synthetic_images(4, 64).cuda(), synthetic_labels(4, 5).cuda()
+    model.train(); other.train()
+    out_a = model(images, labels)
+    out_b = other(images, labels)                       # overwrites the saved activations of out_a's forward
+    with pytest.raises(Exception, match="stale backward"):
+        out_a["loss"].backward()
+    out_b["loss"].backward()                            # the latest forward is still differentiable
+    assert all(p.grad is not None for p in other.prompt_learner.parameters())
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "mixed"])
 def test_standard_encode_text_path(dtype):
     """CLIPWrapper.encode_text (clip_wrapper.py:49-51): positional embedding + causal mask + ln_final + EOT pooling."""
