@@ -151,17 +151,17 @@ TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
  *       xb[M,N] = x_out in the 16-bit `dtype` (dense) and stats[M][parts][2] = per-row partial (sum, sum of squares) of x_out,
  *       parts = tapclip_op_gemm_stats_parts(N).  ld 0 = dense.
  *   tapclip_op_gemm_fold  : out[M,N] (16-bit) = act(LayerNorm(x; gamma, beta).W^T + b) computed from the UN-normalised 16-bit rows xb,
- *       their statistics partials and the folded operands (w_fold = W diag(gamma), fold_s[n] = sum_k w_fold[n,k], bias_fold = b + W beta):
- *       LN(x) W^T + b = rstd (xb w_fold^T - mean fold_s) + bias_fold.  out_pre (nullable, needs act): pre-activation copy.
+ *       their statistics partials and the folded operands (w_fold = W diag(gamma) with every row centred -- the centring subtracts
+ *       the mean of x inside the contraction --, bias_fold = b + W beta):  LN(x) W^T + b = rstd (xb w_fold^T) + bias_fold.
+ *       out_pre (nullable, needs act): pre-activation copy.
  *   tapclip_op_fold_ln_weight / tapclip_op_row_stats_cast : build the folded operands / the (xb, stats) pair of arbitrary rows. */
 TAPCLIP_API int32_t tapclip_op_gemm_stats_parts(int64_t N);
 TAPCLIP_API int tapclip_op_gemm_resid(const void* a, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out,
                           int64_t ld_out, void* xb, float* stats, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream);
 TAPCLIP_API int tapclip_op_gemm_fold(const void* xb, const float* stats, int32_t stats_parts, const void* w_fold, const float* bias_fold,
-                         const float* fold_s, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int32_t dtype, int32_t act,
-                         void* stream);
+                         void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int32_t dtype, int32_t act, void* stream);
 TAPCLIP_API int tapclip_op_fold_ln_weight(const float* w, const float* bias, const float* gamma, const float* beta, void* w_fold,
-                              int32_t dtype, float* fold_s, float* bias_fold, int32_t N, int32_t K, void* stream);
+                              int32_t dtype, float* bias_fold, int32_t N, int32_t K, void* stream);
 TAPCLIP_API int tapclip_op_row_stats_cast(const float* x, void* xb, int32_t dtype, float* stats, int64_t rows, int32_t d, void* stream);
 
 /* Image preprocessing on the device: what `CLIPWrapper.get_preprocess()` (models/clip_wrapper.py:64-65,

@@ -156,7 +156,10 @@ class CLIPWrapper(nn.Module):
       dtype        'mixed' (default: tcgen05 tensor cores, bf16 operands in the image tower and the backward pass,
                    fp16 operands in the text-tower forward — meets the 1e-2 logit bar) | 'bf16' (bf16 operands
                    everywhere) | 'fp32' (SIMT parity mode, logits within 1e-4)
-      tokenizer    any ``str -> LongTensor[1,77]`` callable (e.g. open_clip's); default: SyntheticTokenizer
+      tokenizer    any ``str -> LongTensor[1,77]`` callable.  Default: with REAL weights (``pretrained_path`` / ``state_dict``) the
+                   reference's own ``open_clip.get_tokenizer(model_name)`` (clip_wrapper.py:27) -- and a RuntimeError if open_clip is
+                   not importable, because token ids from any other vocabulary make the class prompts meaningless; with random-init
+                   (synthetic / benchmark) weights the dependency-free SyntheticTokenizer.  Pass ``tokenizer="synthetic"`` to force it.
     """
 
     def __init__(self, model_name="ViT-B-32", pretrained_path=None, device="cuda", *, state_dict=None, seed=0,
@@ -185,7 +188,24 @@ class CLIPWrapper(nn.Module):
         self.sync_engine_weights()
         self.model.register_load_state_dict_post_hook(lambda module, incompatible: self.sync_engine_weights())
         self.attention_maps = []                                     # clip_wrapper.py:23
-        self.tokenizer = tokenizer or SyntheticTokenizer(cfg.context_length)   # clip_wrapper.py:27
+        self.tokenizer = self._pick_tokenizer(tokenizer, model_name, cfg, real_weights=state_dict is not None)   # clip_wrapper.py:27
+
+    @staticmethod
+    def _pick_tokenizer(tokenizer, model_name, cfg, real_weights):
+        if tokenizer == "synthetic":
+            return SyntheticTokenizer(cfg.context_length)
+        if tokenizer is not None:
+            return tokenizer
+        if not real_weights:
+            return SyntheticTokenizer(cfg.context_length)            # random-init weights: any consistent id assignment will do
+        try:
+            import open_clip                                         # the reference's tokenizer source (clip_wrapper.py:5,27)
+        except ImportError as e:
+            raise RuntimeError(
+                "CLIPWrapper was given real weights but no tokenizer, and open_clip (whose BPE vocabulary those weights were trained "
+                "with) is not importable. Pass tokenizer=<str -> LongTensor[1,77] callable> (e.g. open_clip.get_tokenizer(model_name)), "
+                "or tokenizer='synthetic' if hashed token ids are really what you want.") from e
+        return open_clip.get_tokenizer(model_name)
 
     def sync_engine_weights(self):
         self.engine.load_state_dict(self.model.state_dict())

@@ -166,22 +166,21 @@ TAPCLIP_API int tapclip_op_gemm_resid(const void* a, const void* w, const float*
 }
 
 TAPCLIP_API int tapclip_op_gemm_fold(const void* xb, const float* stats, int32_t stats_parts, const void* w_fold, const float* bias_fold,
-                         const float* fold_s, void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int32_t dtype, int32_t act,
-                         void* stream) {
+                         void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int32_t dtype, int32_t act, void* stream) {
     TC_API_BEGIN
     GemmArgs g;
     g.a = xb; g.w = w_fold; g.bias = bias_fold; g.out = out; g.out_pre = out_pre;
     g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = EPI_BF16; g.act = act; g.dt = dtype;
-    g.stats_in = stats; g.stats_parts = stats_parts; g.fold_s = fold_s;
+    g.stats_in = stats; g.stats_parts = stats_parts;
     TC_CHECK(stats != nullptr, "stats is required");
     gemm_tc(g, S(stream));
     TC_API_END
 }
 
 TAPCLIP_API int tapclip_op_fold_ln_weight(const float* w, const float* bias, const float* gamma, const float* beta, void* w_fold,
-                              int32_t dtype, float* fold_s, float* bias_fold, int32_t N, int32_t K, void* stream) {
+                              int32_t dtype, float* bias_fold, int32_t N, int32_t K, void* stream) {
     TC_API_BEGIN
-    fold_ln_weight(w, bias, gamma, beta, w_fold, dtype, fold_s, bias_fold, N, K, S(stream));
+    fold_ln_weight(w, bias, gamma, beta, w_fold, dtype, bias_fold, N, K, S(stream));
     TC_API_END
 }
 

@@ -253,11 +253,14 @@ __global__ void ce_rows_kernel(const float* __restrict__ logits, const int64_t* 
     for (int c = lane; c < C; c += 32) s += expf(row[c] - m);
     s = warp_sum(s);
     const float lse = m + logf(s);
-    const int label = (int)labels[b];
-    if (lane == 0) row_loss[b] = (lse - row[label]) * inv_batch_total;
+    // a label outside [0, C) (F.cross_entropy's ignore_index included) poisons the loss with NaN instead of reading out of bounds
+    const int64_t label = labels[b];
+    const bool ok = label >= 0 && label < C;
+    const float nan = __int_as_float(0x7fc00000);
+    if (lane == 0) row_loss[b] = ok ? (lse - row[label]) * inv_batch_total : nan;
     if (dlogits)
         for (int c = lane; c < C; c += 32)
-            dlogits[(int64_t)b * C + c] = (expf(row[c] - lse) - (c == label ? 1.f : 0.f)) * inv_batch_total;
+            dlogits[(int64_t)b * C + c] = ok ? (expf(row[c] - lse) - (c == label ? 1.f : 0.f)) * inv_batch_total : nan;
 }
 // deterministic single-block sum
 __global__ void sum_kernel(const float* __restrict__ v, float* __restrict__ out, int n) {

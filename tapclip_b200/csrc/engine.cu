@@ -96,7 +96,17 @@ std::vector<DevBuf*> Engine::all_bufs() {
     return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled, &v_roll_qkv, &v_lse, &v_roll,
             &t_x, &t_ln, &t_qkv, &t_attn, &t_h, &t_pooled, &t_feat, &t_tfeat, &t_inv_norm, &t_probe, &t_attr, &t_attr_raw,
             &t_save_x, &t_save_qkv, &t_save_h, &b_dx, &b_dxc, &b_dh, &b_dln, &b_dattn, &b_dqkv, &b_dfeat, &b_dfeatc, &b_dpool,
-            &s_rows, &s_cls, &e_eot, &e_pool, &v_xb, &v_stats, &v_xlive, &t_xb, &t_stats, &t_xlive};
+            &s_rows, &s_cls, &e_eot, &e_pool, &v_xb, &v_stats, &v_xlive, &t_xb, &t_stats, &t_xlive, &s_ticket};
+}
+
+// two self-resetting tickets of the head kernels' last-CTA reductions (zeroed once, synchronously, when first needed)
+int* Engine::tickets() {
+    if (s_ticket.p == nullptr) {
+        s_ticket.ensure(2 * sizeof(int));
+        TC_CUDA(cudaMemset(s_ticket.p, 0, 2 * sizeof(int)));
+        TC_CUDA(cudaDeviceSynchronize());
+    }
+    return (int*)s_ticket.p;
 }
 
 int64_t Engine::workspace_bytes() {
@@ -227,12 +237,11 @@ void Engine::fold_group(BlockWeights& b, int group, const std::string& prefix, i
         return p;
     };
     void* wf = alloc(key + ".w", (size_t)N * K * dtype_size(dt));
-    float* fs = (float*)alloc(key + ".s", (size_t)N * 4);
     float* fb = (float*)alloc(key + ".b", (size_t)N * 4);
-    fold_ln_weight(W, bias, gamma, beta, wf, dt, fs, fb, N, K, st);
+    fold_ln_weight(W, bias, gamma, beta, wf, dt, fb, N, K, st);
     ++launches;
-    if (group == 0) { b.wf_qkv = wf; b.fs_qkv = fs; b.fb_qkv = fb; }
-    else { b.wf_fc = wf; b.fs_fc = fs; b.fb_fc = fb; }
+    if (group == 0) { b.wf_qkv = wf; b.fb_qkv = fb; }
+    else { b.wf_fc = wf; b.fb_fc = fb; }
 }
 
 std::string Engine::missing_weights() const {
@@ -335,13 +344,13 @@ void Engine::attn_bwd(const void* qkv, const void* d_out, void* dqkv, int S, int
     ++launches;
 }
 
-void Engine::gemm_fold(const void* xb, const float* stats, int parts, const void* wf, const float* fb, const float* fs, void* out,
+void Engine::gemm_fold(const void* xb, const float* stats, int parts, const void* wf, const float* fb, void* out,
                        void* out_pre, int64_t M, int64_t N, int64_t K, int act, int dt, cudaStream_t st) {
-    TC_CHECK(wf && fb && fs, "folded LayerNorm weights are missing (load ln_*, in_proj_* and c_fc.* of every block)");
+    TC_CHECK(wf && fb, "folded LayerNorm weights are missing (load ln_*, in_proj_* and c_fc.* of every block)");
     GemmArgs g;
     g.a = xb; g.w = wf; g.bias = fb; g.out = out; g.out_pre = out_pre;
     g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = N; g.epi = EPI_BF16; g.act = act; g.dt = dt;
-    g.stats_in = stats; g.stats_parts = parts; g.fold_s = fs;
+    g.stats_in = stats; g.stats_parts = parts;
     ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, 6};
     if (profiling) prof_begin(r, st);
     gemm_tc(g, st);
@@ -419,7 +428,7 @@ void Engine::block_forward_fused(const BlockWeights& b, float*& x, int& parts, f
         shpre = (uint8_t*)t_save_h.p + (int64_t)save_slot * M * 4 * d * esz;
     }
     if (rollout_qkv) sqkv = rollout_qkv;
-    gemm_fold(xb.p, (const float*)stats.p, parts, b.wf_qkv, b.fb_qkv, b.fs_qkv, sqkv, nullptr, M, 3 * d, d, ACT_NONE, dt, st);
+    gemm_fold(xb.p, (const float*)stats.p, parts, b.wf_qkv, b.fb_qkv, sqkv, nullptr, M, 3 * d, d, ACT_NONE, dt, st);
     attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
     if (probs_only) return;
     if (live_row >= 0) {
@@ -438,7 +447,7 @@ void Engine::block_forward_fused(const BlockWeights& b, float*& x, int& parts, f
     float* x1 = sx1 ? sx1 : x;
     gemm_resid(attn.p, 0, b.w_o, b.b_o, x, d, x1, d, xb.p, (float*)stats.p, M, d, d, dt, st);
     parts = gemm_stats_parts(d);
-    gemm_fold(xb.p, (const float*)stats.p, parts, b.wf_fc, b.fb_fc, b.fs_fc, hbuf.p, shpre, M, 4 * d, d, cfg.act, dt, st);
+    gemm_fold(xb.p, (const float*)stats.p, parts, b.wf_fc, b.fb_fc, hbuf.p, shpre, M, 4 * d, d, cfg.act, dt, st);
     float* x2 = next_sx0 ? next_sx0 : (save_slot >= 0 ? scratch : x1);
     gemm_resid(hbuf.p, 0, b.w_proj, b.b_proj, x1, d, x2, d, xb.p, (float*)stats.p, M, d, 4 * d, dt, st);
     x = x2;
@@ -599,10 +608,15 @@ int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, i
     float* xp = (fused && save) ? (float*)t_save_x.p : x;
     splice_prompts(ctx, tok, attr, PA, xp, C, P, Lc, D, st); ++launches;
     run_blocks(xp, false, save, x_end, pool_stride, pool_offset);
-    gather_rows(x_end, t_pooled.p, tdt, C, pool_stride, pool_offset, D, st); ++launches;
-    gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, tdt, st);
-    l2norm_fwd((const float*)t_feat.p, (float*)t_tfeat.p, (float*)t_inv_norm.p, C, E, st); ++launches;
-    if (out_text_feat) TC_CUDA(cudaMemcpyAsync(out_text_feat, t_tfeat.p, (size_t)C * E * 4, cudaMemcpyDeviceToDevice, st));
+    if (fuse_head) {
+        // K4 (head.cu): pool position T-1, @ text_projection, L2-normalise -- one launch, fp32 rows against the 16-bit weight
+        text_head(x_end, pool_stride, pool_offset, w_tproj, tdt, (float*)t_tfeat.p, (float*)t_inv_norm.p, out_text_feat, C, D, E, st); ++launches;
+    } else {
+        gather_rows(x_end, t_pooled.p, tdt, C, pool_stride, pool_offset, D, st); ++launches;
+        gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, tdt, st);
+        l2norm_fwd((const float*)t_feat.p, (float*)t_tfeat.p, (float*)t_inv_norm.p, C, E, st); ++launches;
+        if (out_text_feat) TC_CUDA(cudaMemcpyAsync(out_text_feat, t_tfeat.p, (size_t)C * E * 4, cudaMemcpyDeviceToDevice, st));
+    }
     if (save) {
         saved.valid = true; saved.C = C; saved.P = P; saved.T = T; saved.PA = PA; saved.has_attr = (mode == 1); saved.dead_last = dead_rows;
         saved.token = ++forward_seq;
@@ -661,12 +675,17 @@ void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream
     b_dfeat.ensure((int64_t)C * E * 4);
     b_dfeatc.ensure((int64_t)C * E * esz);
     b_dpool.ensure((int64_t)C * D * 4);
-    // L2-norm and projection backward (model_wrapper.py:74-75), then scatter into the last position (:73)
-    l2norm_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, (float*)b_dfeat.p, b_dfeatc.p, gdt, C, E, st); ++launches;
-    gemm(b_dfeatc.p, wt_tproj, nullptr, b_dpool.p, nullptr, C, D, E, EPI_F32, ACT_NONE, gdt, st);
+    // L2-norm and projection backward (model_wrapper.py:74-75), scattered into the last position (:73)
     TC_CUDA(cudaMemsetAsync(b_dx.p, 0, (size_t)M * D * 4, st));
     TC_CUDA(cudaMemsetAsync(b_dxc.p, 0, (size_t)M * D * esz, st));
-    scatter_rows((const float*)b_dpool.p, (float*)b_dx.p, b_dxc.p, gdt, C, T, T - 1, D, st); ++launches;
+    if (fuse_head) {
+        text_head_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, wt_tproj, gdt, (float*)b_dx.p, b_dxc.p, gdt, T, T - 1,
+                      C, D, E, st); ++launches;
+    } else {
+        l2norm_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, (float*)b_dfeat.p, b_dfeatc.p, gdt, C, E, st); ++launches;
+        gemm(b_dfeatc.p, wt_tproj, nullptr, b_dpool.p, nullptr, C, D, E, EPI_F32, ACT_NONE, gdt, st);
+        scatter_rows((const float*)b_dpool.p, (float*)b_dx.p, b_dxc.p, gdt, C, T, T - 1, D, st); ++launches;
+    }
     for (int l = L - 1; l >= 0; --l) {
         const BlockWeights& b = txt[l];
         const float* x0 = (const float*)t_save_x.p + (int64_t)(2 * l) * M * D;
@@ -721,6 +740,15 @@ void Engine::logits(const float* img_feat, const float* text_feat, const float* 
                     cudaStream_t st) {
     if (B == 0 || C == 0) return;
     const int E = cfg.embed_dim;
+    if (labels) TC_CHECK(out_loss != nullptr, "out_loss is required when labels are given");
+    if (fuse_head && (size_t)(E + C + 32) * sizeof(float) <= 48 * 1024) {
+        // K4 (head.cu): image L2-norm, logits, cross-entropy, its gradient and the batch mean in ONE launch
+        s_rows.ensure((size_t)B * 4);
+        logits_ce(img_feat, text_feat, logit_scale, labels, out_img_norm, out_logits, out_loss, out_dlogits, (float*)s_rows.p, tickets(),
+                  B, C, E, inv_batch_total, st);
+        ++launches;
+        return;
+    }
     l2norm_fwd(img_feat, out_img_norm, nullptr, B, E, st); ++launches;
     cosine_logits(out_img_norm, text_feat, logit_scale, out_logits, B, C, E, st); ++launches;
     if (labels) {
@@ -734,6 +762,11 @@ void Engine::logits_backward(const float* dlogits, const float* logits_, const f
                              int C, float* out_d_text, float* out_d_scale, cudaStream_t st) {
     if (C == 0) return;
     s_cls.ensure((size_t)C * 4);
+    if (fuse_head && (size_t)(B + 32) * sizeof(float) <= 48 * 1024) {
+        logits_bwd_fused(dlogits, logits_, img_norm, logit_scale, out_d_text, out_d_scale, (float*)s_cls.p, tickets() + 1, B, C, cfg.embed_dim, st);
+        ++launches;
+        return;
+    }
     logits_bwd(dlogits, logits_, img_norm, logit_scale, out_d_text, out_d_scale, (float*)s_cls.p, B, C, cfg.embed_dim, st);
     launches += 2;
 }

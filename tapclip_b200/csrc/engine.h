@@ -23,11 +23,11 @@ struct BlockWeights {
     float *b_qkv = nullptr, *b_o = nullptr, *b_fc = nullptr, *b_proj = nullptr;
     void *w_qkv = nullptr, *w_o = nullptr, *w_fc = nullptr, *w_proj = nullptr;        // [N,K], activation type
     void *wt_qkv = nullptr, *wt_o = nullptr, *wt_fc = nullptr, *wt_proj = nullptr;    // [K,N] dgrad operands (text tower)
-    // LayerNorm folded into the consumer GEMM (16-bit modes; gemm.h GemmArgs::stats_in): W' = W diag(gamma) in the operand type,
-    // s[n] = sum_k W'[n,k], b' = b + W beta; built from fp32 copies of W as soon as W, b, gamma and beta of a group are loaded
+    // LayerNorm folded into the consumer GEMM (16-bit modes; gemm.h GemmArgs::stats_in): W" = W diag(gamma), rows centred, in the
+    // operand type; b' = b + W beta; built from fp32 copies of W as soon as W, b, gamma and beta of a group are loaded
     float *f32_qkv = nullptr, *f32_fc = nullptr;
     void *wf_qkv = nullptr, *wf_fc = nullptr;
-    float *fs_qkv = nullptr, *fb_qkv = nullptr, *fs_fc = nullptr, *fb_fc = nullptr;
+    float *fb_qkv = nullptr, *fb_fc = nullptr;
 };
 
 struct Engine {
@@ -52,7 +52,10 @@ struct Engine {
     DevBuf v_xb, v_stats, v_xlive, t_xb, t_stats, t_xlive;      // folded-LayerNorm path: 16-bit residual copy, row statistics, live rows of the last block
     DevBuf t_save_x, t_save_qkv, t_save_h;
     DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
-    DevBuf s_rows, s_cls, e_eot, e_pool;
+    DevBuf s_rows, s_cls, s_ticket, e_eot, e_pool;
+    int* tickets();
+    // TAPCLIP_FUSE_HEAD=0: the head (pool + projection + L2-norm, logits + CE, their backward) as separate launches (A/B parity)
+    bool fuse_head = !(getenv("TAPCLIP_FUSE_HEAD") && atoi(getenv("TAPCLIP_FUSE_HEAD")) == 0);
     // activations kept by text_forward(save) for text_backward; `token` identifies the forward that wrote them (a later
     // text_forward / encode_text on this handle overwrites the slot: its backward must then fail, not use the wrong tensors)
     struct { bool valid = false; int C = 0, P = 0, T = 0, PA = 1; bool has_attr = false; bool dead_last = false; int64_t token = 0; } saved;
@@ -92,7 +95,7 @@ struct Engine {
     void block_forward_fused(const BlockWeights& b, float*& x, int& parts, float* scratch, int S, int N, int d, int H, int dt, DevBuf& xb,
                              DevBuf& stats, DevBuf& xlive, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf, const AttnProbe& probe,
                              bool probs_only, int save_slot, bool has_next, cudaStream_t st, void* rollout_qkv = nullptr, int live_row = -1);
-    void gemm_fold(const void* xb, const float* stats, int parts, const void* wf, const float* fb, const float* fs, void* out, void* out_pre,
+    void gemm_fold(const void* xb, const float* stats, int parts, const void* wf, const float* fb, void* out, void* out_pre,
                    int64_t M, int64_t N, int64_t K, int act, int dt, cudaStream_t st);
     void gemm_resid(const void* a, int64_t lda, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out, int64_t ldo,
                     void* xb, float* stats, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st);

@@ -35,12 +35,11 @@ struct GemmArgs {
     int64_t ld_in = 0;
     void* xb = nullptr;                // optional: 16-bit copy (type dt) of the updated rows, dense [M, N]
     float* stats_out = nullptr;        // optional: [M][gemm_stats_parts(N)][2] partial (sum, sum of squares) of the updated rows
-    // LayerNorm folded into the GEMM (EPI_BF16 only): A holds the UN-normalised rows x in 16 bits, W the gamma-scaled weight
-    // W' = W * diag(gamma), bias the folded bias b' = b + W beta, fold_s[n] = sum_k W'[n,k]; with the row statistics
-    // (mean, rstd) recovered from stats_in the epilogue forms  LN(x) W^T + b = rstd * (x W'^T - mean * s) + b'.
+    // LayerNorm folded into the GEMM (EPI_BF16 only): A holds the UN-normalised rows x in 16 bits, W the gamma-scaled and
+    // row-centred weight W" = W diag(gamma) - rowmean(W diag(gamma)) (so x W"^T = (x - mean(x)) (W diag(gamma))^T), bias the folded
+    // bias b' = b + W beta; with rstd recovered from stats_in the epilogue forms  LN(x) W^T + b = rstd * (x W"^T) + b'.
     const float* stats_in = nullptr;   // [M][stats_parts][2] partial (sum, sum of squares) over the K elements of each row of A
     int stats_parts = 0;
-    const float* fold_s = nullptr;     // [N]
 };
 // number of (sum, sum of squares) partials per row an EPI_F32_RESID GEMM with N output columns writes (2 per n-tile)
 int gemm_stats_parts(int64_t N);

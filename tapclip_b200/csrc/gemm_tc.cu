@@ -22,8 +22,10 @@
 //   EPI_F32_RESID  the residual update x_new = x_old + A W^T + b also writes x_new in the 16-bit operand type and per-row
 //                  partial (sum, sum of squares) of x_new (one pair per n-tile and epilogue-warp parity: written, never
 //                  accumulated, so there is no zeroing pass and the result is deterministic);
-//   FOLD           the consumer GEMM multiplies the UN-normalised 16-bit rows with W' = W diag(gamma) and applies
-//                  LN(x) W^T + b = rstd (x W'^T - mean s) + b'  per row in its epilogue (s = row sums of W', b' = b + W beta).
+//   FOLD           the consumer GEMM multiplies the UN-normalised 16-bit rows with the gamma-scaled, row-centred weight
+//                  W" = W diag(gamma) - (row mean of W diag(gamma)) -- centring the weight rows subtracts the mean of x inside the
+//                  contraction -- and applies  LN(x) W^T + b = rstd (x W"^T) + b'  per row in its epilogue (b' = b + W beta):
+//                  one FMA per element, the cost of a plain bias add.
 //
 // Two tile shapes:
 //   CTA2 = false  cta_group::1, UMMA 128 x BLOCK_N x 16, one CTA per tile (48 KB of operands per k-block).
@@ -55,11 +57,10 @@ template <int BLOCK_N, bool CTA2> struct Cfg {
     static constexpr int STAGE_BYTES = STAGE_A_BYTES + STAGE_B_BYTES;
     static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;            // 4 (48 KB), 6 (32 KB), 8 (24 KB)
     static constexpr int TMEM_COLS = 2 * BLOCK_N;
-    // barriers (ring, TMEM, scheduler ring) + scheduler tiles + TMEM slot: 256 B; bias tile and fold_s tile: 2 x BLOCK_N floats
-    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 2 * BLOCK_N * 4;
-    // the dynamic shared memory window starts 1024-byte aligned in practice (no static shared memory in this kernel); 768 B of
-    // slack cover any base that is at least 256-byte aligned, and the kernel traps if the carve-up would not fit
-    static constexpr int SMEM_BYTES = SMEM_USED + 768;
+    // barriers (ring, TMEM, scheduler ring) + scheduler tiles + TMEM slot: 256 B; bias tile: BLOCK_N floats
+    static constexpr int SMEM_USED = STAGES * STAGE_BYTES + EPI_BYTES + 256 + BLOCK_N * 4;
+    // 1024 B of slack for the manual 1024-byte alignment of the carve-up (the kernel traps if it would not fit)
+    static constexpr int SMEM_BYTES = SMEM_USED + 1024;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert((2 * STAGES + 4 + 2 * 4) * 8 + 4 * 4 + 4 <= 256, "barrier region");
 };
@@ -69,7 +70,7 @@ constexpr int SCHED_DEPTH = 4;
 struct GemmExtra {
     const float* resid_in; int ld_in;      // EPI_F32_RESID
     void* xb; float* stats_out;
-    const float* stats_in; int stats_parts; const float* fold_s;      // FOLD
+    const float* stats_in; int stats_parts;      // FOLD
     int* sched;                            // {next tile, finished CTAs} or null (static tile order)
 };
 
@@ -138,7 +139,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int* sched_tile = reinterpret_cast<int*>(sched_empty + SCHED_DEPTH);
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(sched_tile + SCHED_DEPTH);
     float* bias_s = reinterpret_cast<float*>(smem_epi + EPI_BYTES + 256);      // bias of the current tile, shared by the epilogue warps
-    float* fold_s_s = bias_s + BLOCK_N;                                        // FOLD: row sums of W' for the tile's columns
 
     // warp index (and below the TMEM base) come out of shuffles so that ptxas knows they are warp-uniform
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -316,16 +316,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (col < N) b = __ldg(reinterpret_cast<const float4*>(bias + col));
                     *reinterpret_cast<float4*>(bias_s + et * 4) = b;
-                } else if (FOLD && et < BLOCK_N / 2) {
-                    const int e2 = et - BLOCK_N / 4, col = n0 + e2 * 4;
-                    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (col < N) b = __ldg(reinterpret_cast<const float4*>(ex.fold_s + col));
-                    *reinterpret_cast<float4*>(fold_s_s + e2 * 4) = b;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
             }
-            // FOLD: this thread's row statistics -> out = fa * acc + (fb * s[n] + b'[n]),  fa = rstd, fb = -mean * rstd
-            float fa = 1.f, fb = 0.f;
+            // FOLD: this thread's row statistics -> out = fa * acc + b'[n],  fa = rstd (the mean is subtracted by the centred weight)
+            float fa = 1.f;
             if constexpr (FOLD) {
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -340,7 +335,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const float inv_k = 1.0f / (float)K;
                 const float mean = s1 * inv_k;
                 fa = rsqrtf(fmaxf(s2 * inv_k - mean * mean, 0.f) + 1e-5f);
-                fb = -mean * fa;
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
             if constexpr (RESID) {
@@ -474,9 +468,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < CH; j += 4) {
                         const float4 b = *reinterpret_cast<const float4*>(bias_s + c * CH + j);   // smem broadcast
-                        const float4 s = *reinterpret_cast<const float4*>(fold_s_s + c * CH + j);
-                        v[j] = fmaf(fa, v[j], fmaf(fb, s.x, b.x)); v[j + 1] = fmaf(fa, v[j + 1], fmaf(fb, s.y, b.y));
-                        v[j + 2] = fmaf(fa, v[j + 2], fmaf(fb, s.z, b.z)); v[j + 3] = fmaf(fa, v[j + 3], fmaf(fb, s.w, b.w));
+                        v[j] = fmaf(fa, v[j], b.x); v[j + 1] = fmaf(fa, v[j + 1], b.y);
+                        v[j + 2] = fmaf(fa, v[j + 2], b.z); v[j + 3] = fmaf(fa, v[j + 3], b.w);
                     }
                 } else if (bias != nullptr) {
 #pragma unroll
@@ -693,9 +686,9 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
         ex.resid_in = g.resid_in; ex.ld_in = (int)g.ld_in; ex.xb = g.xb; ex.stats_out = g.stats_out;
     }
     if (FOLD) {
-        TC_CHECK(g.stats_in != nullptr && g.stats_parts >= 1 && g.fold_s != nullptr && g.bias != nullptr, "folded-LayerNorm GEMM needs stats_in, fold_s and the folded bias");
-        TC_CHECK((reinterpret_cast<uintptr_t>(g.stats_in) & 7) == 0 && (reinterpret_cast<uintptr_t>(g.fold_s) & 15) == 0, "stats_in / fold_s alignment");
-        ex.stats_in = g.stats_in; ex.stats_parts = g.stats_parts; ex.fold_s = g.fold_s;
+        TC_CHECK(g.stats_in != nullptr && g.stats_parts >= 1 && g.bias != nullptr, "folded-LayerNorm GEMM needs stats_in and the folded bias");
+        TC_CHECK((reinterpret_cast<uintptr_t>(g.stats_in) & 7) == 0, "stats_in alignment");
+        ex.stats_in = g.stats_in; ex.stats_parts = g.stats_parts;
     }
     if (g.bias) TC_CHECK((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "bias must be 16-byte aligned");
     if (CTA2) {

@@ -20,9 +20,9 @@ void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos,
 // (gemm.h, GemmArgs::stats_in with stats_parts = 1) for rows that no EPI_F32_RESID GEMM produced
 void row_stats_cast(const float* x, void* xb, int xb_dt, float* stats, int64_t rows, int d, cudaStream_t stream);
 // LayerNorm(gamma, beta) followed by Linear(W [N,K], bias) folded into one GEMM over the un-normalised rows (gemm.h):
-// Wf = W diag(gamma) in the 16-bit type dt, fs[n] = sum_k Wf[n,k] (of the rounded values), fb = bias + W beta
-void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, void* Wf, int dt, float* fs, float* fb,
-                    int N, int K, cudaStream_t stream);
+// Wf = W diag(gamma) with every row centred (its mean over k subtracted), in the 16-bit type dt;  fb = bias + W beta
+void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, void* Wf, int dt, float* fb, int N, int K,
+                    cudaStream_t stream);
 // dx_acc[r,:] += LN'(dy[r,:]; x[r,:], gamma)  (mean/rstd recomputed from x);  dx_cast (optional, activation
 // type) receives the updated dx_acc row cast to the activation type.
 // dy and x are dense [rows, d]; dx_acc / dx_cast rows are dx_row_stride elements apart (0 = dense).
@@ -33,6 +33,22 @@ void l2norm_fwd(const float* x, float* out, float* inv_norm, int64_t rows, int d
 // dx = (g - xhat * <xhat, g>) * inv_norm ; optional cast copy in the activation type
 void l2norm_bwd(const float* g, const float* xhat, const float* inv_norm, float* dx, void* dx_cast, int cast_dt,
                 int64_t rows, int d, cudaStream_t stream);
+
+// ---- head.cu (K4) ------------------------------------------------------------------------------------
+// tfeat[c,:] = l2norm(x[(c*row_stride + row_offset),:] @ w_proj^T), w_proj [E,D] of type w_dt; inv_norm[c] = 1/||.||;
+// tfeat_copy (optional) receives the same rows (the caller's output tensor)
+void text_head(const float* x, int64_t row_stride, int64_t row_offset, const void* w_proj, int w_dt, float* tfeat, float* inv_norm,
+               float* tfeat_copy, int C, int D, int E, cudaStream_t stream);
+// backward of text_head: dx[(c*row_stride + row_offset),:] = l2norm'(g[c,:]) @ wt_proj^T (wt_proj [D,E], gradient type) + 16-bit copy
+void text_head_bwd(const float* g, const float* tfeat, const float* inv_norm, const void* wt_proj, int w_dt, float* dx, void* dx_cast,
+                   int cast_dt, int64_t row_stride, int64_t row_offset, int C, int D, int E, cudaStream_t stream);
+// img_norm = l2norm(img); logits = exp(*logit_scale) * img_norm . txt^T; with labels: loss[0] = sum_b CE_b * inv_batch_total (summed
+// by the last CTA in row order), dlogits = dloss/dlogits.  row_scratch [B] floats, ticket: one int, zero before the first use
+void logits_ce(const float* img, const float* txt, const float* logit_scale, const int64_t* labels, float* img_norm, float* logits,
+               float* loss, float* dlogits, float* row_scratch, int* ticket, int B, int C, int E, float inv_batch_total, cudaStream_t stream);
+// d_txt[c,:] = exp(s) * sum_b dlogits[b,c] * img[b,:];  d_scale[0] = sum dlogits * logits.  class_scratch [C] floats, ticket as above
+void logits_bwd_fused(const float* dlogits, const float* logits, const float* img, const float* logit_scale, float* d_txt, float* d_scale,
+                      float* class_scratch, int* ticket, int B, int C, int E, cudaStream_t stream);
 
 // ---- attention.cu ----------------------------------------------------------------------------------
 enum ProbeMode : int { PROBE_NONE = 0, PROBE_TEXT_COL = 1, PROBE_CLS_ROW = 2 };

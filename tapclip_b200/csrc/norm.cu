@@ -269,25 +269,24 @@ l2norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ xhat, c
 }
 
 // LayerNorm folded into a Linear (gemm.h, GemmArgs::stats_in): one warp per output row n of W [N,K]:
-//   Wf[n,k] = T(W[n,k] * gamma[k]),  fs[n] = sum_k float(Wf[n,k])  (of the ROUNDED values: the mean term must cancel what the
-//   tensor cores accumulate),  fb[n] = bias[n] + sum_k W[n,k] * beta[k]
+//   Wf[n,k] = T(W[n,k] * gamma[k] - m_n),  m_n = (1/K) sum_k W[n,k] * gamma[k]   (row-centred: x Wf^T = (x - mean x)(W diag gamma)^T)
+//   fb[n]   = bias[n] + sum_k W[n,k] * beta[k]
 template <typename T>
 __global__ void fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, T* __restrict__ Wf, float* __restrict__ fs, float* __restrict__ fb,
-                                      int N, int K) {
+                                      const float* __restrict__ beta, T* __restrict__ Wf, float* __restrict__ fb, int N, int K) {
     pdl_wait_and_trigger();
     const int n = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
     float s = 0.f, bb = 0.f;
     for (int k = lane; k < K; k += 32) {
         const float w = W[(int64_t)n * K + k];
-        const T wf = from_f32<T>(w * gamma[k]);
-        Wf[(int64_t)n * K + k] = wf;
-        s += to_f32<T>(wf);
+        s += w * gamma[k];
         bb += w * beta[k];
     }
     s = warp_sum(s); bb = warp_sum(bb);
-    if (lane == 0) { fs[n] = s; fb[n] = (bias ? bias[n] : 0.f) + bb; }
+    const float m = s / (float)K;
+    for (int k = lane; k < K; k += 32) Wf[(int64_t)n * K + k] = from_f32<T>(W[(int64_t)n * K + k] * gamma[k] - m);
+    if (lane == 0) fb[n] = (bias ? bias[n] : 0.f) + bb;
 }
 
 void check_d(int d) { TC_CHECK(d % 128 == 0 && d >= 128 && d <= 128 * MAXV, "row width %d unsupported (need d %% 128 == 0, d <= 1024)", d); }
@@ -316,12 +315,12 @@ void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos,
     TC_LAUNCH_CHECK();
 }
 
-void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, void* Wf, int dt, float* fs, float* fb,
-                    int N, int K, cudaStream_t stream) {
+void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, void* Wf, int dt, float* fb, int N, int K,
+                    cudaStream_t stream) {
     TC_CHECK(dt == DT_BF16 || dt == DT_F16, "folded weights are 16-bit operands");
     const unsigned grid = (unsigned)ceil_div((int64_t)N * 32, 256);
-    if (dt == DT_F16) launch_pdl(fold_ln_weight_kernel<f16>, grid, 256, 0, stream, W, bias, gamma, beta, (f16*)Wf, fs, fb, N, K);
-    else launch_pdl(fold_ln_weight_kernel<bf16>, grid, 256, 0, stream, W, bias, gamma, beta, (bf16*)Wf, fs, fb, N, K);
+    if (dt == DT_F16) launch_pdl(fold_ln_weight_kernel<f16>, grid, 256, 0, stream, W, bias, gamma, beta, (f16*)Wf, fb, N, K);
+    else launch_pdl(fold_ln_weight_kernel<bf16>, grid, 256, 0, stream, W, bias, gamma, beta, (bf16*)Wf, fb, N, K);
     TC_LAUNCH_CHECK();
 }
 

@@ -25,7 +25,8 @@ def build_oracle(model_name, C_, P, mode, seed=0, method="scale"):
 def build_cuda(model_name, C_, P, mode, dtype, oracle_wrapper, method="scale"):
     """tapclip_b200 model with the oracle's weights and the same ctx (+ adjustor) draw (global CPU RNG, seed 4)."""
     import tapclip_b200 as tb
-    clip = tb.CLIPWrapper(model_name, None, "cuda", state_dict=oracle_wrapper.model.state_dict(), attribution=mode, dtype=dtype)
+    clip = tb.CLIPWrapper(model_name, None, "cuda", state_dict=oracle_wrapper.model.state_dict(), attribution=mode, dtype=dtype,
+                          tokenizer="synthetic")      # the oracle's weights are random-init: same hashed ids on both sides
     torch.manual_seed(CTX_SEED)
     model = tb.FullModel(class_names(C_), clip, prompt_len=P, adjustor_method=method)
     return clip, model

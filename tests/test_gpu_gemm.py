@@ -189,15 +189,16 @@ def test_gemm_residual_statistics_and_folded_layernorm(M, N, K, N2, act, dtype):
     assert torch.equal(x_inplace, x1) and torch.equal(stats2, stats)
     # folded consumer
     wf = torch.empty(N2, N, device="cuda", dtype=tdt)
-    fs = torch.empty(N2, device="cuda")
     fb = torch.empty(N2, device="cuda")
     _lib.check(lib.tapclip_op_fold_ln_weight(_lib.ptr(w2), _lib.ptr(b2), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(wf), _lib.DTYPE[dtype],
-                                             _lib.ptr(fs), _lib.ptr(fb), N2, N, _lib.stream_ptr()))
-    assert torch.equal(wf, (w2 * gamma).to(tdt))
-    assert (fs - wf.float().sum(1)).abs().max().item() < 1e-3 and (fb - (b2 + w2 @ beta)).abs().max().item() < 1e-4
+                                             _lib.ptr(fb), N2, N, _lib.stream_ptr()))
+    wg = w2 * gamma
+    assert (wf.float() - (wg - wg.mean(1, keepdim=True))).abs().max().item() < (2e-2 if dtype == "bf16" else 2e-3)   # one rounding
+    assert wf.float().sum(1).abs().max().item() < 0.3                       # rows are centred (up to the rounding of N entries)
+    assert (fb - (b2 + w2 @ beta)).abs().max().item() < 1e-4
     out = torch.empty(M, N2, device="cuda", dtype=tdt)
     pre = torch.empty(M, N2, device="cuda", dtype=tdt) if act >= 0 else None
-    _lib.check(lib.tapclip_op_gemm_fold(_lib.ptr(xb), _lib.ptr(stats), parts, _lib.ptr(wf), _lib.ptr(fb), _lib.ptr(fs), _lib.ptr(out), _lib.ptr(pre),
+    _lib.check(lib.tapclip_op_gemm_fold(_lib.ptr(xb), _lib.ptr(stats), parts, _lib.ptr(wf), _lib.ptr(fb), _lib.ptr(out), _lib.ptr(pre),
                                         M, N2, N, _lib.DTYPE[dtype], act, _lib.stream_ptr()))
     torch.cuda.synchronize()
     ln_ref = torch.nn.functional.layer_norm(x_ref, (N,), gamma, beta, 1e-5)
@@ -214,7 +215,7 @@ def test_gemm_residual_statistics_and_folded_layernorm(M, N, K, N2, act, dtype):
     st0 = torch.empty(M, 1, 2, device="cuda")
     _lib.check(lib.tapclip_op_row_stats_cast(_lib.ptr(x_ref), _lib.ptr(xb0), _lib.DTYPE[dtype], _lib.ptr(st0), M, N, _lib.stream_ptr()))
     out0 = torch.empty(M, N2, device="cuda", dtype=tdt)
-    _lib.check(lib.tapclip_op_gemm_fold(_lib.ptr(xb0), _lib.ptr(st0), 1, _lib.ptr(wf), _lib.ptr(fb), _lib.ptr(fs), _lib.ptr(out0), None,
+    _lib.check(lib.tapclip_op_gemm_fold(_lib.ptr(xb0), _lib.ptr(st0), 1, _lib.ptr(wf), _lib.ptr(fb), _lib.ptr(out0), None,
                                         M, N2, N, _lib.DTYPE[dtype], act, _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert (out0.float() - ref).abs().max().item() < tol

@@ -35,6 +35,24 @@ def test_tokenizer_contract():
     assert a(["x", "y z"]).shape == (2, 77)
 
 
+def test_tokenizer_choice_follows_the_weights():
+    """Real weights need the vocabulary they were trained with (the reference always uses open_clip.get_tokenizer,
+    clip_wrapper.py:27): without open_clip and without an explicit tokenizer the wrapper refuses instead of hashing words."""
+    from tapclip_b200.clip_wrapper import CLIPWrapper
+    from tapclip_b200.configs import get_model_config
+    from tapclip_b200.tokenizer import SyntheticTokenizer
+    cfg = get_model_config("mini-16")
+    assert isinstance(CLIPWrapper._pick_tokenizer(None, "mini-16", cfg, real_weights=False), SyntheticTokenizer)
+    assert isinstance(CLIPWrapper._pick_tokenizer("synthetic", "mini-16", cfg, real_weights=True), SyntheticTokenizer)
+    mine = lambda s: torch.zeros(1, 77, dtype=torch.long)
+    assert CLIPWrapper._pick_tokenizer(mine, "mini-16", cfg, real_weights=True) is mine
+    try:
+        import open_clip  # noqa: F401
+    except ImportError:
+        with pytest.raises(RuntimeError, match="open_clip"):
+            CLIPWrapper._pick_tokenizer(None, "ViT-B-16", cfg, real_weights=True)
+
+
 def _models(case, mode):
     import tapclip_b200 as tb
     gold = load_golden(case, mode)

@@ -52,9 +52,9 @@ for tag, M, d, dt_name in (("image tower (B=128)", 25216, 768, "bf16"), ("text t
     bq, bo, bf_, bp = (torch.randn(n, device=dev) * 0.1 for n in (3 * d, d, 4 * d, d))
 
     def fold(w, b):
-        wf = torch.empty_like(w, dtype=tdt); fs = torch.empty(w.shape[0], device=dev); fb = torch.empty(w.shape[0], device=dev)
-        _lib.check(lib.tapclip_op_fold_ln_weight(P(w), P(b), P(g1), P(b1), P(wf), DT, P(fs), P(fb), w.shape[0], w.shape[1], S()))
-        return wf, fs, fb
+        wf = torch.empty_like(w, dtype=tdt); fb = torch.empty(w.shape[0], device=dev)
+        _lib.check(lib.tapclip_op_fold_ln_weight(P(w), P(b), P(g1), P(b1), P(wf), DT, P(fb), w.shape[0], w.shape[1], S()))
+        return wf, fb
     fq, ff = fold(w_qkv, bq), fold(w_fc, bf_)
 
     def gemm(a, w, b, out, Mm, N, K, epi, act):
@@ -67,7 +67,7 @@ for tag, M, d, dt_name in (("image tower (B=128)", 25216, 768, "bf16"), ("text t
         _lib.check(lib.tapclip_op_gemm_resid(P(a), P(w), P(b), P(x), 0, P(x), 0, P(xb), P(stats), M, d, K, DT, S()))
 
     def foldg(f, out, N, act):
-        _lib.check(lib.tapclip_op_gemm_fold(P(xb), P(stats), parts, P(f[0]), P(f[2]), P(f[1]), P(out), None, M, N, d, DT, act, S()))
+        _lib.check(lib.tapclip_op_gemm_fold(P(xb), P(stats), parts, P(f[0]), P(f[1]), P(out), None, M, N, d, DT, act, S()))
 
     resid(attn, wo16, bo, d)          # valid statistics for the folded GEMMs
     rows = [
