@@ -148,8 +148,10 @@ TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
  * `x = x + mlp(ln_2(x))` of open_clip's ResidualAttentionBlock (invoked from models/model_wrapper.py:58,72 and
  * models/clip_wrapper.py:47).
  *   tapclip_op_gemm_resid : x_out[M,N] (fp32, ld_out) = x_in[M,N] (fp32, ld_in; may alias x_out) + A[M,K].W[N,K]^T + bias; optionally
- *       xb[M,N] = x_out in the 16-bit `dtype` (dense) and stats[M][parts][2] = per-row partial (sum, sum of squares) of x_out,
- *       parts = tapclip_op_gemm_stats_parts(N).  ld 0 = dense.
+ *       xb[M,N] = x_out - shift in the 16-bit `dtype` (dense), stats[M][parts][2] = per-row partial (sum, sum of squares) of the
+ *       shifted rows (parts = tapclip_op_gemm_stats_parts(N)) and shift[M] = the per-row shift: the mean of the row of x_in,
+ *       recovered from the statistics describing x_in (stats_prev [M][prev_parts][2] + shift_prev [M]; null: shift 0).  LayerNorm is
+ *       invariant to the shift; it keeps the rounded 16-bit values centred.  ld 0 = dense; N % 128 == 0.
  *   tapclip_op_gemm_fold  : out[M,N] (16-bit) = act(LayerNorm(x; gamma, beta).W^T + b) computed from the UN-normalised 16-bit rows xb,
  *       their statistics partials and the folded operands (w_fold = W diag(gamma) with every row centred -- the centring subtracts
  *       the mean of x inside the contraction --, bias_fold = b + W beta):  LN(x) W^T + b = rstd (xb w_fold^T) + bias_fold.
@@ -157,12 +159,14 @@ TAPCLIP_API const char* tapclip_profile_report(tapclip_handle h);
  *   tapclip_op_fold_ln_weight / tapclip_op_row_stats_cast : build the folded operands / the (xb, stats) pair of arbitrary rows. */
 TAPCLIP_API int32_t tapclip_op_gemm_stats_parts(int64_t N);
 TAPCLIP_API int tapclip_op_gemm_resid(const void* a, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out,
-                          int64_t ld_out, void* xb, float* stats, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream);
+                          int64_t ld_out, void* xb, float* stats, float* shift, const float* stats_prev, const float* shift_prev,
+                          int32_t prev_parts, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream);
 TAPCLIP_API int tapclip_op_gemm_fold(const void* xb, const float* stats, int32_t stats_parts, const void* w_fold, const float* bias_fold,
                          void* out, void* out_pre, int64_t M, int64_t N, int64_t K, int32_t dtype, int32_t act, void* stream);
 TAPCLIP_API int tapclip_op_fold_ln_weight(const float* w, const float* bias, const float* gamma, const float* beta, void* w_fold,
                               int32_t dtype, float* bias_fold, int32_t N, int32_t K, void* stream);
-TAPCLIP_API int tapclip_op_row_stats_cast(const float* x, void* xb, int32_t dtype, float* stats, int64_t rows, int32_t d, void* stream);
+TAPCLIP_API int tapclip_op_row_stats_cast(const float* x, void* xb, int32_t dtype, float* stats, float* shift, int64_t rows, int32_t d,
+                              void* stream);
 
 /* Image preprocessing on the device: what `CLIPWrapper.get_preprocess()` (models/clip_wrapper.py:64-65,
  * open_clip's inference transform, applied per image at dataset.py:31) does on the host with Pillow/torchvision:

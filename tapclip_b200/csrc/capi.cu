@@ -155,12 +155,14 @@ TAPCLIP_API int tapclip_op_gemm(const void* a, const void* w, const float* bias,
 TAPCLIP_API int32_t tapclip_op_gemm_stats_parts(int64_t N) { return gemm_stats_parts(N); }
 
 TAPCLIP_API int tapclip_op_gemm_resid(const void* a, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out,
-                          int64_t ld_out, void* xb, float* stats, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream) {
+                          int64_t ld_out, void* xb, float* stats, float* shift, const float* stats_prev, const float* shift_prev,
+                          int32_t prev_parts, int64_t M, int64_t N, int64_t K, int32_t dtype, void* stream) {
     TC_API_BEGIN
     GemmArgs g;
     g.a = a; g.w = w; g.bias = bias; g.out = x_out;
     g.M = M; g.N = N; g.K = K; g.lda = K; g.ldw = K; g.ldo = ld_out ? ld_out : N; g.epi = EPI_F32_RESID; g.act = ACT_NONE; g.dt = dtype;
-    g.resid_in = x_in; g.ld_in = ld_in ? ld_in : N; g.xb = xb; g.stats_out = stats;
+    g.resid_in = x_in; g.ld_in = ld_in ? ld_in : N; g.xb = xb; g.stats_out = stats; g.shift_out = shift;
+    g.stats_prev = stats_prev; g.shift_prev = shift_prev; g.prev_parts = prev_parts;
     gemm_tc(g, S(stream));
     TC_API_END
 }
@@ -184,9 +186,10 @@ TAPCLIP_API int tapclip_op_fold_ln_weight(const float* w, const float* bias, con
     TC_API_END
 }
 
-TAPCLIP_API int tapclip_op_row_stats_cast(const float* x, void* xb, int32_t dtype, float* stats, int64_t rows, int32_t d, void* stream) {
+TAPCLIP_API int tapclip_op_row_stats_cast(const float* x, void* xb, int32_t dtype, float* stats, float* shift, int64_t rows, int32_t d,
+                              void* stream) {
     TC_API_BEGIN
-    row_stats_cast(x, xb, dtype, stats, rows, d, S(stream));
+    row_stats_cast(x, xb, dtype, stats, shift, rows, d, S(stream));
     TC_API_END
 }
 

@@ -96,7 +96,8 @@ std::vector<DevBuf*> Engine::all_bufs() {
     return {&v_patches, &v_patch_out, &v_x, &v_ln, &v_qkv, &v_attn, &v_h, &v_pooled, &v_roll_qkv, &v_lse, &v_roll,
             &t_x, &t_ln, &t_qkv, &t_attn, &t_h, &t_pooled, &t_feat, &t_tfeat, &t_inv_norm, &t_probe, &t_attr, &t_attr_raw,
             &t_save_x, &t_save_qkv, &t_save_h, &b_dx, &b_dxc, &b_dh, &b_dln, &b_dattn, &b_dqkv, &b_dfeat, &b_dfeatc, &b_dpool,
-            &s_rows, &s_cls, &e_eot, &e_pool, &v_xb, &v_stats, &v_xlive, &t_xb, &t_stats, &t_xlive, &s_ticket};
+            &s_rows, &s_cls, &e_eot, &e_pool, &v_xb, &v_xlive, &t_xb, &t_xlive, &s_ticket, &v_rs.stats[0], &v_rs.stats[1], &v_rs.shift[0], &v_rs.shift[1],
+            &t_rs.stats[0], &t_rs.stats[1], &t_rs.shift[0], &t_rs.shift[1]};
 }
 
 // two self-resetting tickets of the head kernels' last-CTA reductions (zeroed once, synchronously, when first needed)
@@ -359,11 +360,18 @@ void Engine::gemm_fold(const void* xb, const float* stats, int parts, const void
 }
 
 void Engine::gemm_resid(const void* a, int64_t lda, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out,
-                        int64_t ldo, void* xb, float* stats, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st) {
+                        int64_t ldo, void* xb, RowStats* rs, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st) {
     GemmArgs g;
     g.a = a; g.w = w; g.bias = bias; g.out = x_out;
     g.M = M; g.N = N; g.K = K; g.lda = lda ? lda : K; g.ldw = K; g.ldo = ldo ? ldo : N; g.epi = EPI_F32_RESID; g.act = ACT_NONE; g.dt = dt;
-    g.resid_in = x_in; g.ld_in = ld_in ? ld_in : N; g.xb = xb; g.stats_out = stats;
+    g.resid_in = x_in; g.ld_in = ld_in ? ld_in : N;
+    if (rs != nullptr) {
+        // the set describing x_in is read (mean of the old rows = the shift of the new 16-bit copy), the other set is written
+        g.xb = xb;
+        g.stats_prev = rs->s(rs->cur); g.shift_prev = rs->h(rs->cur); g.prev_parts = rs->parts;
+        rs->cur ^= 1; rs->parts = gemm_stats_parts(N);
+        g.stats_out = rs->s(rs->cur); g.shift_out = rs->h(rs->cur);
+    }
     ProfRec r{nullptr, nullptr, 2.0 * (double)M * (double)N * (double)K, 0, M, N, K, 7};
     if (profiling) prof_begin(r, st);
     gemm_tc(g, st);
@@ -413,8 +421,8 @@ void Engine::block_forward(const BlockWeights& b, float* x, int S, int N, int d,
 }
 
 // The same block with no LayerNorm kernel (16-bit modes; see engine.h).  On entry xb / stats describe the rows at `x`.
-void Engine::block_forward_fused(const BlockWeights& b, float*& x, int& parts, float* scratch, int S, int N, int d, int H, int dt,
-                                 DevBuf& xb, DevBuf& stats, DevBuf& xlive, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf,
+void Engine::block_forward_fused(const BlockWeights& b, float*& x, RowStats& rs, float* scratch, int S, int N, int d, int H, int dt,
+                                 DevBuf& xb, DevBuf& xlive, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf,
                                  const AttnProbe& probe, bool probs_only, int save_slot, bool has_next, cudaStream_t st, void* rollout_qkv,
                                  int live_row) {
     const int64_t M = (int64_t)S * N;
@@ -428,7 +436,7 @@ void Engine::block_forward_fused(const BlockWeights& b, float*& x, int& parts, f
         shpre = (uint8_t*)t_save_h.p + (int64_t)save_slot * M * 4 * d * esz;
     }
     if (rollout_qkv) sqkv = rollout_qkv;
-    gemm_fold(xb.p, (const float*)stats.p, parts, b.wf_qkv, b.fb_qkv, sqkv, nullptr, M, 3 * d, d, ACT_NONE, dt, st);
+    gemm_fold(xb.p, rs.s(rs.cur), rs.parts, b.wf_qkv, b.fb_qkv, sqkv, nullptr, M, 3 * d, d, ACT_NONE, dt, st);
     attn_fwd(sqkv, attn.p, dt, S, N, H, probe, st);
     if (probs_only) return;
     if (live_row >= 0) {
@@ -445,11 +453,10 @@ void Engine::block_forward_fused(const BlockWeights& b, float*& x, int& parts, f
         return;
     }
     float* x1 = sx1 ? sx1 : x;
-    gemm_resid(attn.p, 0, b.w_o, b.b_o, x, d, x1, d, xb.p, (float*)stats.p, M, d, d, dt, st);
-    parts = gemm_stats_parts(d);
-    gemm_fold(xb.p, (const float*)stats.p, parts, b.wf_fc, b.fb_fc, hbuf.p, shpre, M, 4 * d, d, cfg.act, dt, st);
+    gemm_resid(attn.p, 0, b.w_o, b.b_o, x, d, x1, d, xb.p, &rs, M, d, d, dt, st);
+    gemm_fold(xb.p, rs.s(rs.cur), rs.parts, b.wf_fc, b.fb_fc, hbuf.p, shpre, M, 4 * d, d, cfg.act, dt, st);
     float* x2 = next_sx0 ? next_sx0 : (save_slot >= 0 ? scratch : x1);
-    gemm_resid(hbuf.p, 0, b.w_proj, b.b_proj, x1, d, x2, d, xb.p, (float*)stats.p, M, d, 4 * d, dt, st);
+    gemm_resid(hbuf.p, 0, b.w_proj, b.b_proj, x1, d, x2, d, xb.p, &rs, M, d, 4 * d, dt, st);
     x = x2;
 }
 
@@ -480,16 +487,16 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
     const bool fused = use_fold(true);
     if (fused) {
         v_xb.ensure(M * d * esz);
-        v_stats.ensure((size_t)M * gemm_stats_parts(d) * 2 * sizeof(float));
+        v_rs.ensure(M, gemm_stats_parts(d));
         v_xlive.ensure((size_t)B * d * sizeof(float));
+        v_rs.cur = 0; v_rs.parts = 1;
     }
     patchify(images, v_patches.p, vdt, B, cfg.image_size, cfg.patch_size, kpatch_pad, st); ++launches;
     gemm(v_patches.p, w_patch, nullptr, v_patch_out.p, nullptr, Mp, d, kpatch_pad, EPI_F32, ACT_NONE, vdt, st);
     assemble_ln_pre((const float*)v_patch_out.p, cls_emb, pos_emb, ln_pre_g, ln_pre_b, (float*)v_x.p, B, N, d, st,
-                    fused ? v_xb.p : nullptr, fused ? (float*)v_stats.p : nullptr); ++launches;
+                    fused ? v_xb.p : nullptr, fused ? v_rs.s(0) : nullptr, fused ? v_rs.h(0) : nullptr); ++launches;
     float* xcur = (float*)v_x.p;                      // where the residual stream lives (fused path: may move to the compact live rows)
     int64_t x_stride = (int64_t)N * d;                // distance between the CLS rows of consecutive images
-    int parts = 1;
     for (int l = 0; l < L; ++l) {
         AttnProbe probe;
         if (out_cls_rows) {
@@ -502,7 +509,7 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
         void* roll_qkv = out_rollout ? (uint8_t*)v_roll_qkv.p + (int64_t)l * M * 3 * d * esz : nullptr;
         const int live_row = (l == L - 1 && dead_rows) ? 0 : -1;                       // only the CLS row feeds ln_post
         if (fused) {
-            block_forward_fused(vis[l], xcur, parts, (float*)v_x.p, B, N, d, H, vdt, v_xb, v_stats, v_xlive, v_ln, v_qkv, v_attn, v_h, probe,
+            block_forward_fused(vis[l], xcur, v_rs, (float*)v_x.p, B, N, d, H, vdt, v_xb, v_xlive, v_ln, v_qkv, v_attn, v_h, probe,
                                 false, -1, l + 1 < L, st, roll_qkv, live_row);
             if (live_row >= 0) x_stride = d;
         } else {
@@ -558,7 +565,7 @@ int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, i
     }
     if (fused) {
         t_xb.ensure(M * D * esz);
-        t_stats.ensure((size_t)M * gemm_stats_parts(D) * 2 * sizeof(float));
+        t_rs.ensure(M, gemm_stats_parts(D));
         t_xlive.ensure((size_t)C * D * sizeof(float));
     }
     float* x = (float*)t_x.p;
@@ -566,9 +573,8 @@ int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, i
     // one pass of the text transformer over the prompts already spliced into `xp` (fused path: xp may be save slot 0)
     auto run_blocks = [&](float* xp, bool attribution_pass, bool keep, float*& x_end, int64_t& pool_stride, int64_t& pool_offset) {
         float* xc = xp;
-        int parts = 1;
         pool_stride = T; pool_offset = T - 1;
-        if (fused) { row_stats_cast(xc, t_xb.p, tdt, (float*)t_stats.p, M, D, st); ++launches; }
+        if (fused) { t_rs.cur = 0; t_rs.parts = 1; row_stats_cast(xc, t_xb.p, tdt, t_rs.s(0), t_rs.h(0), M, D, st); ++launches; }
         for (int l = 0; l < L; ++l) {
             AttnProbe probe;
             const bool last = (l == L - 1);
@@ -576,7 +582,7 @@ int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, i
             // feature pass, last block: only position T-1 is pooled (model_wrapper.py:73) -> out-projection and MLP on C rows
             const int live_row = (!attribution_pass && last && dead_rows) ? T - 1 : -1;
             if (fused) {
-                block_forward_fused(txt[l], xc, parts, (float*)t_x.p, C, T, D, H, tdt, t_xb, t_stats, t_xlive, t_ln, t_qkv, t_attn, t_h, probe,
+                block_forward_fused(txt[l], xc, t_rs, (float*)t_x.p, C, T, D, H, tdt, t_xb, t_xlive, t_ln, t_qkv, t_attn, t_h, probe,
                                     attribution_pass && last, keep ? l : -1, l + 1 < L, st, nullptr, live_row);
                 if (live_row >= 0) { pool_stride = 1; pool_offset = 0; }
             } else {

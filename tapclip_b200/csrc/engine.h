@@ -49,7 +49,16 @@ struct Engine {
     // workspaces (grow-only)
     DevBuf v_patches, v_patch_out, v_x, v_ln, v_qkv, v_attn, v_h, v_pooled, v_roll_qkv, v_lse, v_roll;
     DevBuf t_x, t_ln, t_qkv, t_attn, t_h, t_pooled, t_feat, t_tfeat, t_inv_norm, t_probe, t_attr, t_attr_raw;
-    DevBuf v_xb, v_stats, v_xlive, t_xb, t_stats, t_xlive;      // folded-LayerNorm path: 16-bit residual copy, row statistics, live rows of the last block
+    // folded-LayerNorm path: 16-bit (row-shifted) residual copy, live rows of the last block, and the row statistics + shifts in
+    // two alternating sets (a residual GEMM reads the set describing its input while it writes the set describing its output)
+    DevBuf v_xb, v_xlive, t_xb, t_xlive;
+    struct RowStats {
+        DevBuf stats[2], shift[2];
+        int cur = 0, parts = 1;                                     // set describing the current residual rows; partials per row in it
+        void ensure(int64_t rows, int max_parts) { for (int i = 0; i < 2; ++i) { stats[i].ensure((size_t)rows * max_parts * 2 * sizeof(float)); shift[i].ensure((size_t)rows * sizeof(float)); } }
+        float* s(int which) { return (float*)stats[which].p; }
+        float* h(int which) { return (float*)shift[which].p; }
+    } v_rs, t_rs;
     DevBuf t_save_x, t_save_qkv, t_save_h;
     DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
     DevBuf s_rows, s_cls, s_ticket, e_eot, e_pool;
@@ -92,13 +101,14 @@ struct Engine {
     // updated rows in 16 bits plus per-row (sum, sum of squares); the QKV / c_fc GEMMs consume them with LayerNorm folded into the
     // weights.  `x` follows the residual stream (it hops through the save slots when save_slot >= 0; after a last block with
     // live_row >= 0 it points at the compact [S, d] live rows); `parts` = statistics partials per row currently in `stats`.
-    void block_forward_fused(const BlockWeights& b, float*& x, int& parts, float* scratch, int S, int N, int d, int H, int dt, DevBuf& xb,
-                             DevBuf& stats, DevBuf& xlive, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf, const AttnProbe& probe,
+    void block_forward_fused(const BlockWeights& b, float*& x, RowStats& rs, float* scratch, int S, int N, int d, int H, int dt, DevBuf& xb,
+                             DevBuf& xlive, DevBuf& ln, DevBuf& qkv, DevBuf& attn, DevBuf& hbuf, const AttnProbe& probe,
                              bool probs_only, int save_slot, bool has_next, cudaStream_t st, void* rollout_qkv = nullptr, int live_row = -1);
     void gemm_fold(const void* xb, const float* stats, int parts, const void* wf, const float* fb, void* out, void* out_pre,
                    int64_t M, int64_t N, int64_t K, int act, int dt, cudaStream_t st);
+    // rs != nullptr: also emit the shifted 16-bit copy into xb and the next statistics set (rs flips to it)
     void gemm_resid(const void* a, int64_t lda, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out, int64_t ldo,
-                    void* xb, float* stats, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st);
+                    void* xb, RowStats* rs, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st);
     void fold_group(BlockWeights& b, int group, const std::string& prefix, int d, int dt, cudaStream_t st);
     // TAPCLIP_FUSE_LN: 0 = LayerNorm as its own kernel; 1 = folded into the GEMMs of the text tower; 2 = of both towers (default)
     int fuse_ln = getenv("TAPCLIP_FUSE_LN") ? atoi(getenv("TAPCLIP_FUSE_LN")) : 2;

@@ -13,8 +13,11 @@ enum Epi : int {
                            // the saved 16-bit pre-activations, type aux_dt, same [M,N] layout and leading dimension as out)
     EPI_F32_RESID = 4,     // out (f32, ldo) = resid_in (f32, ld_in) + acc + bias: the residual update `x = x + f(...)` of a pre-LN
                            // block, out of place (or in place: resid_in == out).  Optionally also emits what the NEXT LayerNorm
-                           // needs: xb = the updated rows in the 16-bit operand type (dense [M,N]) and stats_out = per-row partial
-                           // (sum, sum of squares) of the updated rows, one pair per (n-tile, epilogue-warp parity) -- see `fold`
+                           // needs: xb = the updated rows, SHIFTED by a per-row constant, in the 16-bit operand type (dense [M,N]),
+                           // stats_out = per-row partial (sum, sum of squares) of the shifted rows, one pair per (n-tile,
+                           // epilogue-warp parity), shift_out = the shift (the mean of the row BEFORE the update, taken from the
+                           // previous statistics; 0 without them).  LayerNorm is invariant to the shift; it keeps the rounded
+                           // values centred -- see stats_in
 };
 
 struct GemmArgs {
@@ -33,9 +36,13 @@ struct GemmArgs {
     // EPI_F32_RESID
     const float* resid_in = nullptr;   // [M, N] fp32, leading dimension ld_in
     int64_t ld_in = 0;
-    void* xb = nullptr;                // optional: 16-bit copy (type dt) of the updated rows, dense [M, N]
-    float* stats_out = nullptr;        // optional: [M][gemm_stats_parts(N)][2] partial (sum, sum of squares) of the updated rows
-    // LayerNorm folded into the GEMM (EPI_BF16 only): A holds the UN-normalised rows x in 16 bits, W the gamma-scaled and
+    void* xb = nullptr;                // optional: 16-bit copy (type dt) of the updated rows minus their shift, dense [M, N]
+    float* stats_out = nullptr;        // optional: [M][gemm_stats_parts(N)][2] partial (sum, sum of squares) of the shifted rows
+    float* shift_out = nullptr;        // [M] the shift used (goes with stats_out)
+    const float* stats_prev = nullptr; // optional: the statistics / shifts describing resid_in (another buffer than stats_out):
+    const float* shift_prev = nullptr; //   shift = shift_prev + sum(stats_prev.x) / N = mean of the row of resid_in
+    int prev_parts = 0;
+    // LayerNorm folded into the GEMM (EPI_BF16 only): A holds the UN-normalised (possibly row-shifted) rows x in 16 bits, W the gamma-scaled and
     // row-centred weight W" = W diag(gamma) - rowmean(W diag(gamma)) (so x W"^T = (x - mean(x)) (W diag(gamma))^T), bias the folded
     // bias b' = b + W beta; with rstd recovered from stats_in the epilogue forms  LN(x) W^T + b = rstd * (x W"^T) + b'.
     const float* stats_in = nullptr;   // [M][stats_parts][2] partial (sum, sum of squares) over the K elements of each row of A

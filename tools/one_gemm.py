@@ -17,6 +17,7 @@ x = torch.randn(M, d, device=dev)
 xb = torch.empty(M, d, device=dev, dtype=torch.bfloat16)
 parts = lib.tapclip_op_gemm_stats_parts(d)
 stats = torch.zeros(M, parts, 2, device=dev)
+stats_b, shift_a, shift_b = torch.zeros_like(stats), torch.zeros(M, device=dev), torch.zeros(M, device=dev)
 attn = torch.randn(M, d, device=dev).bfloat16()
 ln = torch.randn(M, d, device=dev).bfloat16()
 h = torch.empty(M, 4 * d, device=dev, dtype=torch.bfloat16)
@@ -31,7 +32,8 @@ w_fc16 = w_fc.bfloat16()
 big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # L2 flush between launches
 for _ in range(3):
     big.zero_()
-    _lib.check(lib.tapclip_op_gemm_resid(P(attn), P(w_o), P(b_o), P(x), 0, P(x), 0, P(xb), P(stats), M, d, d, DT, S()))
+    _lib.check(lib.tapclip_op_gemm_resid(P(attn), P(w_o), P(b_o), P(x), 0, P(x), 0, P(xb), P(stats), P(shift_a), P(stats_b), P(shift_b), parts,
+                                         M, d, d, DT, S()))
 for _ in range(3):
     big.zero_()
     _lib.check(lib.tapclip_op_gemm(P(attn), P(w_o), P(b_o), P(x), None, M, d, d, DT, 2, -1, 0, S()))
