@@ -62,10 +62,22 @@ class _TapClipFunction(torch.autograd.Function):
             img_feat = model._encode_image(images)
             text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad, adjusted)
             text_feat = all_gather_rows(text_local, shard, n_cls)                 # [C, E]
+        ctx.reduced = None
         if labels is not None:
             b_total = shard.global_batch(images.shape[0])
             logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale, labels, 1.0 / b_total)
-            loss = all_reduce_sum_(loss.clone(), shard) if shard.world > 1 else loss
+            if shard.world > 1 and (need_grad or logit_scale.requires_grad):
+                # ONE collective for the whole logit head: the CE gradient is already known here (the fused logits kernel emits
+                # dloss/dlogits), so d T^ [C,E], d logit_scale and the loss are reduced together; backward scales the cached
+                # result by the incoming d loss (they are linear in it) instead of issuing two more all-reduces
+                d_text, d_scale = eng.logits_backward(dlogits_ce, logits, img_norm, logit_scale)
+                packed = torch.cat([d_text.reshape(-1), d_scale.reshape(1), loss.reshape(1)])
+                all_reduce_sum_(packed, shard)
+                n = d_text.numel()
+                ctx.reduced = (packed[:n].view_as(d_text), packed[n])
+                loss = packed[n + 1].clone()
+            elif shard.world > 1:
+                loss = all_reduce_sum_(loss.clone(), shard)
         else:
             logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale)
         if adjusted is None:
@@ -89,18 +101,23 @@ class _TapClipFunction(torch.autograd.Function):
         eng = model.clip.engine
         n_cls, P, lo, hi = ctx.dims
         logits, dlogits_ce, img_norm, logit_scale = ctx.saved_tensors
-        dl = None
-        if ctx.has_ce and g_loss is not None:
-            dl = dlogits_ce * g_loss
-        if g_logits is not None:
-            dl = g_logits.contiguous() if dl is None else dl + g_logits
         n_in = 5 + (1 if ctx.adjusted else n_cls)
-        if dl is None:
-            return (None,) * n_in
-        d_text, d_scale = eng.logits_backward(dl.contiguous(), logits, img_norm, logit_scale)
-        if shard.world > 1:
-            all_reduce_sum_(d_text, shard)
-            all_reduce_sum_(d_scale, shard)
+        if ctx.reduced is not None and g_logits is None and g_loss is not None:
+            # the usual `loss.backward()`: the reduced gradients of the head were computed (and all-reduced) in forward
+            d_text, d_scale = ctx.reduced[0] * g_loss, ctx.reduced[1] * g_loss
+        else:
+            dl = None
+            if ctx.has_ce and g_loss is not None:
+                dl = dlogits_ce * g_loss
+            if g_logits is not None:
+                dl = g_logits.contiguous() if dl is None else dl + g_logits
+            if dl is None:
+                return (None,) * n_in
+            d_text, d_scale = eng.logits_backward(dl.contiguous(), logits, img_norm, logit_scale)
+            if shard.world > 1:                                                   # one collective for both
+                packed = torch.cat([d_text.reshape(-1), d_scale.reshape(1)])
+                all_reduce_sum_(packed, shard)
+                d_text, d_scale = packed[:-1].view_as(d_text), packed[-1]
         grads = [None] * n_cls
         if ctx.need_grad:
             d_local = d_text[lo:hi].contiguous()

@@ -48,23 +48,39 @@ class ClassSharding:
         return local_batch * self.world
 
 
+_UNPAD_INDEX = {}
+
+
+def _unpad_index(shard: ClassSharding, n_rows_total: int, device) -> torch.Tensor:
+    """Row indices that pick every rank's real rows out of the gathered [world * max_shard, W] block (cached)."""
+    key = (shard.world, n_rows_total, str(device))
+    idx = _UNPAD_INDEX.get(key)
+    if idx is None:
+        m = shard.max_shard(n_rows_total)
+        rows = []
+        for r in range(shard.world):
+            lo, hi = shard.bounds(n_rows_total, r)
+            rows.extend(range(r * m, r * m + (hi - lo)))
+        idx = _UNPAD_INDEX[key] = torch.tensor(rows, dtype=torch.int64, device=device)
+    return idx
+
+
 def all_gather_rows(local: torch.Tensor, shard: ClassSharding, n_rows_total: int) -> torch.Tensor:
-    """Concatenate every rank's ``[rows_r, W]`` block (rows_r = shard.bounds) into ``[n_rows_total, W]``."""
+    """Concatenate every rank's ``[rows_r, W]`` block (rows_r = shard.bounds) into ``[n_rows_total, W]``: ONE collective into a
+    pre-sized buffer.  Even shards land at their final offsets (no copy before or after); ragged shards are gathered at a
+    fixed pitch of max_shard rows and compacted with one cached index_select."""
     if shard.world == 1:
         return local
     width = local.shape[1]
     m = shard.max_shard(n_rows_total)
-    padded = local.new_zeros(m, width)
-    padded[: local.shape[0]] = local
+    even = n_rows_total % shard.world == 0
+    src = local.contiguous()
+    if not even and local.shape[0] < m:                      # only the short ranks of a ragged partition pad their block
+        src = local.new_zeros(m, width)
+        src[: local.shape[0]] = local
     out = local.new_empty(shard.world * m, width)
-    dist.all_gather_into_tensor(out, padded, group=shard.group)
-    if n_rows_total % shard.world == 0:
-        return out
-    parts = []
-    for r in range(shard.world):
-        lo, hi = shard.bounds(n_rows_total, r)
-        parts.append(out[r * m: r * m + (hi - lo)])
-    return torch.cat(parts, dim=0)
+    dist.all_gather_into_tensor(out, src, group=shard.group)
+    return out if even else out.index_select(0, _unpad_index(shard, n_rows_total, local.device))
 
 
 def all_reduce_sum_(t: torch.Tensor, shard: ClassSharding) -> torch.Tensor:

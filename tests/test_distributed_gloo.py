@@ -48,11 +48,25 @@ def _worker(rank, world, port, out_dir, C, B_local, mode):
     images, labels = synthetic_images(B_local * world, 64), synthetic_labels(B_local * world, C)
     sl = slice(rank * B_local, (rank + 1) * B_local)
     model.train()
+    # count the collectives of one train step: text-feature all-gather, ONE packed all-reduce (d T^, d logit_scale, loss),
+    # ctx-gradient all-gather
+    calls = {"all_reduce": 0, "all_gather": 0}
+    real_ar, real_ag = dist.all_reduce, dist.all_gather_into_tensor
+    def count_ar(*a, **k): calls["all_reduce"] += 1; return real_ar(*a, **k)
+    def count_ag(*a, **k): calls["all_gather"] += 1; return real_ag(*a, **k)
+    dist.all_reduce, dist.all_gather_into_tensor = count_ar, count_ag
     out = model(images[sl], labels[sl])
     out["loss"].backward()
+    dist.all_reduce, dist.all_gather_into_tensor = real_ar, real_ag
     g = torch.stack([model.prompt_learner.context_bank[n].grad for n in class_names(C)])
-    torch.save({"logits": out["logits"].detach(), "loss": out["loss"].detach(), "grad": g,
-                "sgrad": model.logit_scale.grad.detach()}, os.path.join(out_dir, f"r{rank}.pt"))
+    sgrad = model.logit_scale.grad.detach().clone()
+    # a loss that also uses the logits directly takes the general backward path (gradients not pre-reduced in forward)
+    model.zero_grad()
+    out2 = model(images[sl], labels[sl])
+    (2.0 * out2["loss"] + 0.1 * out2["logits"].square().sum() / (B_local * world)).backward()
+    g2 = torch.stack([model.prompt_learner.context_bank[n].grad for n in class_names(C)])
+    torch.save({"logits": out["logits"].detach(), "loss": out["loss"].detach(), "grad": g, "sgrad": sgrad, "calls": calls,
+                "grad2": g2, "sgrad2": model.logit_scale.grad.detach()}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.destroy_process_group()
 
 
@@ -78,3 +92,12 @@ def test_two_rank_gloo_matches_single_process(mode, C):
         assert ((p["grad"] - g_ref).norm() / g_ref.norm()).item() < 1e-4
         assert abs(p["sgrad"].item() - om.logit_scale.grad.item()) < 1e-5
     assert torch.equal(parts[0]["grad"], parts[1]["grad"])
+    assert parts[0]["calls"] == {"all_reduce": 1, "all_gather": 2}        # three collectives per train step (five before the packing)
+    # general path: d/dctx of 2*loss + 0.1*mean_b sum_c logits^2
+    om.zero_grad()
+    ref2 = om.forward_dedup(images, labels)
+    (2.0 * ref2["loss"] + 0.1 * ref2["logits"].square().sum() / (B_local * world)).backward()
+    g_ref2 = torch.stack([om.prompt_learner.context_bank[n].grad for n in class_names(C)])
+    for p in parts:
+        assert ((p["grad2"] - g_ref2).norm() / g_ref2.norm()).item() < 1e-4
+        assert abs(p["sgrad2"].item() - om.logit_scale.grad.item()) < 1e-4
