@@ -65,22 +65,23 @@ def ncu_gemm_traffic():
     import csv
     import glob
     import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*ncu_full_gemm*.csv")),
-                   key=lambda f: re.match(r"r(\d+)([a-z]*)", os.path.basename(f)).groups() if re.match(r"r(\d+)([a-z]*)", os.path.basename(f)) else ("", ""))
-    if not files:
-        return None, None
-    path = files[-1]
-    with open(path, newline="") as f:
-        rows = list(csv.reader(f))
-    try:
-        hdr, units = rows[0], rows[1]
-        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
-                for r in rows[2:] if r and "gemm_tc_kernel" in r[0]]
-    except (ValueError, IndexError):
-        return None, os.path.basename(path)
-    return (sum(vals) / len(vals) if vals else None), os.path.basename(path)
+    def order(f):
+        m = re.match(r"r(\d+)([a-z]*)", os.path.basename(f))
+        return (int(m.group(1)), m.group(2)) if m else (-1, "")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*ncu_full_gemm*.csv")), key=order, reverse=True):
+        try:
+            with open(path, newline="") as f:
+                rows = list(csv.reader(f))
+            hdr, units = rows[0], rows[1]
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+                    for r in rows[2:] if r and "gemm_tc_kernel" in r[0]]
+        except (ValueError, IndexError, OSError):
+            continue
+        if vals:                                             # the newest capture that holds gemm_tc_kernel launches
+            return sum(vals) / len(vals), os.path.basename(path)
+    return None, None
 
 
 class ClockSampler:

@@ -345,50 +345,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
             if constexpr (RESID) {
                 // ---- x_new = x_old + A W^T + b, its 16-bit copy and its row statistics -------------------------------------------
-                // Everything happens in the accumulator's own layout: thread <-> row, 32 consecutive fp32 columns (128 contiguous
-                // bytes of the row) per chunk, so there is no shared-memory transpose, no shuffle and one address per thread; the
-                // row statistics are plain per-thread sums.  (The staged, coalesced form of this epilogue executed 3x the
-                // instructions of the red.add epilogue -- 14.1 M vs 4.8 M warp instructions on the 25216x768x768 out-projection --
-                // and a single epilogue warp's issue rate became the kernel's bound.)  A warp-wide 16-byte access touches 32 rows,
-                // i.e. 32 sectors; both halves of every sector are accessed back to back and merge in L1 (loads) / L2 (stores).
+                // Global memory is touched in the coalesced store mapping only (lane (rd_row, rd_ch) owns 16 bytes of rows
+                // it*4 + rd_row; 8 lanes cover a 128-byte row segment): the accumulator chunk goes through the warp's swizzled
+                // staging buffer as in the other epilogues.  (Accessing memory straight from the accumulator layout -- thread <->
+                // row, every warp-wide 16-byte access spread over 32 rows -- needs a third of the instructions and no shuffles,
+                // but ran 1.7x slower: 96 vs 55 us on the 25216x768x768 out-projection.)
                 // The old residual values are the only global READ: requested two chunks ahead -- the first two chunks while this
-                // tile's MMAs still run (the MMA warp pulled the tile's rows into L2 when it started the tile).
+                // tile's MMAs still run (the MMA warp pulled the tile's rows into L2 when it started the tile).  Addresses and row
+                // predicates are formed once per tile; the row sums stay lane-local through the chunk loop and cross the 8 lanes
+                // of a row once per tile (the first version reduced per chunk and executed 3x the instructions of the red.add
+                // epilogue: one epilogue warp's issue rate had become the kernel's bound).
                 //
                 // The 16-bit copy is SHIFTED by the previous mean of its row, zb = x_new - mean(x_old) (the folded-LayerNorm consumer
                 // is invariant to a per-row shift): what gets rounded is then the centred value, as when LayerNorm's output is
                 // rounded, and the statistics (sum z, sum z^2) are well conditioned.  mean(x_old) comes from the previous
                 // statistics of the row (stats_prev + shift_prev); the new shift is stored for the next producer.
-                constexpr int RCH = 32;                              // fp32 columns per chunk
+                constexpr int RCH = 32;                              // fp32 columns per 128-byte staging row
                 constexpr int NMINE = BLOCK_N / RCH / 2;             // chunks of this warp: c = chunk_par + 2 i
-                const int row = row0 + lane;
-                const bool row_ok = row < M && dbg == 0;
-                const float* xin = ex.resid_in + (int64_t)row * ex.ld_in + n0 + chunk_par * RCH;
+                const int col_l = chunk_par * RCH + rd_ch * 4;       // this lane's first column inside the tile (chunk 0 of the warp)
+                const int64_t row_l = row0 + rd_row;                 // this lane's first row (it = 0)
+                const float* xin = ex.resid_in + row_l * ex.ld_in + n0 + col_l;
+                float* xout = reinterpret_cast<float*>(out) + row_l * ldo + n0 + col_l;
+                T16* zout = reinterpret_cast<T16*>(ex.xb) + row_l * N + n0 + col_l;
+                const int64_t in_step = 4 * (int64_t)ex.ld_in, out_step = 4 * (int64_t)ldo, z_step = 4 * (int64_t)N;
+                uint32_t okmask = 0;                                 // bit it: row it*4 + rd_row of this warp's 32 rows exists
+                float sh[8];                                         // the rows' shifts
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int64_t r = row_l + it * 4;
+                    sh[it] = 0.f;
+                    if (r < M && dbg == 0) {
+                        okmask |= 1u << it;
+                        if (ex.stats_prev != nullptr) {
+                            const float2* sp = reinterpret_cast<const float2*>(ex.stats_prev) + r * ex.prev_parts;
+                            float s1 = 0.f;
+                            for (int p = 0; p < ex.prev_parts; ++p) s1 += sp[p].x;
+                            sh[it] = ex.shift_prev[r] + s1 / (float)N;       // = mean of the row of x_old
+                        }
+                    }
+                }
                 float4 xo[2][8];
                 auto request = [&](int i, float4 (&dst)[8]) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row_ok) dst[j] = *reinterpret_cast<const float4*>(xin + i * 2 * RCH + j * 4);
+                    for (int it = 0; it < 8; ++it) {
+                        dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (okmask >> it & 1u) dst[it] = *reinterpret_cast<const float4*>(xin + it * in_step + i * 2 * RCH);
                     }
                 };
                 request(0, xo[0]);
                 if constexpr (NMINE > 1) request(1, xo[1]);
-                float shift = 0.f;
-                if (ex.stats_prev != nullptr && row < M) {
-                    const float2* sp = reinterpret_cast<const float2*>(ex.stats_prev) + (int64_t)row * ex.prev_parts;
-                    float s1 = 0.f;
-                    for (int p0 = 0; p0 < ex.prev_parts; p0 += 8) {
+                float rs[8], rq[8];                                  // lane-local (sum, sum of squares) of rows it*4 + rd_row
 #pragma unroll
-                        for (int p = 0; p < 8; ++p)
-                            if (p0 + p < ex.prev_parts) s1 += sp[p0 + p].x;
-                    }
-                    shift = ex.shift_prev[row] + s1 / (float)N;       // = mean of the row of x_old
-                }
-                float s1 = 0.f, s2 = 0.f;                            // (sum, sum of squares) of this warp's shifted columns of the row
+                for (int it = 0; it < 8; ++it) { rs[it] = 0.f; rq[it] = 0.f; }
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-                float* xout = reinterpret_cast<float*>(out) + (int64_t)row * ldo + n0 + chunk_par * RCH;
-                T16* zout = reinterpret_cast<T16*>(ex.xb) + (int64_t)row * N + n0 + chunk_par * RCH;
 #pragma unroll
                 for (int i = 0; i < NMINE; ++i) {
                     const int c = chunk_par + 2 * i;
@@ -405,35 +415,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                     }
+                    if (bias != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (bias != nullptr) b = *reinterpret_cast<const float4*>(bias_s + c * RCH + j * 4);   // smem broadcast
-                        const float4 o = xo[i & 1][j];
-                        const float a0 = v[4 * j] + b.x + o.x, a1 = v[4 * j + 1] + b.y + o.y;
-                        const float a2 = v[4 * j + 2] + b.z + o.z, a3 = v[4 * j + 3] + b.w + o.w;
-                        if (row_ok) *reinterpret_cast<float4*>(xout + i * 2 * RCH + j * 4) = make_float4(a0, a1, a2, a3);
-                        v[4 * j] = a0 - shift; v[4 * j + 1] = a1 - shift; v[4 * j + 2] = a2 - shift; v[4 * j + 3] = a3 - shift;
+                        for (int j = 0; j < RCH; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias_s + c * RCH + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    }
+                    __syncwarp();                                    // previous read-back of the staging buffer is complete
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + row_off + (((uint32_t)j ^ sw) << 4)),
+                                     "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])), "r"(__float_as_uint(v[4 * j + 2])),
+                                     "r"(__float_as_uint(v[4 * j + 3])) : "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + rd_row;
+                        float a0, a1, a2, a3;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                                     : "r"(stage_u32 + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
+                        if (okmask >> it & 1u) {
+                            const float4 o = xo[i & 1][it];
+                            a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
+                            *reinterpret_cast<float4*>(xout + it * out_step + i * 2 * RCH) = make_float4(a0, a1, a2, a3);
+                            a0 -= sh[it]; a1 -= sh[it]; a2 -= sh[it]; a3 -= sh[it];
+                            if (ex.xb != nullptr)
+                                *reinterpret_cast<uint2*>(zout + it * z_step + i * 2 * RCH) = make_uint2(pack2<T16>(a0, a1), pack2<T16>(a2, a3));
+                            rs[it] += (a0 + a1) + (a2 + a3);
+                            rq[it] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                        }
                     }
                     if (i + 2 < NMINE) request(i + 2, xo[i & 1]);
-#pragma unroll
-                    for (int j = 0; j < RCH; j += 4) {
-                        s1 += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-                        s2 += (v[j] * v[j] + v[j + 1] * v[j + 1]) + (v[j + 2] * v[j + 2] + v[j + 3] * v[j + 3]);
-                    }
-                    if (ex.xb != nullptr && row_ok) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(zout + i * 2 * RCH + j * 8) =
-                                make_uint4(pack2<T16>(v[8 * j], v[8 * j + 1]), pack2<T16>(v[8 * j + 2], v[8 * j + 3]),
-                                           pack2<T16>(v[8 * j + 4], v[8 * j + 5]), pack2<T16>(v[8 * j + 6], v[8 * j + 7]));
-                    }
                 }
-                // one (sum, sum of squares) pair per row, n-tile and warp parity: every slot has exactly one writer
-                if (ex.stats_out != nullptr && row_ok) {
+                if (ex.stats_out != nullptr) {
+                    // the 8 lanes that share a row (consecutive lanes) reduce their sums; one (sum, sum of squares) pair per row,
+                    // n-tile and warp parity: every slot has exactly one writer
                     const int parts = 2 * n_tiles, part = 2 * (tile % n_tiles) + chunk_par;
-                    reinterpret_cast<float2*>(ex.stats_out)[(int64_t)row * parts + part] = make_float2(s1, s2);
-                    if (part == 0) ex.shift_out[row] = shift;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        float ps = rs[it], pq = rq[it];
+                        ps += __shfl_xor_sync(0xffffffffu, ps, 1); pq += __shfl_xor_sync(0xffffffffu, pq, 1);
+                        ps += __shfl_xor_sync(0xffffffffu, ps, 2); pq += __shfl_xor_sync(0xffffffffu, pq, 2);
+                        ps += __shfl_xor_sync(0xffffffffu, ps, 4); pq += __shfl_xor_sync(0xffffffffu, pq, 4);
+                        if (rd_ch == 0 && (okmask >> it & 1u)) {
+                            const int64_t r = row_l + it * 4;
+                            reinterpret_cast<float2*>(ex.stats_out)[r * parts + part] = make_float2(ps, pq);
+                            if (part == 0) ex.shift_out[r] = sh[it];
+                        }
+                    }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : tile + num_units;

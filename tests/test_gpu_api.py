@@ -254,5 +254,5 @@ def test_fused_head_matches_the_separate_launches(dtype, monkeypatch):
     tol = 1e-5 if dtype == "fp32" else 5e-3
     assert max_abs(res["1"][0], res["0"][0]) < tol and abs(res["1"][1] - res["0"][1]) < tol
     assert rel_err(res["1"][2], res["0"][2]) < (1e-5 if dtype == "fp32" else 2e-2)
-    assert abs(res["1"][3] - res["0"][3]) < 1e-4
+    assert abs(res["1"][3] - res["0"][3]) < (1e-5 if dtype == "fp32" else 5e-4)   # sum of cancelling terms: follows the logit differences
     assert res["1"][4] <= res["0"][4] - 8                            # 7 -> 2 launches forward, 5 -> 2 backward
