@@ -600,11 +600,7 @@ template <int NB16, typename TQ>
 void launch_attn_bwd_mma(const TQ* qkv, const bf16* d_out, bf16* dqkv, int S, int N, int H, cudaStream_t stream) {
     constexpr int NP = NB16 * 16;
     const size_t smem = (size_t)4 * NP * 128 + (size_t)2 * NP * (NP * 2 + 16);
-    static bool configured = false;
-    if (!configured) {
-        TC_CUDA(cudaFuncSetAttribute(attn_bwd_mma_kernel<NB16, TQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ensure_dynamic_smem((const void*)attn_bwd_mma_kernel<NB16, TQ>, smem);
     launch_pdl(attn_bwd_mma_kernel<NB16, TQ>, S * H, NB16 * 32, smem, stream, qkv, d_out, dqkv, N, H, 0.125f);
 }
 
@@ -644,13 +640,9 @@ void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, cons
         const int nz = (int)ceil_div(nrb, nwarps);
         const size_t smem = (size_t)(nwarps * 16 + 2 * npad) * 128;
         TC_CHECK(smem <= 227 * 1024, "sequence length %d too long for the attention kernel", N);
-        static size_t configured[2] = {0, 0};
         const int which = dt == DT_F16 ? 1 : 0;
-        if (smem > configured[which]) {
-            if (which) TC_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else TC_CUDA(cudaFuncSetAttribute(attn_fwd_mma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured[which] = smem;
-        }
+        if (which) ensure_dynamic_smem((const void*)attn_fwd_mma_kernel<f16>, smem);
+        else ensure_dynamic_smem((const void*)attn_fwd_mma_kernel<bf16>, smem);
         dim3 grid((unsigned)(S * H), (unsigned)nz);
         const float sl2 = 0.125f * 1.4426950408889634f;
         if (which) launch_pdl(attn_fwd_mma_kernel<f16>, grid, nwarps * 32, smem, stream, (const f16*)qkv, (f16*)out, N, H, npad, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, (int)probe.causal);
@@ -675,8 +667,7 @@ void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, i
     } else {
         TC_CHECK(grad_dt == DT_F32 && qkv_dt == DT_F32, "unsupported dtype combination for attention backward");
         const size_t smem = ((size_t)4 * N * LDH + (size_t)N * (N + 1)) * sizeof(float);
-        static size_t conf_f32 = 0;
-        if (smem > conf_f32) { TC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf_f32 = smem; }
+        ensure_dynamic_smem((const void*)attn_bwd_kernel<float>, smem);
         launch_pdl(attn_bwd_kernel<float>, S * H, 256, smem, stream, (const float*)qkv, (const float*)d_out, (float*)dqkv, N, H, 0.125f);
     }
     TC_LAUNCH_CHECK();

@@ -942,15 +942,10 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
     if (nkp > 256) {
         // flash-style kernel: 128-key blocks through a TMA ring
         const CUtensorMap& tkb = make_tmap(qkv, tdt, 2, (int64_t)S * N, 3 * d, 3 * d, KVB, 64);
-        static bool conf3[2] = {false, false};
-        if (!conf3[f16]) {
-            if (f16) TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN3_SMEM_CLS));
-            else TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN3_SMEM_CLS));
-            conf3[f16] = true;
-        }
+        if (f16) ensure_dynamic_smem((const void*)attn_fwd_tc_kv_kernel<true>, ATTN3_SMEM_CLS);
+        else ensure_dynamic_smem((const void*)attn_fwd_tc_kv_kernel<false>, ATTN3_SMEM_CLS);
         const size_t smem3 = probe.mode == PROBE_CLS_ROW ? ATTN3_SMEM_CLS : ATTN3_SMEM;
-        static int num_sms3 = 0;
-        if (num_sms3 == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms3, cudaDevAttrMultiProcessorCount, dev)); }
+        const int num_sms3 = device_sm_count();
         const int n_items = S * H * nqt;
         const unsigned grid3 = (unsigned)std::min(n_items, num_sms3);
         if (f16) launch_pdl(attn_fwd_tc_kv_kernel<true>, grid3, ATTN2_THREADS, smem3, stream, tq, tkb, out, N, H, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out);
@@ -966,33 +961,24 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         const int pair = (nqt == 2 && pair_env != 0) ? 1 : 0;
         const size_t slots = pair ? 2 * (2 * 128 * 128 + 2 * (size_t)nkp * 128) : NSLOT * (128 * 128 + 2 * (size_t)nkp * 128);
         const size_t smem2 = slots + 128 + 2 * CLS_STAGE2 * sizeof(float) + 1024;   // + barriers/TMEM slot, CLS staging, alignment slack
-        static int num_sms = 0;
-        if (num_sms == 0) { int dev; TC_CUDA(cudaGetDevice(&dev)); TC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+        const int num_sms = device_sm_count();
         const int n_items = pair ? S * H : S * H * nqt;        // scheduling units
         const unsigned grid2 = (unsigned)std::min(n_items, num_sms);
         // softmax chunk count instance: 4 (N <= 64, ViT-B/32), 8 (N <= 128, the text tower), 13 (N <= 208, ViT-B/16)
         const int nch = nkp / 16;
-        auto go = [&](auto kern, size_t& configured) {
-            if (smem2 > configured) {
-                TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                configured = smem2;
-            }
+        auto go = [&](auto kern) {
+            ensure_dynamic_smem((const void*)kern, smem2);
             launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair);
         };
-        static size_t conf2[2][3] = {{0, 0, 0}, {0, 0, 0}};
-        if (nch <= 4) { if (f16) go(attn_fwd_tc2_kernel<true, 4>, conf2[1][0]); else go(attn_fwd_tc2_kernel<false, 4>, conf2[0][0]); }
-        else if (nch <= 8) { if (f16) go(attn_fwd_tc2_kernel<true, 8>, conf2[1][1]); else go(attn_fwd_tc2_kernel<false, 8>, conf2[0][1]); }
-        else { if (f16) go(attn_fwd_tc2_kernel<true, 13>, conf2[1][2]); else go(attn_fwd_tc2_kernel<false, 13>, conf2[0][2]); }
+        if (nch <= 4) { if (f16) go(attn_fwd_tc2_kernel<true, 4>); else go(attn_fwd_tc2_kernel<false, 4>); }
+        else if (nch <= 8) { if (f16) go(attn_fwd_tc2_kernel<true, 8>); else go(attn_fwd_tc2_kernel<false, 8>); }
+        else { if (f16) go(attn_fwd_tc2_kernel<true, 13>); else go(attn_fwd_tc2_kernel<false, 13>); }
         TC_LAUNCH_CHECK();
         return true;
     }
     const size_t smem = 128 * 128 + 2 * (size_t)nkp * 128 + 64 + 1024;
-    static size_t conf[2] = {0, 0};
-    if (smem > conf[f16]) {
-        if (f16) TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else TC_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conf[f16] = smem;
-    }
+    if (f16) ensure_dynamic_smem((const void*)attn_fwd_tc_kernel<true>, smem);
+    else ensure_dynamic_smem((const void*)attn_fwd_tc_kernel<false>, smem);
     const unsigned grid = (unsigned)((int64_t)S * H * nqt);
     if (f16) launch_pdl(attn_fwd_tc_kernel<true>, grid, ATTN_THREADS, smem, stream, tq, tkv, out, N, H, nkp, nqt, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);
     else launch_pdl(attn_fwd_tc_kernel<false>, grid, ATTN_THREADS, smem, stream, tq, tkv, out, N, H, nkp, nqt, sl2, probe.mode, probe.out, probe.P, probe.seq_stride);

@@ -68,6 +68,11 @@ static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     if (e != cudaSuccess) throw Error{std::string("kernel launch failed: ") + cudaGetErrorString(e)};
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remembered per (device, kernel), raised when needed
+void ensure_dynamic_smem(const void* kernel, size_t bytes);
+// SM count of the calling thread's current device (cached per device)
+int device_sm_count();
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

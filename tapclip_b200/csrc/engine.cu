@@ -24,6 +24,25 @@ bool pdl_enabled() {
 }
 const char* get_error() { return g_error.c_str(); }
 
+void ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static std::map<std::pair<int, const void*>, size_t> configured;          // single host thread per process by contract
+    int dev;
+    TC_CUDA(cudaGetDevice(&dev));
+    size_t& have = configured[{dev, kernel}];
+    if (bytes > have) {
+        TC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+}
+int device_sm_count() {
+    static int sms[64] = {};
+    int dev;
+    TC_CUDA(cudaGetDevice(&dev));
+    TC_CHECK(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    if (sms[dev] == 0) TC_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    return sms[dev];
+}
+
 namespace {
 
 template <typename T>

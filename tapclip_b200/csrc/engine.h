@@ -110,8 +110,10 @@ struct Engine {
     void gemm_resid(const void* a, int64_t lda, const void* w, const float* bias, const float* x_in, int64_t ld_in, float* x_out, int64_t ldo,
                     void* xb, RowStats* rs, int64_t M, int64_t N, int64_t K, int dt, cudaStream_t st);
     void fold_group(BlockWeights& b, int group, const std::string& prefix, int d, int dt, cudaStream_t st);
-    // TAPCLIP_FUSE_LN: 0 = LayerNorm as its own kernel; 1 = folded into the GEMMs of the text tower; 2 = of both towers (default)
-    int fuse_ln = getenv("TAPCLIP_FUSE_LN") ? atoi(getenv("TAPCLIP_FUSE_LN")) : 2;
+    // TAPCLIP_FUSE_LN: 0 = LayerNorm as its own kernel (default: measured fastest); 1 = folded into the GEMMs of the
+    // text tower; 2 = of both towers.  All three are parity-tested; the folded form has 2 launches and 77 MB of HBM traffic less per
+    // LayerNorm, but the step time follows the bytes crossing between the SMs and L2, which the folding does not change.
+    int fuse_ln = getenv("TAPCLIP_FUSE_LN") ? atoi(getenv("TAPCLIP_FUSE_LN")) : 0;
     bool use_fold(bool vision) const { return cfg.dtype != DT_F32 && fuse_ln >= (vision ? 2 : 1); }
     void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, float* out_rollout, cudaStream_t st);
     // returns the token of the saved activations (0 when nothing was saved)

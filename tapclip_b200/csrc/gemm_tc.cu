@@ -228,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int cslot = 0; uint32_t cphase = 0;
             int tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : unit;
             while (tile < num_tiles) {
-                if constexpr (RESID) {
+                if (RESID && !(dbg & 32)) {
                     // pull the tile's old residual rows into L2 now: the epilogue reads them one mainloop from here
                     const int pm0 = (tile / n_tiles) * BLOCK_M, pn0 = (tile % n_tiles) * BLOCK_N;
                     const uint32_t bytes = (uint32_t)min(BLOCK_N, N - pn0) * 4u;
@@ -368,103 +368,130 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 float* xout = reinterpret_cast<float*>(out) + row_l * ldo + n0 + col_l;
                 T16* zout = reinterpret_cast<T16*>(ex.xb) + row_l * N + n0 + col_l;
                 const int64_t in_step = 4 * (int64_t)ex.ld_in, out_step = 4 * (int64_t)ldo, z_step = 4 * (int64_t)N;
-                uint32_t okmask = 0;                                 // bit it: row it*4 + rd_row of this warp's 32 rows exists
-                float sh[8];                                         // the rows' shifts
+                // the shift of row (row0 + lane) is formed by lane `lane` -- one row per lane, all of its partials requested at once,
+                // consumed after the accumulator wait -- and handed to the lanes that store the row by shuffle
+                float2 sp_[8];
+                float shp = 0.f;
+                const bool have_prev = ex.stats_prev != nullptr && row0 + lane < M;
+                if (have_prev) {
+                    const float2* sp = reinterpret_cast<const float2*>(ex.stats_prev) + (int64_t)(row0 + lane) * ex.prev_parts;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int64_t r = row_l + it * 4;
-                    sh[it] = 0.f;
-                    if (r < M && dbg == 0) {
-                        okmask |= 1u << it;
-                        if (ex.stats_prev != nullptr) {
-                            const float2* sp = reinterpret_cast<const float2*>(ex.stats_prev) + r * ex.prev_parts;
-                            float s1 = 0.f;
-                            for (int p = 0; p < ex.prev_parts; ++p) s1 += sp[p].x;
-                            sh[it] = ex.shift_prev[r] + s1 / (float)N;       // = mean of the row of x_old
-                        }
+                    for (int p = 0; p < 8; ++p) {
+                        sp_[p] = make_float2(0.f, 0.f);
+                        if (p < ex.prev_parts) sp_[p] = sp[p];
                     }
+                    shp = ex.shift_prev[row0 + lane];
                 }
-                float4 xo[2][8];
-                auto request = [&](int i, float4 (&dst)[8]) {
+                // One body, two instances: FULL = all 32 rows of the warp exist (every tile but the last row block) -> no per-row
+                // predicates, no divergent branches; the tail instance predicates each row.
+                auto body = [&](auto full_tag) {
+                    constexpr bool FULLT = decltype(full_tag)::value;
+                    uint32_t okmask = 0xffu;
+                    if constexpr (!FULLT) {
+                        okmask = 0;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (okmask >> it & 1u) dst[it] = *reinterpret_cast<const float4*>(xin + it * in_step + i * 2 * RCH);
+                        for (int it = 0; it < 8; ++it)
+                            if (row_l + it * 4 < M) okmask |= 1u << it;
                     }
-                };
-                request(0, xo[0]);
-                if constexpr (NMINE > 1) request(1, xo[1]);
-                float rs[8], rq[8];                                  // lane-local (sum, sum of squares) of rows it*4 + rd_row
+                    float4 xo[2][8];
+                    auto request = [&](int i, float4 (&dst)[8]) {
 #pragma unroll
-                for (int it = 0; it < 8; ++it) { rs[it] = 0.f; rq[it] = 0.f; }
-                mbar_wait(&tmem_full[acc], acc_phase);
-                tc_fence_after();
+                        for (int it = 0; it < 8; ++it) {
+                            dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((FULLT || (okmask >> it & 1u)) && !(dbg & 4))
+                                asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst[it].x), "=f"(dst[it].y), "=f"(dst[it].z), "=f"(dst[it].w)
+                                             : "l"(xin + it * in_step + i * 2 * RCH) : "memory");
+                        }
+                    };
+                    request(0, xo[0]);
+                    if constexpr (NMINE > 1) request(1, xo[1]);
+                    float rs[8], rq[8];                              // lane-local (sum, sum of squares) of rows it*4 + rd_row
 #pragma unroll
-                for (int i = 0; i < NMINE; ++i) {
-                    const int c = chunk_par + 2 * i;
-                    float v[RCH];
+                    for (int it = 0; it < 8; ++it) { rs[it] = 0.f; rq[it] = 0.f; }
+                    mbar_wait(&tmem_full[acc], acc_phase);
+                    tc_fence_after();
+                    float sh[8];                                     // the shifts of rows it*4 + rd_row
                     {
+                        float my = 0.f;
+                        if (have_prev) {
+                            float s1 = 0.f;
+#pragma unroll
+                            for (int p = 0; p < 8; ++p) s1 += sp_[p].x;
+                            for (int p = 8; p < ex.prev_parts; ++p)  // more than 8 partials: 128-wide tiles of a wide row
+                                s1 += (reinterpret_cast<const float2*>(ex.stats_prev) + (int64_t)(row0 + lane) * ex.prev_parts)[p].x;
+                            my = shp + s1 / (float)N;                // = mean of the row of x_old
+                        }
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) sh[it] = __shfl_sync(0xffffffffu, my, it * 4 + rd_row);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NMINE; ++i) {
+                        const int c = chunk_par + 2 * i;
                         uint32_t r0[32];
                         tmem_ld_32x32(taddr + c * RCH, r0);
                         tmem_ld_wait();
+                        if (i == NMINE - 1) {                        // this warp's TMEM reads of the tile are done
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                        }
+                        __syncwarp();                                // previous read-back of the staging buffer is complete
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-                    }
-                    if (i == NMINE - 1) {                            // this warp's TMEM reads of the tile are done
-                        tc_fence_before();
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + row_off + (((uint32_t)j ^ sw) << 4)),
+                                         "r"(r0[4 * j]), "r"(r0[4 * j + 1]), "r"(r0[4 * j + 2]), "r"(r0[4 * j + 3]) : "memory");
+                        // the bias of this lane's four columns (the same for all its rows): added together with the old values
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bias != nullptr) b4 = *reinterpret_cast<const float4*>(bias_s + c * RCH + rd_ch * 4);
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-                    }
-                    if (bias != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < RCH; j += 4) {
-                            const float4 b = *reinterpret_cast<const float4*>(bias_s + c * RCH + j);
-                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                        }
-                    }
-                    __syncwarp();                                    // previous read-back of the staging buffer is complete
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + row_off + (((uint32_t)j ^ sw) << 4)),
-                                     "r"(__float_as_uint(v[4 * j])), "r"(__float_as_uint(v[4 * j + 1])), "r"(__float_as_uint(v[4 * j + 2])),
-                                     "r"(__float_as_uint(v[4 * j + 3])) : "memory");
-                    __syncwarp();
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int r = it * 4 + rd_row;
-                        float a0, a1, a2, a3;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
-                                     : "r"(stage_u32 + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
-                        if (okmask >> it & 1u) {
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + rd_row;
+                            float a0, a1, a2, a3;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                                         : "r"(stage_u32 + (uint32_t)r * 128u + (((uint32_t)rd_ch ^ ((uint32_t)r & 7u)) << 4)) : "memory");
                             const float4 o = xo[i & 1][it];
-                            a0 += o.x; a1 += o.y; a2 += o.z; a3 += o.w;
-                            *reinterpret_cast<float4*>(xout + it * out_step + i * 2 * RCH) = make_float4(a0, a1, a2, a3);
+                            a0 += o.x + b4.x; a1 += o.y + b4.y; a2 += o.z + b4.z; a3 += o.w + b4.w;
+                            const bool ok = FULLT || (okmask >> it & 1u);
+                            if (ok && !(dbg & 16))
+                                asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(xout + it * out_step + i * 2 * RCH),
+                                             "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
                             a0 -= sh[it]; a1 -= sh[it]; a2 -= sh[it]; a3 -= sh[it];
-                            if (ex.xb != nullptr)
-                                *reinterpret_cast<uint2*>(zout + it * z_step + i * 2 * RCH) = make_uint2(pack2<T16>(a0, a1), pack2<T16>(a2, a3));
+                            if (ok && ex.xb != nullptr && !(dbg & 8))
+                                asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(zout + it * z_step + i * 2 * RCH),
+                                             "r"(pack2<T16>(a0, a1)), "r"(pack2<T16>(a2, a3)) : "memory");
+                            if (!FULLT && !ok) { a0 = 0.f; a1 = 0.f; a2 = 0.f; a3 = 0.f; }
                             rs[it] += (a0 + a1) + (a2 + a3);
-                            rq[it] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                            rq[it] = fmaf(a0, a0, fmaf(a1, a1, fmaf(a2, a2, fmaf(a3, a3, rq[it]))));
                         }
+                        if (i + 2 < NMINE) request(i + 2, xo[i & 1]);
                     }
-                    if (i + 2 < NMINE) request(i + 2, xo[i & 1]);
-                }
-                if (ex.stats_out != nullptr) {
-                    // the 8 lanes that share a row (consecutive lanes) reduce their sums; one (sum, sum of squares) pair per row,
-                    // n-tile and warp parity: every slot has exactly one writer
-                    const int parts = 2 * n_tiles, part = 2 * (tile % n_tiles) + chunk_par;
+                    if (ex.stats_out != nullptr) {
+                        // the 8 lanes that share a row (consecutive lanes) reduce their sums; one (sum, sum of squares) pair per row,
+                        // n-tile and warp parity: every slot has exactly one writer
+                        const int parts = 2 * n_tiles, part = 2 * (tile % n_tiles) + chunk_par;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        float ps = rs[it], pq = rq[it];
-                        ps += __shfl_xor_sync(0xffffffffu, ps, 1); pq += __shfl_xor_sync(0xffffffffu, pq, 1);
-                        ps += __shfl_xor_sync(0xffffffffu, ps, 2); pq += __shfl_xor_sync(0xffffffffu, pq, 2);
-                        ps += __shfl_xor_sync(0xffffffffu, ps, 4); pq += __shfl_xor_sync(0xffffffffu, pq, 4);
-                        if (rd_ch == 0 && (okmask >> it & 1u)) {
-                            const int64_t r = row_l + it * 4;
-                            reinterpret_cast<float2*>(ex.stats_out)[r * parts + part] = make_float2(ps, pq);
-                            if (part == 0) ex.shift_out[r] = sh[it];
+                        for (int it = 0; it < 8; ++it) {
+                            float ps = rs[it], pq = rq[it];
+                            ps += __shfl_xor_sync(0xffffffffu, ps, 1); pq += __shfl_xor_sync(0xffffffffu, pq, 1);
+                            ps += __shfl_xor_sync(0xffffffffu, ps, 2); pq += __shfl_xor_sync(0xffffffffu, pq, 2);
+                            ps += __shfl_xor_sync(0xffffffffu, ps, 4); pq += __shfl_xor_sync(0xffffffffu, pq, 4);
+                            if (rd_ch == 0 && (FULLT || (okmask >> it & 1u))) {
+                                const int64_t r = row_l + it * 4;
+                                reinterpret_cast<float2*>(ex.stats_out)[r * parts + part] = make_float2(ps, pq);
+                                if (part == 0) ex.shift_out[r] = sh[it];
+                            }
                         }
                     }
-                }
+                };
+                if (dbg == 1 || dbg == 2) {                          // measurement switches: consume the tile, store nothing
+                    mbar_wait(&tmem_full[acc], acc_phase);
+                    tc_fence_after();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                } else if (row0 + 32 <= M) body(std::true_type{});
+                else body(std::false_type{});
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : tile + num_units;
                 continue;
@@ -691,7 +718,8 @@ DeviceState& device_state() {
     if (d.num_sms == 0) TC_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
     return d;
 }
-// TAPCLIP_GEMM_DEBUG (measurement only; results are WRONG when set): 1 = skip the epilogue's global stores, 2 = skip the epilogue body
+// TAPCLIP_GEMM_DEBUG (measurement only; results are WRONG when set): 1 = skip the epilogue's global stores, 2 = skip the epilogue body;
+// residual epilogue ablations (bit flags): 4 = no old-value loads, 8 = no 16-bit copy, 16 = no fp32 store, 32 = no L2 prefetch
 int g_debug = getenv("TAPCLIP_GEMM_DEBUG") ? atoi(getenv("TAPCLIP_GEMM_DEBUG")) : 0;
 // TAPCLIP_GEMM_SCHED: 1 = dynamic tile order (atomic counter), 0 = static striding
 int g_dynamic = getenv("TAPCLIP_GEMM_SCHED") ? atoi(getenv("TAPCLIP_GEMM_SCHED")) : 0;
@@ -704,13 +732,7 @@ void launch(const GemmArgs& g, cudaStream_t stream) {
     auto kern = gemm_tc_kernel<BLOCK_N, EPI, ACT, STORE_PRE, F16, CTA2, FOLD>;
     constexpr CUtensorMapDataType DT16 = F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     DeviceState& ds = device_state();
-    static bool configured[64] = {};
-    int dev;
-    TC_CUDA(cudaGetDevice(&dev));
-    if (!configured[dev]) {
-        TC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured[dev] = true;
-    }
+    ensure_dynamic_smem((const void*)kern, C::SMEM_BYTES);
     const CUtensorMap& ta = make_tmap(g.a, DT16, 2, g.M, g.K, g.lda, BLOCK_M, BLOCK_K);
     const CUtensorMap& tb = make_tmap(g.w, DT16, 2, g.N, g.K, g.ldw, C::B_ROWS, BLOCK_K);
     const int out_esz = (EPI == EPI_BF16 || EPI == EPI_BF16_ACTGRAD) ? 2 : 4;

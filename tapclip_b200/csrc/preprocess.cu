@@ -73,10 +73,12 @@ Coeffs precompute_coeffs(int in_size, int out_size) {
 }
 
 struct DevCoeffs { int ksize = 0; int* bounds = nullptr; int* kk = nullptr; std::vector<int> h_bounds; };
-std::map<std::tuple<int, int>, DevCoeffs> g_coeffs;      // (in_size, out_size) -> device tables (single-threaded per process by contract)
+std::map<std::tuple<int, int, int>, DevCoeffs> g_coeffs;      // (device, in_size, out_size) -> device tables (one host thread per process by contract)
 
 const DevCoeffs& device_coeffs(int in_size, int out_size, cudaStream_t st) {
-    auto key = std::make_tuple(in_size, out_size);
+    int dev;
+    TC_CUDA(cudaGetDevice(&dev));
+    auto key = std::make_tuple(dev, in_size, out_size);
     auto it = g_coeffs.find(key);
     if (it != g_coeffs.end()) return it->second;
     Coeffs c = precompute_coeffs(in_size, out_size);
@@ -87,7 +89,9 @@ const DevCoeffs& device_coeffs(int in_size, int out_size, cudaStream_t st) {
     TC_CUDA(cudaMalloc(&d.kk, c.kk.size() * sizeof(int)));
     TC_CUDA(cudaMemcpyAsync(d.bounds, c.bounds.data(), c.bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     TC_CUDA(cudaMemcpyAsync(d.kk, c.kk.data(), c.kk.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    TC_CUDA(cudaStreamSynchronize(st));                     // the host vectors die with this scope (first use of a size pair only)
+    // first use of a size pair only: after this host-side wait the tables are complete for EVERY stream of the device (and the host
+    // vectors may die with this scope)
+    TC_CUDA(cudaStreamSynchronize(st));
     return g_coeffs.emplace(key, std::move(d)).first->second;
 }
 
@@ -137,7 +141,9 @@ __global__ void resample_v_normalize_kernel(const uint8_t* __restrict__ tmp, int
     out[(size_t)2 * R * R + idx] = __fdiv_rn(__fdiv_rn((float)clip8(s2), 255.f) - m2, d2);
 }
 
-DevBuf g_tmp;                 // horizontally resampled rows (uint8), grow-only
+// horizontally resampled rows (uint8), grow-only, one scratch buffer per (device, stream): concurrent callers on different streams
+// or devices never share it
+std::map<std::pair<int, cudaStream_t>, DevBuf> g_tmp;
 
 }  // namespace
 
@@ -154,11 +160,14 @@ void preprocess_image(const uint8_t* img, int H, int W, float* out, int R, int t
     const int row_first = cv.h_bounds[(size_t)top * 2];
     const int row_last = cv.h_bounds[(size_t)(top + R - 1) * 2] + cv.h_bounds[(size_t)(top + R - 1) * 2 + 1];
     const int rows = row_last - row_first;
-    g_tmp.ensure((size_t)rows * R * 3);
-    resample_h_kernel<<<(unsigned)ceil_div((int64_t)rows * R, 256), 256, 0, st>>>(img, W, (uint8_t*)g_tmp.p, rows, R, row_first, left,
+    int dev;
+    TC_CUDA(cudaGetDevice(&dev));
+    DevBuf& tmp = g_tmp[{dev, st}];
+    tmp.ensure((size_t)rows * R * 3);
+    resample_h_kernel<<<(unsigned)ceil_div((int64_t)rows * R, 256), 256, 0, st>>>(img, W, (uint8_t*)tmp.p, rows, R, row_first, left,
                                                                              ch.bounds, ch.kk, ch.ksize);
     TC_LAUNCH_CHECK();
-    resample_v_normalize_kernel<<<(unsigned)ceil_div((int64_t)R * R, 256), 256, 0, st>>>((const uint8_t*)g_tmp.p, R, out, top, row_first,
+    resample_v_normalize_kernel<<<(unsigned)ceil_div((int64_t)R * R, 256), 256, 0, st>>>((const uint8_t*)tmp.p, R, out, top, row_first,
                                                                                     cv.bounds, cv.kk, cv.ksize, mean[0], mean[1], mean[2],
                                                                                     stdv[0], stdv[1], stdv[2]);
     TC_LAUNCH_CHECK();

@@ -299,13 +299,9 @@ void attention_lse(const void* qkv, float* lse, int dt, int S, int N, int H, cud
         const int nwarps = warps_for(N, ntiles), npad = (int)round_up(N, QC);
         const size_t smem = (size_t)(nwarps * 16 + npad) * 128;
         TC_CHECK(smem <= 227 * 1024, "sequence length %d too long for the attention statistics kernel", N);
-        static size_t conf[2] = {0, 0};
         const int which = dt == DT_F16;
-        if (smem > conf[which]) {
-            if (which) TC_CUDA(cudaFuncSetAttribute(attn_lse_mma_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else TC_CUDA(cudaFuncSetAttribute(attn_lse_mma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            conf[which] = smem;
-        }
+        if (which) ensure_dynamic_smem((const void*)attn_lse_mma_kernel<f16>, smem);
+        else ensure_dynamic_smem((const void*)attn_lse_mma_kernel<bf16>, smem);
         dim3 grid((unsigned)(S * H), (unsigned)ntiles);
         if (which) launch_pdl(attn_lse_mma_kernel<f16>, grid, nwarps * 32, smem, stream, (const f16*)qkv, lse, N, H, npad);
         else launch_pdl(attn_lse_mma_kernel<bf16>, grid, nwarps * 32, smem, stream, (const bf16*)qkv, lse, N, H, npad);
@@ -333,13 +329,9 @@ void rollout_step(const void* qkv, const float* lse, const float* r_in, float* r
         const int npad = (int)round_up(N, QC);
         const size_t smem = (size_t)(nwarps * RS_KEYS + npad) * 128 + (size_t)2 * npad * sizeof(float);
         TC_CHECK(smem <= 227 * 1024, "sequence length %d too long for the rollout kernel", N);
-        static size_t conf[2] = {0, 0};
         const int which = dt == DT_F16;
-        if (smem > conf[which]) {
-            if (which) TC_CUDA(cudaFuncSetAttribute(rollout_step_mma_kernel<f16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else TC_CUDA(cudaFuncSetAttribute(rollout_step_mma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            conf[which] = smem;
-        }
+        if (which) ensure_dynamic_smem((const void*)rollout_step_mma_kernel<f16>, smem);
+        else ensure_dynamic_smem((const void*)rollout_step_mma_kernel<bf16>, smem);
         dim3 grid((unsigned)S, (unsigned)ntiles);
         if (which) launch_pdl(rollout_step_mma_kernel<f16>, grid, nwarps * 32, smem, stream, (const f16*)qkv, lse, r_in, r_out, N, H, npad, skip);
         else launch_pdl(rollout_step_mma_kernel<bf16>, grid, nwarps * 32, smem, stream, (const bf16*)qkv, lse, r_in, r_out, N, H, npad, skip);

@@ -253,12 +253,8 @@ void rollout_step_tc(const void* qkv, const float* lse, const float* r_in, float
     const int ntl = (int)ceil_div(N, RT_KEYS);
     const int kpc = rollout_tc_kpc(N);
     const size_t smem = rollout_tc_smem(npad, kpc);
-    static size_t conf[2] = {0, 0};
-    if (smem > conf[f16]) {
-        if (f16) TC_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else TC_CUDA(cudaFuncSetAttribute(rollout_step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conf[f16] = smem;
-    }
+    if (f16) ensure_dynamic_smem((const void*)rollout_step_tc_kernel<true>, smem);
+    else ensure_dynamic_smem((const void*)rollout_step_tc_kernel<false>, smem);
     const unsigned grid = (unsigned)(S * (int)ceil_div(ntl, kpc));
     // tile-major launch order: the key tiles of an image run at the same time and share its Q rows in L2 (1.28 vs 1.52 ms at
     // B=512, N=577: image-major re-reads every row from HBM, 3.8 GB per launch, as 128-byte pieces)

@@ -232,10 +232,10 @@ def test_large_batch_image_tower_on_the_tcgen05_attention_path():
 @pytest.mark.parametrize("mode", ["literal", "intended"])
 @pytest.mark.parametrize("name,C,P,B", [("mini-t512", 6, 5, 3), ("mini-n197", 5, 16, 130)])
 def test_layernorm_folded_into_the_gemms_matches_the_separate_kernels(name, C, P, B, mode, monkeypatch):
-    """Default path (TAPCLIP_FUSE_LN=2): no LayerNorm kernel inside the blocks -- the residual GEMMs emit the 16-bit rows and
+    """TAPCLIP_FUSE_LN=2: no LayerNorm kernel inside the blocks -- the residual GEMMs emit the (row-shifted) 16-bit rows and
     their statistics, the QKV / c_fc GEMMs apply LayerNorm through folded weights, and the residual stream hops through the save
     slots for the backward pass.  Compared with the CPU oracle (forward + ctx gradients) and with the separate-kernel path
-    (TAPCLIP_FUSE_LN=0); TAPCLIP_FUSE_LN=1 folds the text tower only."""
+    (TAPCLIP_FUSE_LN=0, the default); TAPCLIP_FUSE_LN=1 folds the text tower only."""
     ow, om = build_oracle(name, C, P, mode)
     images, labels = synthetic_images(B, get_config(name).image_size), synthetic_labels(B, C)
     om.train()

@@ -69,6 +69,13 @@ def test_c2_train_step_as_benchmarked_vs_oracle():
     _train_step_vs_oracle("ViT-B-16-quickgelu", 128, 65, 16, "C2 ViT-B/16 B=128 C=65 P=16 mixed intended")
 
 
+def test_c2_train_step_with_layernorm_folded_into_the_gemms_vs_oracle(monkeypatch):
+    """The same configuration through the LayerNorm-free blocks (TAPCLIP_FUSE_LN=2: residual GEMMs emitting the shifted 16-bit
+    rows + statistics, folded QKV / c_fc GEMMs): same bars."""
+    monkeypatch.setenv("TAPCLIP_FUSE_LN", "2")
+    _train_step_vs_oracle("ViT-B-16-quickgelu", 128, 65, 16, "C2 ViT-B/16 B=128 C=65 P=16 mixed intended, TAPCLIP_FUSE_LN=2")
+
+
 def test_c5_class_count_train_step_vs_oracle():
     """BASELINE configs[2]/[4] class count: C=345 (text GEMMs with M = 345*93 = 32 085 rows), B=32, train step."""
     _train_step_vs_oracle("ViT-B-16-quickgelu", 32, 345, 16, "C3/C5 ViT-B/16 B=32 C=345 P=16 mixed intended")
