@@ -88,10 +88,19 @@ TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int3
  *   'gate' / 'residual' adjustors (prompt_adjustor.py:38-44), whose small networks run on the host side between the passes.
  * save_for_backward != 0 keeps the activations `tapclip_text_backward` needs (ONE saved forward per handle: the next
  * tapclip_text_forward / tapclip_encode_text replaces them).
- * out_token (nullable): identifies the activations this call saved (0 if none); pass it to tapclip_text_backward. */
+ * out_token (nullable): identifies the activations this call saved (0 if none); pass it to tapclip_text_backward.
+ * gather_epoch > 0 (after tapclip_text_gather_config; multi-GPU): the C rows are this rank's classes [gather_row_lo, gather_row_lo+C)
+ * of n_cls_total; the head kernel ALSO stores them into every rank's symmetric buffer (peer stores over NVLink) and publishes the
+ * epoch there -- the text-feature all-gather of model_wrapper.py:79,83's contraction, fused into the producing kernel.  0 = off. */
 TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const float* tok, int32_t C, int32_t P, int32_t mode,
                          int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat,
-                         int64_t* out_token, void* stream);
+                         int64_t* out_token, int64_t gather_row_lo, int32_t gather_epoch, void* stream);
+
+/* Fused text-feature all-gather: peer_bufs is a HOST array of `world` device pointers, peer_bufs[r] = rank r's symmetric
+ * buffer as mapped into this process (e.g. torch.distributed._symmetric_memory: hdl.buffer_ptrs), each of
+ * 2 * align128(n_cls_total * E * 4) + 32 bytes, zero-initialised: two feature slots used by epoch parity, then 8 int32 flags.
+ * world = 0 switches the feature off.  Epochs are chosen by the caller: the same strictly increasing sequence on every rank. */
+TAPCLIP_API int tapclip_text_gather_config(tapclip_handle h, void* const* peer_bufs, int32_t world, int32_t rank, int64_t n_cls_total);
 
 /* CLIPWrapper.encode_text (clip_wrapper.py:49-51 -> open_clip CLIP.encode_text; SURVEY 8f rank 1 — FullModel never calls
  * it): token_ids int64 [S, context_length] (device) -> out_feat [S,E] (NOT normalised): token + positional embedding,
@@ -100,10 +109,12 @@ TAPCLIP_API int tapclip_encode_text(tapclip_handle h, const int64_t* token_ids, 
 
 /* Rows A5,A11,A12 (model_wrapper.py:41,79,83,90-93): out_img_norm [B,E] = L2-normalised image features,
  * out_logits [B,C] = exp(*logit_scale) * img_norm . text_feat^T.  If labels (int64 [B], device) is
- * non-null: out_loss[0] = sum_b CE_b * inv_batch_total and out_dlogits [B,C] = dloss/dlogits. */
+ * non-null: out_loss[0] = sum_b CE_b * inv_batch_total and out_dlogits [B,C] = dloss/dlogits.  A label outside [0, C) yields NaN.
+ * gather_epoch > 0: text_feat is this rank's symmetric slot of that epoch (tapclip_text_gather_config); the kernel first waits
+ * (bounded) until every rank has published the epoch, so no separate collective or barrier precedes it. */
 TAPCLIP_API int tapclip_logits(tapclip_handle h, const float* img_feat, const float* text_feat, const float* logit_scale,
                    const int64_t* labels, int32_t B, int32_t C, float inv_batch_total, float* out_img_norm,
-                   float* out_logits, float* out_loss, float* out_dlogits, void* stream);
+                   float* out_logits, float* out_loss, float* out_dlogits, int32_t gather_epoch, void* stream);
 
 /* Backward of the logit contraction: out_d_text [C,E] = exp(s) * dlogits^T . img_norm,
  * out_d_logit_scale[0] = sum dlogits*logits. */

@@ -39,14 +39,15 @@ PROTOTYPES = {
     "tapclip_weights_complete": (C.c_int, [_vp]),
     "tapclip_encode_image": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "tapclip_encode_text": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
-    "tapclip_text_forward": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
+    "tapclip_text_forward": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, C.POINTER(_i64), _i64, _i32, _vp]),
+    "tapclip_text_gather_config": (C.c_int, [_vp, C.POINTER(_vp), _i32, _i32, _i64]),
     "tapclip_op_gemm_stats_parts": (_i32, [_i64]),
     "tapclip_op_gemm_resid": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _i64, _i32, _vp]),
     "tapclip_op_gemm_fold": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp]),
     "tapclip_op_fold_ln_weight": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
     "tapclip_op_row_stats_cast": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
     "tapclip_op_preprocess": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "tapclip_logits": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "tapclip_logits": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "tapclip_logits_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "tapclip_text_backward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "tapclip_adamw_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),

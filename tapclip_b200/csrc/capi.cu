@@ -62,12 +62,21 @@ TAPCLIP_API int tapclip_encode_image(tapclip_handle h, const float* images, int3
 
 TAPCLIP_API int tapclip_text_forward(tapclip_handle h, const float* ctx, const float* tok, int32_t C, int32_t P, int32_t mode,
                          int32_t save_for_backward, float* out_attr_raw, float* out_attr, float* out_text_feat, int64_t* out_token,
-                         void* stream) {
+                         int64_t gather_row_lo, int32_t gather_epoch, void* stream) {
     TC_API_BEGIN
     NEED(h);
     TC_CHECK(C == 0 || (ctx != nullptr && tok != nullptr), "null argument");
-    const int64_t token = h->impl.text_forward(ctx, tok, C, P, mode, save_for_backward != 0, out_attr_raw, out_attr, out_text_feat, S(stream));
+    const int64_t token = h->impl.text_forward(ctx, tok, C, P, mode, save_for_backward != 0, out_attr_raw, out_attr, out_text_feat, S(stream),
+                                               gather_row_lo, gather_epoch);
     if (out_token) *out_token = token;
+    TC_API_END
+}
+
+TAPCLIP_API int tapclip_text_gather_config(tapclip_handle h, void* const* peer_bufs, int32_t world, int32_t rank, int64_t n_cls_total) {
+    TC_API_BEGIN
+    NEED(h);
+    TC_CHECK(world == 0 || peer_bufs != nullptr, "null argument");
+    h->impl.set_text_gather(peer_bufs, world, rank, n_cls_total);
     TC_API_END
 }
 
@@ -81,11 +90,12 @@ TAPCLIP_API int tapclip_encode_text(tapclip_handle h, const int64_t* token_ids, 
 
 TAPCLIP_API int tapclip_logits(tapclip_handle h, const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels,
                    int32_t B, int32_t C, float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss,
-                   float* out_dlogits, void* stream) {
+                   float* out_dlogits, int32_t gather_epoch, void* stream) {
     TC_API_BEGIN
     NEED(h);
     TC_CHECK(img_feat && text_feat && logit_scale && out_img_norm && out_logits, "null argument");
-    h->impl.logits(img_feat, text_feat, logit_scale, labels, B, C, inv_batch_total, out_img_norm, out_logits, out_loss, out_dlogits, S(stream));
+    h->impl.logits(img_feat, text_feat, logit_scale, labels, B, C, inv_batch_total, out_img_norm, out_logits, out_loss, out_dlogits, S(stream),
+                   gather_epoch);
     TC_API_END
 }
 

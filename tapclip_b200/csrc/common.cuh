@@ -414,6 +414,24 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         ::"r"(smem_u32(bar)) : "memory");
 }
 
+// cta_group::2 forms of the same (issued by the leader CTA of a pair; the whole warp runs the control flow)
+__device__ __forceinline__ void umma_2sm_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_elect(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

@@ -120,10 +120,17 @@ std::vector<DevBuf*> Engine::all_bufs() {
 }
 
 // two self-resetting tickets of the head kernels' last-CTA reductions (zeroed once, synchronously, when first needed)
+void Engine::set_text_gather(void* const* peer_bufs, int world, int rank, int64_t n_cls_total) {
+    TC_CHECK(world >= 0 && world <= 8 && rank >= 0 && (world == 0 || rank < world) && n_cls_total >= 0, "bad text-gather configuration");
+    gather.world = world; gather.rank = rank; gather.n_cls = n_cls_total;
+    for (int r = 0; r < 8; ++r) gather.peers[r] = (r < world) ? (uint8_t*)peer_bufs[r] : nullptr;
+    for (int r = 0; r < world; ++r) TC_CHECK(gather.peers[r] != nullptr && ((uintptr_t)gather.peers[r] & 127) == 0, "peer buffer %d missing or misaligned", r);
+}
+
 int* Engine::tickets() {
     if (s_ticket.p == nullptr) {
-        s_ticket.ensure(2 * sizeof(int));
-        TC_CUDA(cudaMemset(s_ticket.p, 0, 2 * sizeof(int)));
+        s_ticket.ensure(4 * sizeof(int));
+        TC_CUDA(cudaMemset(s_ticket.p, 0, 4 * sizeof(int)));
         TC_CUDA(cudaDeviceSynchronize());
     }
     return (int*)s_ticket.p;
@@ -552,7 +559,7 @@ void Engine::encode_image(const float* images, int B, float* out_feat, float* ou
 
 // ---- text side (rows A2, A6-A10) ----------------------------------------------------------------------
 int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw,
-                             float* out_attr, float* out_text_feat, cudaStream_t st) {
+                             float* out_attr, float* out_text_feat, cudaStream_t st, int64_t gather_row_lo, int gather_epoch) {
     TC_CHECK(C >= 0 && P >= 1, "bad class count / prompt length");
     TC_CHECK(mode >= 0 && mode <= 2, "attribution mode must be 0 (literal), 1 (intended) or 2 (intended attribution pass only)");
     const bool attr_only = (mode == 2);
@@ -633,9 +640,23 @@ int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, i
     float* xp = (fused && save) ? (float*)t_save_x.p : x;
     splice_prompts(ctx, tok, attr, PA, xp, C, P, Lc, D, st); ++launches;
     run_blocks(xp, false, save, x_end, pool_stride, pool_offset);
+    PeerScatter ps = {};
+    if (gather_epoch > 0) {
+        TC_CHECK(gather.world > 0 && fuse_head, "fused text-feature gather needs tapclip_text_gather_config and the fused head kernels");
+        TC_CHECK(gather_row_lo >= 0 && gather_row_lo + C <= gather.n_cls, "gathered rows [%lld, %lld) outside the %lld configured classes",
+                 (long long)gather_row_lo, (long long)(gather_row_lo + C), (long long)gather.n_cls);
+        const size_t slot = gather_slot_bytes();
+        for (int r = 0; r < gather.world; ++r) {
+            ps.dst[r] = (float*)(gather.peers[r] + (size_t)(gather_epoch & 1) * slot);
+            ps.flag[r] = (int*)(gather.peers[r] + 2 * slot) + gather.rank;
+        }
+        ps.world = gather.world; ps.epoch = gather_epoch; ps.row_lo = gather_row_lo; ps.ticket = tickets() + 2;
+    }
     if (fuse_head) {
         // K4 (head.cu): pool position T-1, @ text_projection, L2-normalise -- one launch, fp32 rows against the 16-bit weight
-        text_head(x_end, pool_stride, pool_offset, w_tproj, tdt, (float*)t_tfeat.p, (float*)t_inv_norm.p, out_text_feat, C, D, E, st); ++launches;
+        // (+ K5: the rows also go straight into every rank's symmetric buffer)
+        text_head(x_end, pool_stride, pool_offset, w_tproj, tdt, (float*)t_tfeat.p, (float*)t_inv_norm.p, out_text_feat, C, D, E, st,
+                  gather_epoch > 0 ? &ps : nullptr); ++launches;
     } else {
         gather_rows(x_end, t_pooled.p, tdt, C, pool_stride, pool_offset, D, st); ++launches;
         gemm(t_pooled.p, w_tproj, nullptr, t_feat.p, nullptr, C, E, D, EPI_F32, ACT_NONE, tdt, st);
@@ -762,15 +783,23 @@ void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream
 // ---- logits / loss (rows A5, A11, A12) ------------------------------------------------------------------------
 void Engine::logits(const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels, int B, int C,
                     float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss, float* out_dlogits,
-                    cudaStream_t st) {
+                    cudaStream_t st, int gather_epoch) {
     if (B == 0 || C == 0) return;
+    if (gather_epoch > 0) {
+        TC_CHECK(gather.world > 0 && fuse_head && (size_t)(cfg.embed_dim + C + 32) * sizeof(float) <= 48 * 1024 && C == gather.n_cls,
+                 "fused text-feature gather: not configured for %d classes", C);
+        TC_CHECK(text_feat == (const float*)(gather.peers[gather.rank] + (size_t)(gather_epoch & 1) * gather_slot_bytes()),
+                 "text_feat must be this rank's symmetric slot of the epoch");
+    }
     const int E = cfg.embed_dim;
     if (labels) TC_CHECK(out_loss != nullptr, "out_loss is required when labels are given");
     if (fuse_head && (size_t)(E + C + 32) * sizeof(float) <= 48 * 1024) {
         // K4 (head.cu): image L2-norm, logits, cross-entropy, its gradient and the batch mean in ONE launch
         s_rows.ensure((size_t)B * 4);
         logits_ce(img_feat, text_feat, logit_scale, labels, out_img_norm, out_logits, out_loss, out_dlogits, (float*)s_rows.p, tickets(),
-                  B, C, E, inv_batch_total, st);
+                  B, C, E, inv_batch_total, st,
+                  gather_epoch > 0 ? (const int*)(gather.peers[gather.rank] + 2 * gather_slot_bytes()) : nullptr,
+                  gather_epoch > 0 ? gather.world : 0, gather_epoch);
         ++launches;
         return;
     }

@@ -63,6 +63,11 @@ struct Engine {
     DevBuf b_dx, b_dxc, b_dh, b_dln, b_dattn, b_dqkv, b_dfeat, b_dfeatc, b_dpool;
     DevBuf s_rows, s_cls, s_ticket, e_eot, e_pool;
     int* tickets();
+    // K5: text-feature all-gather fused into the head kernel.  peers[r] = rank r's symmetric buffer as mapped into THIS
+    // process: [2 slots][n_cls * E] floats, then 8 int flags (flag[r] = last epoch rank r published here)
+    struct { int world = 0, rank = 0; int64_t n_cls = 0; uint8_t* peers[8] = {}; } gather;
+    size_t gather_slot_bytes() const { return ((size_t)gather.n_cls * cfg.embed_dim * sizeof(float) + 127) & ~(size_t)127; }
+    void set_text_gather(void* const* peer_bufs, int world, int rank, int64_t n_cls_total);
     // TAPCLIP_FUSE_HEAD=0: the head (pool + projection + L2-norm, logits + CE, their backward) as separate launches (A/B parity)
     bool fuse_head = !(getenv("TAPCLIP_FUSE_HEAD") && atoi(getenv("TAPCLIP_FUSE_HEAD")) == 0);
     // activations kept by text_forward(save) for text_backward; `token` identifies the forward that wrote them (a later
@@ -117,13 +122,17 @@ struct Engine {
     bool use_fold(bool vision) const { return cfg.dtype != DT_F32 && fuse_ln >= (vision ? 2 : 1); }
     void encode_image(const float* images, int B, float* out_feat, float* out_cls_rows, float* out_rollout, cudaStream_t st);
     // returns the token of the saved activations (0 when nothing was saved)
+    // gather_epoch > 0 (needs set_text_gather): the normalised features of this rank's classes [gather_row_lo, gather_row_lo + C) are
+    // also stored into every rank's symmetric buffer and the epoch is published to every rank
     int64_t text_forward(const float* ctx, const float* tok, int C, int P, int mode, bool save, float* out_attr_raw, float* out_attr,
-                         float* out_text_feat, cudaStream_t st);
+                         float* out_text_feat, cudaStream_t st, int64_t gather_row_lo = 0, int gather_epoch = 0);
     // token: as returned by the text_forward whose activations are to be used (0 = whatever was saved last); C, P: checked when > 0
     void text_backward(const float* d_text_feat, float* out_dctx, cudaStream_t st, int64_t token = 0, int C = 0, int P = 0);
     void encode_text(const int64_t* ids, int S, float* out_feat, cudaStream_t st);
+    // gather_epoch > 0: text_feat is this rank's symmetric slot of that epoch; the kernel first waits for every rank's flag
     void logits(const float* img_feat, const float* text_feat, const float* logit_scale, const int64_t* labels, int B, int C,
-                float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss, float* out_dlogits, cudaStream_t st);
+                float inv_batch_total, float* out_img_norm, float* out_logits, float* out_loss, float* out_dlogits, cudaStream_t st,
+                int gather_epoch = 0);
     void logits_backward(const float* dlogits, const float* logits_, const float* img_norm, const float* logit_scale, int B, int C,
                          float* out_d_text, float* out_d_scale, cudaStream_t st);
 };

@@ -145,7 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     // work decomposition: a "unit" is one CTA (CTA2 = false) or one 2-CTA cluster owning 256 rows (CTA2 = true)
     constexpr int UNIT_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
-    const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+    const uint32_t cta_rank = CTA2 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;      // through a shuffle: warp-uniform for ptxas
     const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int num_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int m_tiles = (M + UNIT_M - 1) / UNIT_M, n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
@@ -256,7 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 tile = dyn ? sched_fetch(sched_full, sched_empty, sched_tile, cslot, cphase) : tile + num_units;
             }
-        } else if (lane == 0 && cta_rank == 0) {
+        } else if (cta_rank == 0) {
+            // leader CTA of the pair: the same warp-converged issue loop (the pair rank is warp-uniform), cta_group::2 forms
             constexpr uint32_t idesc = make_idesc(UNIT_M, BLOCK_N, F16);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -270,11 +271,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * STAGE_A_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * C::STAGE_B_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit_2sm(&empty_bar[stage]);             // frees this smem stage in both CTAs of the pair
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) umma_2sm_elect(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit_2sm_elect(&empty_bar[stage]);       // frees this smem stage in both CTAs of the pair
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2sm(&tmem_full[acc]);                   // accumulator ready for the epilogue warps of both CTAs
+                umma_commit_2sm_elect(&tmem_full[acc]);             // accumulator ready for the epilogue warps of both CTAs
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }

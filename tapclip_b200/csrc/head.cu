@@ -73,10 +73,16 @@ __device__ __forceinline__ void matvec_rows(const float* vec_s, const TW* __rest
     }
 }
 
+// K5: the text-feature all-gather fused into the kernel that produces the features.  Every rank owns a symmetric buffer
+// (torch symmetric memory: the same allocation mapped into every peer's address space over NVLink); the head kernel stores its
+// normalised rows straight into EVERY rank's buffer at the rows' global class offsets (peer stores), then the last CTA publishes
+// `epoch` in flag slot [rank] of every peer (system-scope release).  The consumer (logits_ce) spins on its local flags until every
+// rank's epoch has arrived (system-scope acquire).  Two slots, used by epoch parity: a rank that runs one step ahead never
+// overwrites rows a slower peer is still reading.
 template <typename TW>
 __global__ void __launch_bounds__(HEAD_THREADS)
 text_head_kernel(const float* __restrict__ x, int64_t row_stride, int64_t row_offset, const TW* __restrict__ w_proj /*[E,D]*/,
-                 float* __restrict__ tfeat, float* __restrict__ inv_norm, float* __restrict__ tfeat_copy, int D, int E) {
+                 float* __restrict__ tfeat, float* __restrict__ inv_norm, float* __restrict__ tfeat_copy, int D, int E, const PeerScatter ps) {
     pdl_wait_and_trigger();
     extern __shared__ float sm[];
     float* xs = sm;                 // [D]
@@ -96,6 +102,19 @@ text_head_kernel(const float* __restrict__ x, int64_t row_stride, int64_t row_of
         const float v = fs[e] * inv;
         tfeat[(int64_t)c * E + e] = v;
         if (tfeat_copy) tfeat_copy[(int64_t)c * E + e] = v;
+        for (int r = 0; r < ps.world; ++r) ps.dst[r][(ps.row_lo + c) * E + e] = v;          // peer stores (NVLink), incl. this rank's own buffer
+    }
+    if (ps.world > 0) {
+        __shared__ int is_last;
+        __threadfence_system();                          // this CTA's peer stores are ordered before its ticket
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = (atomicAdd(ps.ticket, 1) == (int)gridDim.x - 1);
+        __syncthreads();
+        if (is_last && threadIdx.x < ps.world) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.b32 [%0], %1;" ::"l"(ps.flag[threadIdx.x]), "r"(ps.epoch) : "memory");
+            if (threadIdx.x == 0) *ps.ticket = 0;
+        }
     }
 }
 
@@ -142,11 +161,27 @@ __device__ __forceinline__ void last_block_sum(const float* partial, int n, floa
 }
 
 __global__ void __launch_bounds__(HEAD_THREADS)
-logits_ce_kernel(const float* __restrict__ img, const float* __restrict__ txt, const float* __restrict__ logit_scale,
+logits_ce_kernel(const float* __restrict__ img, const float* txt, const float* __restrict__ logit_scale,
                  const int64_t* __restrict__ labels, float* __restrict__ img_norm, float* __restrict__ logits, float* __restrict__ loss,
                  float* __restrict__ dlogits, float* __restrict__ row_loss, int* __restrict__ ticket, int B, int C, int E,
-                 float inv_batch_total) {
+                 float inv_batch_total, const int* wait_flags, int wait_world, int wait_epoch) {
     pdl_wait_and_trigger();
+    if (wait_world > 0) {
+        // K5 consumer side: the text features in `txt` (this rank's symmetric buffer) are complete once every rank has published
+        // the epoch.  Bounded spin: a peer that never arrives becomes a trap, not a hung GPU.
+        if (threadIdx.x < wait_world) {
+            const long long t0 = clock64();
+            int v;
+            do {
+                asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+                if (v < wait_epoch && clock64() - t0 > 20000000000LL) {
+                    printf("tapclip: rank %d never published text-feature epoch %d (flag %d)\n", (int)threadIdx.x, wait_epoch, v);
+                    __trap();
+                }
+            } while (v < wait_epoch);
+        }
+        __syncthreads();
+    }
     extern __shared__ float sm[];
     float* is = sm;                 // [E] normalised image row
     float* ls = sm + E;             // [C] logits of this row
@@ -162,7 +197,7 @@ logits_ce_kernel(const float* __restrict__ img, const float* __restrict__ txt, c
     for (int c = warp; c < C; c += nw) {
         float s = 0.f;
         for (int e = lane * 4; e < E; e += 128) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(txt + (int64_t)c * E + e));
+            const float4 t = *reinterpret_cast<const float4*>(txt + (int64_t)c * E + e);      // may be peer-written: no read-only path
             s += (is[e] * t.x + is[e + 1] * t.y) + (is[e + 2] * t.z + is[e + 3] * t.w);
         }
         s = warp_sum(s);
@@ -218,13 +253,15 @@ logits_bwd_fused_kernel(const float* __restrict__ dlogits, const float* __restri
 }  // namespace
 
 void text_head(const float* x, int64_t row_stride, int64_t row_offset, const void* w_proj, int w_dt, float* tfeat, float* inv_norm,
-               float* tfeat_copy, int C, int D, int E, cudaStream_t stream) {
+               float* tfeat_copy, int C, int D, int E, cudaStream_t stream, const PeerScatter* peers) {
+    PeerScatter ps = {};
+    if (peers) ps = *peers;
     if (C == 0) return;
     TC_CHECK(D % 8 == 0 && E % 8 == 0, "text_head needs D %% 8 == 0 and E %% 8 == 0");
     const size_t smem = (size_t)(D + E + 32) * sizeof(float);
-    if (w_dt == DT_BF16) launch_pdl(text_head_kernel<bf16>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const bf16*)w_proj, tfeat, inv_norm, tfeat_copy, D, E);
-    else if (w_dt == DT_F16) launch_pdl(text_head_kernel<f16>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const f16*)w_proj, tfeat, inv_norm, tfeat_copy, D, E);
-    else launch_pdl(text_head_kernel<float>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const float*)w_proj, tfeat, inv_norm, tfeat_copy, D, E);
+    if (w_dt == DT_BF16) launch_pdl(text_head_kernel<bf16>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const bf16*)w_proj, tfeat, inv_norm, tfeat_copy, D, E, ps);
+    else if (w_dt == DT_F16) launch_pdl(text_head_kernel<f16>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const f16*)w_proj, tfeat, inv_norm, tfeat_copy, D, E, ps);
+    else launch_pdl(text_head_kernel<float>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const float*)w_proj, tfeat, inv_norm, tfeat_copy, D, E, ps);
     TC_LAUNCH_CHECK();
 }
 
@@ -240,13 +277,14 @@ void text_head_bwd(const float* g, const float* tfeat, const float* inv_norm, co
 }
 
 void logits_ce(const float* img, const float* txt, const float* logit_scale, const int64_t* labels, float* img_norm, float* logits,
-               float* loss, float* dlogits, float* row_scratch, int* ticket, int B, int C, int E, float inv_batch_total, cudaStream_t stream) {
+               float* loss, float* dlogits, float* row_scratch, int* ticket, int B, int C, int E, float inv_batch_total, cudaStream_t stream,
+               const int* wait_flags, int wait_world, int wait_epoch) {
     if (B == 0) return;
     TC_CHECK(E % 4 == 0, "embed dim must be a multiple of 4");
     const size_t smem = (size_t)(E + C + 32) * sizeof(float);
     TC_CHECK(smem <= 48 * 1024, "too many classes for the fused logits kernel (%d)", C);
     launch_pdl(logits_ce_kernel, B, HEAD_THREADS, smem, stream, img, txt, logit_scale, labels, img_norm, logits, loss, dlogits, row_scratch,
-               ticket, B, C, E, inv_batch_total);
+               ticket, B, C, E, inv_batch_total, wait_flags, wait_world, wait_epoch);
     TC_LAUNCH_CHECK();
 }
 

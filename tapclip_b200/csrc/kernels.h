@@ -35,18 +35,29 @@ void l2norm_fwd(const float* x, float* out, float* inv_norm, int64_t rows, int d
 void l2norm_bwd(const float* g, const float* xhat, const float* inv_norm, float* dx, void* dx_cast, int cast_dt,
                 int64_t rows, int d, cudaStream_t stream);
 
-// ---- head.cu (K4) ------------------------------------------------------------------------------------
+// ---- head.cu (K4, K5) ---------------------------------------------------------------------------------
+// K5: where text_head also stores its rows (peer-mapped symmetric buffers of all ranks, this rank included) and publishes an epoch
+struct PeerScatter {
+    float* dst[8];        // per rank: base of the [n_cls_total, E] slot of this epoch's parity
+    int* flag[8];         // per rank: &flags[this rank] in that rank's buffer
+    int world;            // 0 = no peer stores
+    int epoch;
+    int64_t row_lo;       // global class index of this rank's first row
+    int* ticket;          // one int, zero before the first use (self-resetting)
+};
 // tfeat[c,:] = l2norm(x[(c*row_stride + row_offset),:] @ w_proj^T), w_proj [E,D] of type w_dt; inv_norm[c] = 1/||.||;
 // tfeat_copy (optional) receives the same rows (the caller's output tensor)
 void text_head(const float* x, int64_t row_stride, int64_t row_offset, const void* w_proj, int w_dt, float* tfeat, float* inv_norm,
-               float* tfeat_copy, int C, int D, int E, cudaStream_t stream);
+               float* tfeat_copy, int C, int D, int E, cudaStream_t stream, const PeerScatter* peers = nullptr);
 // backward of text_head: dx[(c*row_stride + row_offset),:] = l2norm'(g[c,:]) @ wt_proj^T (wt_proj [D,E], gradient type) + 16-bit copy
 void text_head_bwd(const float* g, const float* tfeat, const float* inv_norm, const void* wt_proj, int w_dt, float* dx, void* dx_cast,
                    int cast_dt, int64_t row_stride, int64_t row_offset, int C, int D, int E, cudaStream_t stream);
 // img_norm = l2norm(img); logits = exp(*logit_scale) * img_norm . txt^T; with labels: loss[0] = sum_b CE_b * inv_batch_total (summed
 // by the last CTA in row order), dlogits = dloss/dlogits.  row_scratch [B] floats, ticket: one int, zero before the first use
+// wait_world > 0 (K5): txt is this rank's symmetric slot; the kernel first waits until wait_flags[r] >= wait_epoch for every rank r
 void logits_ce(const float* img, const float* txt, const float* logit_scale, const int64_t* labels, float* img_norm, float* logits,
-               float* loss, float* dlogits, float* row_scratch, int* ticket, int B, int C, int E, float inv_batch_total, cudaStream_t stream);
+               float* loss, float* dlogits, float* row_scratch, int* ticket, int B, int C, int E, float inv_batch_total, cudaStream_t stream,
+               const int* wait_flags = nullptr, int wait_world = 0, int wait_epoch = 0);
 // d_txt[c,:] = exp(s) * sum_b dlogits[b,c] * img[b,:];  d_scale[0] = sum dlogits * logits.  class_scratch [C] floats, ticket as above
 void logits_bwd_fused(const float* dlogits, const float* logits, const float* img, const float* logit_scale, float* d_txt, float* d_scale,
                       float* class_scratch, int* ticket, int B, int C, int E, cudaStream_t stream);

@@ -81,7 +81,14 @@ class Engine:
         _lib.check(self.lib.tapclip_encode_text(self._h, _lib.ptr(ids), ids.shape[0], _lib.ptr(feat), _lib.stream_ptr()))
         return feat
 
-    def text_forward(self, ctx: torch.Tensor, tok: torch.Tensor, mode: str, save_for_backward: bool):
+    def set_text_gather(self, peer_ptrs, rank: int, n_cls_total: int):
+        """K5: symmetric buffers of all ranks (device pointers as mapped into this process) for the fused text-feature gather."""
+        world = len(peer_ptrs)
+        arr = (C.c_void_p * max(world, 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        _lib.check(self.lib.tapclip_text_gather_config(self._h, arr, world, rank, n_cls_total))
+
+    def text_forward(self, ctx: torch.Tensor, tok: torch.Tensor, mode: str, save_for_backward: bool, gather=None):
+        """``gather`` = (row_lo, epoch): also store the features into every rank's symmetric buffer (see set_text_gather)."""
         _check_cuda_f32(ctx, "ctx")
         _check_cuda_f32(tok, "tok")
         cfg = self.cfg
@@ -95,7 +102,7 @@ class Engine:
         token = C.c_int64(0)
         _lib.check(self.lib.tapclip_text_forward(self._h, _lib.ptr(ctx), _lib.ptr(tok), Cn, P, _lib.ATTR_MODE[mode],
                                                  1 if save_for_backward else 0, _lib.ptr(raw), _lib.ptr(attr), _lib.ptr(feat),
-                                                 C.byref(token), _lib.stream_ptr()))
+                                                 C.byref(token), gather[0] if gather else 0, gather[1] if gather else 0, _lib.stream_ptr()))
         self.last_forward_token = int(token.value)      # identifies the saved activations; text_backward(token=...) checks it
         return feat, attr, raw
 
@@ -109,10 +116,10 @@ class Engine:
         attr = torch.empty(Cn, P, device=ctx.device, dtype=torch.float32)
         raw = torch.empty(Cn, P, device=ctx.device, dtype=torch.float32)
         _lib.check(self.lib.tapclip_text_forward(self._h, _lib.ptr(ctx), _lib.ptr(tok), Cn, P, _lib.ATTR_MODE["attribution_only"], 0,
-                                                 _lib.ptr(raw), _lib.ptr(attr), None, None, _lib.stream_ptr()))
+                                                 _lib.ptr(raw), _lib.ptr(attr), None, None, 0, 0, _lib.stream_ptr()))
         return attr, raw
 
-    def logits(self, img_feat, text_feat, logit_scale, labels=None, inv_batch_total=None):
+    def logits(self, img_feat, text_feat, logit_scale, labels=None, inv_batch_total=None, gather_epoch=0):
         B, Cn = img_feat.shape[0], text_feat.shape[0]
         dev = img_feat.device
         img_norm = torch.empty_like(img_feat)
@@ -127,7 +134,7 @@ class Engine:
         inv = float(inv_batch_total) if inv_batch_total is not None else (1.0 / max(B, 1))
         _lib.check(self.lib.tapclip_logits(self._h, _lib.ptr(img_feat), _lib.ptr(text_feat), _lib.ptr(logit_scale), _lib.ptr(labels),
                                            B, Cn, inv, _lib.ptr(img_norm), _lib.ptr(logits), _lib.ptr(loss), _lib.ptr(dlogits),
-                                           _lib.stream_ptr()))
+                                           int(gather_epoch), _lib.stream_ptr()))
         return logits, loss, dlogits, img_norm
 
     def logits_backward(self, dlogits, logits, img_norm, logit_scale):

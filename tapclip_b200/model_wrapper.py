@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from .attribution_monitor import AttributionMonitor
-from .parallel import ClassSharding, all_gather_rows, all_reduce_sum_
+from .parallel import ClassSharding, TextGather, all_gather_rows, all_reduce_sum_
 from .prompt_adjustor import PromptAdjustor
 from .prompt_learner import PromptLearner
 
@@ -46,13 +46,23 @@ class _TapClipFunction(torch.autograd.Function):
 
         # The two towers are independent until the logit contraction: the (small, launch-bound) text passes run on a
         # side stream and fill the image tower's kernel tails; joined before the logits.
+        # multi-GPU: the text-feature all-gather is either fused into the head kernel (peer stores into every rank's symmetric buffer,
+        # parallel.TextGather; used whenever the features are recomputed per step) or one NCCL all-gather (cached eval features, gloo)
+        tg = model._text_gather(shard, n_cls, images.device, need_grad)
+        epoch = tg.next_epoch() if tg is not None else 0
+        gather = (lo, epoch) if tg is not None else None
+
+        def text_side():
+            local, attr_l, raw_l = model._text_features(lo, hi, need_grad, adjusted, gather)   # rows A6-A10, this rank's classes
+            feat = tg.slot(epoch) if tg is not None else all_gather_rows(local, shard, n_cls)   # [C, E]
+            return local, attr_l, raw_l, feat
+
         side = model._side_stream(images.device)
         if side is not None:
             main = torch.cuda.current_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad, adjusted)   # rows A6-A10, this rank's classes
-                text_feat = all_gather_rows(text_local, shard, n_cls)             # [C, E]; the collective hides behind the image tower too
+                text_local, attr_local, raw_local, text_feat = text_side()        # the collective hides behind the image tower too
             img_feat = model._encode_image(images)                                # row A4 (+ A-ext probes)
             main.wait_stream(side)
             for t in (text_local, attr_local, raw_local, text_feat):
@@ -60,12 +70,12 @@ class _TapClipFunction(torch.autograd.Function):
                     t.record_stream(main)
         else:
             img_feat = model._encode_image(images)
-            text_local, attr_local, raw_local = model._text_features(lo, hi, need_grad, adjusted)
-            text_feat = all_gather_rows(text_local, shard, n_cls)                 # [C, E]
+            text_local, attr_local, raw_local, text_feat = text_side()
         ctx.reduced = None
+        ge = {"gather_epoch": epoch} if epoch else {}
         if labels is not None:
             b_total = shard.global_batch(images.shape[0])
-            logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale, labels, 1.0 / b_total)
+            logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale, labels, 1.0 / b_total, **ge)
             if shard.world > 1 and (need_grad or logit_scale.requires_grad):
                 # ONE collective for the whole logit head: the CE gradient is already known here (the fused logits kernel emits
                 # dloss/dlogits), so d T^ [C,E], d logit_scale and the loss are reduced together; backward scales the cached
@@ -79,7 +89,7 @@ class _TapClipFunction(torch.autograd.Function):
             elif shard.world > 1:
                 loss = all_reduce_sum_(loss.clone(), shard)
         else:
-            logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale)
+            logits, loss, dlogits_ce, img_norm = eng.logits(img_feat, text_feat, logit_scale, **ge)
         if adjusted is None:
             model.clip.attention_maps[:] = [raw_local if raw_local is not None else attr_local]   # compact probe, see clip_wrapper.py
             model.last_attribution = attr_local
@@ -154,6 +164,8 @@ class FullModel(nn.Module):
         self.last_attribution = None
         self.overlap_towers = overlap_towers
         self._side = None
+        self.fused_gather = True          # multi-GPU: text-feature all-gather fused into the head kernel when available (TextGather)
+        self._tg = None
         # north-star extension (SURVEY 8a row A-ext, not in the reference): None | 'cls' (per-layer, per-head CLS-row
         # attention probabilities [B,L,H,N]) | 'rollout' (additionally the attention-rollout map [B,N-1]); emitted by the
         # same image pass that produces the features, returned in the forward() dict
@@ -193,6 +205,20 @@ class FullModel(nn.Module):
     def _sharding(self) -> ClassSharding:
         return ClassSharding.current(self.distributed)
 
+    def _text_gather(self, shard, n_cls, device, need_grad):
+        """The fused text-feature gather (parallel.TextGather) when it applies: several ranks over NCCL on CUDA, and text features
+        that are recomputed by this forward (training, or eval without the feature cache)."""
+        if shard.world == 1 or not self.fused_gather:
+            return None
+        if self.cache_text_features and not need_grad and not self.training:
+            return None                                                           # cached eval features: one NCCL all-gather per ctx version
+        if self._tg is None or self._tg.n_cls != n_cls:
+            if not TextGather.available(device):
+                self.fused_gather = False
+                return None
+            self._tg = TextGather(self.clip.engine, shard, n_cls, self.clip.model.cfg.embed_dim, device)
+        return self._tg
+
     def _adjusted_path(self):
         """'gate' / 'residual': the adjusted context is built by torch ops outside the engine (prompt_adjustor.py:38-44)."""
         return self.prompt_adjustor.method != "scale"
@@ -212,12 +238,12 @@ class FullModel(nn.Module):
         self.last_attribution = attr
         return self.prompt_adjustor(bank, attr)            # attr [C,P] or [C,1]: broadcasts exactly like the reference's [B,1,1]
 
-    def _text_features(self, lo, hi, need_grad, adjusted=None):
+    def _text_features(self, lo, hi, need_grad, adjusted=None, gather=None):
         """Rows A6-A10 for classes [lo, hi).  With ctx unchanged and no gradient needed (evaluation: the reference
         recomputes the text side for every batch, test_cross_domain.py:84) the result is reused."""
         pl = self.prompt_learner
         if adjusted is not None:                                               # feature pass on the host-adjusted context
-            return self.clip.engine.text_forward(adjusted[lo:hi].contiguous(), pl.flat_tok()[lo:hi], "literal", need_grad)
+            return self.clip.engine.text_forward(adjusted[lo:hi].contiguous(), pl.flat_tok()[lo:hi], "literal", need_grad, **({"gather": gather} if gather else {}))
         ctx_bank = pl.flat_ctx()
         use_cache = self.cache_text_features and not need_grad and not self.training
         if use_cache:
@@ -225,7 +251,7 @@ class FullModel(nn.Module):
                    self.clip.engine.weight_generation)
             if self._text_cache is not None and self._text_cache[0] == key:
                 return self._text_cache[1]
-        out = self.clip.engine.text_forward(ctx_bank[lo:hi], pl.flat_tok()[lo:hi], self.clip.attribution, need_grad)
+        out = self.clip.engine.text_forward(ctx_bank[lo:hi], pl.flat_tok()[lo:hi], self.clip.attribution, need_grad, **({"gather": gather} if gather else {}))
         self._text_cache = (key, out) if use_cache else None
         return out
 

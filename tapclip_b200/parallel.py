@@ -12,6 +12,7 @@ collective and stripped afterwards.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -81,6 +82,55 @@ def all_gather_rows(local: torch.Tensor, shard: ClassSharding, n_rows_total: int
     out = local.new_empty(shard.world * m, width)
     dist.all_gather_into_tensor(out, src, group=shard.group)
     return out if even else out.index_select(0, _unpad_index(shard, n_rows_total, local.device))
+
+
+class TextGather:
+    """Fused text-feature all-gather: every rank owns a symmetric buffer (``torch.distributed._symmetric_memory``:
+    one allocation mapped into every peer's address space over NVLink / NVSwitch).  The engine's head kernel stores the
+    normalised text features of this rank's classes straight into EVERY rank's buffer (peer stores from the L2-norm epilogue)
+    and publishes an epoch flag; the logits kernel waits on the flags.  No NCCL call, no extra launch, no barrier.
+
+    Buffer layout (bytes): two feature slots ``[n_cls, E]`` fp32 (used by epoch parity: a rank one step ahead never overwrites rows a
+    slower peer still reads), each padded to 128 bytes, then 8 int32 flags.
+    """
+
+    def __init__(self, engine, shard: ClassSharding, n_cls: int, embed_dim: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.n_cls, self.embed_dim = n_cls, embed_dim
+        self.slot_floats = ((n_cls * embed_dim * 4 + 127) // 128 * 128) // 4
+        self.buf = symm.empty(2 * self.slot_floats + 8, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        group = shard.group if shard.group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.buf, group)
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(group=shard.group)                   # every rank's zeroed buffer is mapped before the first peer store
+        engine.set_text_gather(list(self.hdl.buffer_ptrs), shard.rank, n_cls)
+        self.epoch = 0
+
+    def next_epoch(self) -> int:
+        """Called once per forward on every rank (ranks run in lockstep: same sequence everywhere)."""
+        self.epoch += 1
+        return self.epoch
+
+    def slot(self, epoch: int) -> torch.Tensor:
+        """This rank's ``[n_cls, E]`` view of the slot that holds (or will hold) the features of ``epoch``."""
+        o = (epoch & 1) * self.slot_floats
+        return self.buf[o: o + self.n_cls * self.embed_dim].view(self.n_cls, self.embed_dim)
+
+    @staticmethod
+    def available(device) -> bool:
+        if os.environ.get("TAPCLIP_FUSED_GATHER", "1") == "0":
+            return False
+        if torch.device(device).type != "cuda" or not (dist.is_available() and dist.is_initialized()):
+            return False
+        if dist.get_backend() != "nccl" or dist.get_world_size() > 8:
+            return False
+        try:
+            import importlib
+            importlib.import_module("torch.distributed._symmetric_memory")
+        except Exception:
+            return False
+        return True
 
 
 def all_reduce_sum_(t: torch.Tensor, shard: ClassSharding) -> torch.Tensor:

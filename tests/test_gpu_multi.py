@@ -26,23 +26,38 @@ g = torch.Generator().manual_seed(1)
 images = torch.randn(B * world, 3, 64, 64, generator=g).cuda()
 labels = torch.randint(0, C, (B * world,), generator=g).cuda()
 model.train()
-out = model(images[rank * B:(rank + 1) * B].contiguous(), labels[rank * B:(rank + 1) * B].contiguous())
-out["loss"].backward()
+opt = tb.FusedAdamW(model, lr=2e-3, weight_decay=0.01)
+mine = slice(rank * B, (rank + 1) * B)
+for step in range(3):                                 # three steps: both parities of the fused gather's slots, updated ctx
+    out = model(images[mine].contiguous(), labels[mine].contiguous())
+    opt.zero_grad()
+    out["loss"].backward()
+    if step < 2:
+        opt.step()
 grad = torch.stack([p.grad for p in model.prompt_learner.context_bank.values()])
+model.eval()
+model.cache_text_features = False
+with torch.no_grad():
+    ev = model(images[mine].contiguous())["logits"]
 torch.save({"logits": out["logits"].detach().cpu(), "loss": out["loss"].detach().cpu(), "grad": grad.cpu(),
-            "sgrad": model.logit_scale.grad.cpu()}, os.path.join(os.environ["TAPCLIP_OUT"], f"r{rank}.pt"))
+            "sgrad": model.logit_scale.grad.cpu(), "eval_logits": ev.cpu(), "fused_gather": model._tg is not None,
+            "epoch": model._tg.epoch if model._tg is not None else 0},
+           os.path.join(os.environ["TAPCLIP_OUT"], f"r{rank}.pt"))
 dist.destroy_process_group()
 '''
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_nccl_matches_single_gpu():
+@pytest.mark.parametrize("fused_gather", ["1", "0"])
+def test_two_gpu_nccl_matches_single_gpu(fused_gather):
+    """fused_gather=1: the text features cross NVLink as peer stores from the head kernel into every rank's symmetric buffer and the
+    logits kernel waits on epoch flags (parallel.TextGather, no NCCL call on that path); 0: one NCCL all-gather."""
     import tapclip_b200 as tb
     world, C, P, B = 2, 7, 4, 4
     with tempfile.TemporaryDirectory() as d:
         script = os.path.join(d, "worker.py")
         open(script, "w").write(WORKER)
-        env = dict(os.environ, TAPCLIP_ROOT=ROOT, TAPCLIP_OUT=d)
+        env = dict(os.environ, TAPCLIP_ROOT=ROOT, TAPCLIP_OUT=d, TAPCLIP_FUSED_GATHER=fused_gather)
         subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
                         "127.0.0.1", "--master-port", "29533", script], check=True, env=env, timeout=600)
         parts = [torch.load(os.path.join(d, f"r{r}.pt")) for r in range(world)]
@@ -53,9 +68,21 @@ def test_two_gpu_nccl_matches_single_gpu():
     images = torch.randn(B * world, 3, 64, 64, generator=g).cuda()
     labels = torch.randint(0, C, (B * world,), generator=g).cuda()
     model.train()
-    out = model(images, labels)
-    out["loss"].backward()
+    opt = tb.FusedAdamW(model, lr=2e-3, weight_decay=0.01)
+    for step in range(3):
+        out = model(images, labels)
+        opt.zero_grad()
+        out["loss"].backward()
+        if step < 2:
+            opt.step()
     grad = torch.stack([p.grad for p in model.prompt_learner.context_bank.values()]).cpu()
+    model.eval()
+    with torch.no_grad():
+        ev = model(images)["logits"].cpu()
+    assert all(p["fused_gather"] == (fused_gather == "1") for p in parts)
+    if fused_gather == "1":
+        assert all(p["epoch"] == 4 for p in parts)                 # three train steps + one uncached eval forward
+    assert (torch.cat([p["eval_logits"] for p in parts], 0) - ev).abs().max().item() < 1e-5
     logits = torch.cat([p["logits"] for p in parts], 0)
     assert (logits - out["logits"].detach().cpu()).abs().max().item() < 1e-5
     for p in parts:
