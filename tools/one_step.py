@@ -10,6 +10,8 @@ B, C, P = 128, 65, 16
 clip = tb.CLIPWrapper("ViT-B-16-quickgelu", None, "cuda", seed=0, attribution="intended", dtype="mixed")
 torch.manual_seed(4)
 model = tb.FullModel([f"class_{i:03d}" for i in range(C)], clip, prompt_len=P, cache_text_features=False)
+if os.environ.get("TAPCLIP_NO_OVERLAP") == "1":      # image tower first, then the text side, on one stream (ncu -s/-c by launch order)
+    model.overlap_towers = False
 opt = tb.FusedAdamW(model, lr=2e-3, weight_decay=0.01)
 model.train()
 g = torch.Generator().manual_seed(1)
