@@ -202,6 +202,7 @@ void Engine::load_weight(const std::string& name, const float* data, int ndim, c
         if (!shape_is(ndim, shape, {dt, E})) bad_shape();
         w_tproj = store(name, data, dt, E, dt, true, tdt, st);                  // [E, D] forward operand
         wt_tproj = store(name + "#T", data, dt, E, E, false, gdt, st);          // [D, E] dgrad operand
+        wde_tproj = store(name + "#DE", data, dt, E, E, false, tdt, st);        // [D, E] in the forward type: the head kernel's layout
         return;
     }
     // transformer blocks
@@ -655,7 +656,7 @@ int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, i
     if (fuse_head) {
         // K4 (head.cu): pool position T-1, @ text_projection, L2-normalise -- one launch, fp32 rows against the 16-bit weight
         // (+ K5: the rows also go straight into every rank's symmetric buffer)
-        text_head(x_end, pool_stride, pool_offset, w_tproj, tdt, (float*)t_tfeat.p, (float*)t_inv_norm.p, out_text_feat, C, D, E, st,
+        text_head(x_end, pool_stride, pool_offset, wde_tproj, tdt, (float*)t_tfeat.p, (float*)t_inv_norm.p, out_text_feat, C, D, E, st,
                   gather_epoch > 0 ? &ps : nullptr); ++launches;
     } else {
         gather_rows(x_end, t_pooled.p, tdt, C, pool_stride, pool_offset, D, st); ++launches;
@@ -725,7 +726,7 @@ void Engine::text_backward(const float* d_text_feat, float* out_dctx, cudaStream
     TC_CUDA(cudaMemsetAsync(b_dx.p, 0, (size_t)M * D * 4, st));
     TC_CUDA(cudaMemsetAsync(b_dxc.p, 0, (size_t)M * D * esz, st));
     if (fuse_head) {
-        text_head_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, wt_tproj, gdt, (float*)b_dx.p, b_dxc.p, gdt, T, T - 1,
+        text_head_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, w_tproj, tdt, (float*)b_dx.p, b_dxc.p, gdt, T, T - 1,
                       C, D, E, st); ++launches;
     } else {
         l2norm_bwd(d_text_feat, (const float*)t_tfeat.p, (const float*)t_inv_norm.p, (float*)b_dfeat.p, b_dfeatc.p, gdt, C, E, st); ++launches;

@@ -42,7 +42,7 @@ struct Engine {
     std::map<std::string, void*> weights;     // owning storage, keyed by state-dict name (+"#T" for transposes)
     void* w_patch = nullptr; float* cls_emb = nullptr; float* pos_emb = nullptr;
     float *ln_pre_g = nullptr, *ln_pre_b = nullptr, *ln_post_g = nullptr, *ln_post_b = nullptr;
-    void *w_vproj = nullptr, *w_tproj = nullptr, *wt_tproj = nullptr;
+    void *w_vproj = nullptr, *w_tproj = nullptr, *wt_tproj = nullptr, *wde_tproj = nullptr;
     float *tok_emb = nullptr, *text_pos = nullptr, *ln_final_g = nullptr, *ln_final_b = nullptr;   // standard encode_text only
     std::vector<BlockWeights> vis, txt;
 

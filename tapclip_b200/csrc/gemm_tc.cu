@@ -394,13 +394,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         for (int it = 0; it < 8; ++it)
                             if (row_l + it * 4 < M) okmask |= 1u << it;
                     }
+                    // all three streams of this epilogue are touched once: streaming (evict-first) accesses keep the A / W operand tiles,
+                    // which other CTAs re-read, resident in L2
                     float4 xo[2][8];
                     auto request = [&](int i, float4 (&dst)[8]) {
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if ((FULLT || (okmask >> it & 1u)) && !(dbg & 4))
-                                asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst[it].x), "=f"(dst[it].y), "=f"(dst[it].z), "=f"(dst[it].w)
+                                asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dst[it].x), "=f"(dst[it].y), "=f"(dst[it].z), "=f"(dst[it].w)
                                              : "l"(xin + it * in_step + i * 2 * RCH) : "memory");
                         }
                     };
@@ -455,11 +457,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             a0 += o.x + b4.x; a1 += o.y + b4.y; a2 += o.z + b4.z; a3 += o.w + b4.w;
                             const bool ok = FULLT || (okmask >> it & 1u);
                             if (ok && !(dbg & 16))
-                                asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(xout + it * out_step + i * 2 * RCH),
+                                asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(xout + it * out_step + i * 2 * RCH),
                                              "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
                             a0 -= sh[it]; a1 -= sh[it]; a2 -= sh[it]; a3 -= sh[it];
                             if (ok && ex.xb != nullptr && !(dbg & 8))
-                                asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(zout + it * z_step + i * 2 * RCH),
+                                asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(zout + it * z_step + i * 2 * RCH),
                                              "r"(pack2<T16>(a0, a1)), "r"(pack2<T16>(a2, a3)) : "memory");
                             if (!FULLT && !ok) { a0 = 0.f; a1 = 0.f; a2 = 0.f; a3 = 0.f; }
                             rs[it] += (a0 + a1) + (a2 + a3);

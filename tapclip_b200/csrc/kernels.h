@@ -45,11 +45,13 @@ struct PeerScatter {
     int64_t row_lo;       // global class index of this rank's first row
     int* ticket;          // one int, zero before the first use (self-resetting)
 };
-// tfeat[c,:] = l2norm(x[(c*row_stride + row_offset),:] @ w_proj^T), w_proj [E,D] of type w_dt; inv_norm[c] = 1/||.||;
+// tfeat[c,:] = l2norm(x[(c*row_stride + row_offset),:] @ w_proj), w_proj [D,E] (text_projection as stored by open_clip) of type w_dt;
+// inv_norm[c] = 1/||.||;
 // tfeat_copy (optional) receives the same rows (the caller's output tensor)
 void text_head(const float* x, int64_t row_stride, int64_t row_offset, const void* w_proj, int w_dt, float* tfeat, float* inv_norm,
                float* tfeat_copy, int C, int D, int E, cudaStream_t stream, const PeerScatter* peers = nullptr);
-// backward of text_head: dx[(c*row_stride + row_offset),:] = l2norm'(g[c,:]) @ wt_proj^T (wt_proj [D,E], gradient type) + 16-bit copy
+// backward of text_head: dx[(c*row_stride + row_offset),:] = l2norm'(g[c,:]) @ wt_proj (wt_proj [E,D] = text_projection^T, type w_dt)
+// + copy in the gradient type cast_dt
 void text_head_bwd(const float* g, const float* tfeat, const float* inv_norm, const void* wt_proj, int w_dt, float* dx, void* dx_cast,
                    int cast_dt, int64_t row_stride, int64_t row_offset, int C, int D, int E, cudaStream_t stream);
 // img_norm = l2norm(img); logits = exp(*logit_scale) * img_norm . txt^T; with labels: loss[0] = sum_b CE_b * inv_batch_total (summed
