@@ -57,35 +57,46 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
     return t;
 }
 
-template <typename T> __device__ __forceinline__ float2 load2(const T* p);
-template <> __device__ __forceinline__ float2 load2<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-template <> __device__ __forceinline__ float2 load2<bf16>(const bf16* p) {
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
-    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
-}
-template <> __device__ __forceinline__ float2 load2<f16>(const f16* p) {
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
-    return __half22float2(*reinterpret_cast<const __half2*>(&w));
-}
-
-// out[n] = sum_k vec[k] * W[k, n] for n in [0, N), W row-major [K, N]: every thread owns two adjacent columns, so a step of the k loop
-// is one coalesced read of a row of W by the whole CTA, and the (independent) loads of 8 steps are in flight together.  (The first
-// version walked rows of a [N, K] matrix warp by warp -- two dependent L2 round trips per output -- and took 70 us for a
-// 512 x 512 projection of 65 rows; this form takes a few microseconds.)
+// out[n] = sum_k vec[k] * W[k, n] for n in [0, N), W row-major [K, N] (N % 8 == 0).  The CTA's 256 threads form 4 groups of 64; a
+// group takes a quarter of the k range, a thread 8 adjacent columns (one 16-byte / 32-byte load per k step), and 8 k steps are
+// loaded before any of them is used, so 8 independent loads per thread are in flight; the 4 partial results meet in shared memory.
+// (History: walking rows of a [N, K] matrix warp by warp -- two dependent L2 round trips per output -- took 70 us for a 512 x 512
+// projection of 65 rows; two columns per thread with 4-byte loads was still 80 us: the kernel is pure load latency.)
+// part_s: [4][N] floats of scratch; out_s may alias part_s[0].  Needs blockDim.x == 256.
 template <typename TW>
-__device__ __forceinline__ void matvec_cols(const float* vec_s, const TW* __restrict__ W, float* out_s, int N, int K) {
-    for (int n0 = threadIdx.x * 2; n0 < N; n0 += blockDim.x * 2) {
-        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-        int k = 0;
-#pragma unroll 4
-        for (; k + 1 < K; k += 2) {
-            const float2 w0 = load2<TW>(W + (int64_t)k * N + n0), w1 = load2<TW>(W + (int64_t)(k + 1) * N + n0);
-            a0 = fmaf(vec_s[k], w0.x, a0); a1 = fmaf(vec_s[k], w0.y, a1);
-            b0 = fmaf(vec_s[k + 1], w1.x, b0); b1 = fmaf(vec_s[k + 1], w1.y, b1);
+__device__ __forceinline__ void matvec_cols(const float* vec_s, const TW* __restrict__ W, float* out_s, float* part_s, int N, int K) {
+    const int grp = threadIdx.x >> 6, j = threadIdx.x & 63;
+    const int k_lo = (K * grp) / 4, k_hi = (K * (grp + 1)) / 4;
+    for (int n0 = j * 8; n0 < N; n0 += 64 * 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        int k = k_lo;
+        for (; k + 8 <= k_hi; k += 8) {
+            float w[8][8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) load8<TW>(W + (int64_t)(k + u) * N + n0, w[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float v = vec_s[k + u];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, w[u][i], acc[i]);
+            }
         }
-        if (k < K) { const float2 w0 = load2<TW>(W + (int64_t)k * N + n0); a0 = fmaf(vec_s[k], w0.x, a0); a1 = fmaf(vec_s[k], w0.y, a1); }
-        out_s[n0] = a0 + b0; out_s[n0 + 1] = a1 + b1;
+        for (; k < k_hi; ++k) {
+            float w[8];
+            load8<TW>(W + (int64_t)k * N + n0, w);
+            const float v = vec_s[k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, w[i], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part_s[grp * N + n0 + i] = acc[i];
     }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x)
+        out_s[n] = (part_s[n] + part_s[N + n]) + (part_s[2 * N + n] + part_s[3 * N + n]);
+    __syncthreads();
 }
 
 // K5: the text-feature all-gather fused into the kernel that produces the features.  Every rank owns a symmetric buffer
@@ -101,14 +112,13 @@ text_head_kernel(const float* __restrict__ x, int64_t row_stride, int64_t row_of
     pdl_wait_and_trigger();
     extern __shared__ float sm[];
     float* xs = sm;                 // [D]
-    float* fs = sm + D;             // [E]
-    float* red = fs + E;            // [32]
+    float* fs = sm + D;             // [4][E] partial results of the four k groups; fs[0..E) then holds the projected row
+    float* red = fs + 4 * E;        // [32]
     const int c = blockIdx.x;
     const float* xr = x + ((int64_t)c * row_stride + row_offset) * D;
     for (int k = threadIdx.x * 4; k < D; k += HEAD_THREADS * 4) *reinterpret_cast<float4*>(xs + k) = *reinterpret_cast<const float4*>(xr + k);
     __syncthreads();
-    matvec_cols<TW>(xs, w_proj, fs, E, D);
-    __syncthreads();
+    matvec_cols<TW>(xs, w_proj, fs, fs, E, D);
     float q = 0.f;
     for (int e = threadIdx.x; e < E; e += HEAD_THREADS) q += fs[e] * fs[e];
     const float inv = 1.0f / sqrtf(block_sum(q, red));
@@ -141,8 +151,8 @@ text_head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ tfea
     pdl_wait_and_trigger();
     extern __shared__ float sm[];
     float* gs = sm;                 // [E]  d feat (before the projection)
-    float* ds = sm + E;             // [D]
-    float* red = ds + D;
+    float* ds = sm + E;             // [4][D] partials; ds[0..D) then holds the result
+    float* red = ds + 4 * D;
     const int c = blockIdx.x;
     float dot = 0.f;
     for (int e = threadIdx.x; e < E; e += HEAD_THREADS) dot += g[(int64_t)c * E + e] * tfeat[(int64_t)c * E + e];
@@ -151,8 +161,7 @@ text_head_bwd_kernel(const float* __restrict__ g, const float* __restrict__ tfea
     for (int e = threadIdx.x; e < E; e += HEAD_THREADS)
         gs[e] = (g[(int64_t)c * E + e] - tfeat[(int64_t)c * E + e] * dot) * inv;          // d/dx of x / ||x||
     __syncthreads();
-    matvec_cols<TW>(gs, wt_proj, ds, D, E);
-    __syncthreads();
+    matvec_cols<TW>(gs, wt_proj, ds, ds, D, E);
     const int64_t o = ((int64_t)c * row_stride + row_offset) * D;
     for (int k = threadIdx.x; k < D; k += HEAD_THREADS) {
         dx[o + k] = ds[k];
@@ -267,16 +276,21 @@ logits_bwd_fused_kernel(const float* __restrict__ dlogits, const float* __restri
     p = block_sum(p, red);          // also orders the dl[] writes before the reads below
     if (threadIdx.x == 0) class_part[c] = p;
     const float es = expf(__ldg(logit_scale));
-    for (int e = threadIdx.x; e < E; e += HEAD_THREADS) {
+    for (int e = threadIdx.x * 2; e < E; e += HEAD_THREADS * 2) {     // two adjacent columns per thread; 8 rows loaded before any is used
         float s0 = 0.f, s1 = 0.f;
         int b = 0;
-#pragma unroll 4
-        for (; b + 1 < B; b += 2) {                          // independent loads of 8 rows in flight
-            s0 = fmaf(dl[b], __ldg(img + (int64_t)b * E + e), s0);
-            s1 = fmaf(dl[b + 1], __ldg(img + (int64_t)(b + 1) * E + e), s1);
+        for (; b + 8 <= B; b += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float2*>(img + (int64_t)(b + u) * E + e));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s0 = fmaf(dl[b + u], v[u].x, s0); s1 = fmaf(dl[b + u], v[u].y, s1); }
         }
-        if (b < B) s0 = fmaf(dl[b], __ldg(img + (int64_t)b * E + e), s0);
-        d_txt[(int64_t)c * E + e] = es * (s0 + s1);
+        for (; b < B; ++b) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(img + (int64_t)b * E + e));
+            s0 = fmaf(dl[b], v.x, s0); s1 = fmaf(dl[b], v.y, s1);
+        }
+        d_txt[(int64_t)c * E + e] = es * s0; d_txt[(int64_t)c * E + e + 1] = es * s1;
     }
     last_block_sum(class_part, C, d_scale, ticket, red);
 }
@@ -289,7 +303,7 @@ void text_head(const float* x, int64_t row_stride, int64_t row_offset, const voi
     if (peers) ps = *peers;
     if (C == 0) return;
     TC_CHECK(D % 8 == 0 && E % 8 == 0, "text_head needs D %% 8 == 0 and E %% 8 == 0");
-    const size_t smem = (size_t)(D + E + 32) * sizeof(float);
+    const size_t smem = (size_t)(D + 4 * E + 32) * sizeof(float);
     if (w_dt == DT_BF16) launch_pdl(text_head_kernel<bf16>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const bf16*)w_proj, tfeat, inv_norm, tfeat_copy, D, E, ps);
     else if (w_dt == DT_F16) launch_pdl(text_head_kernel<f16>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const f16*)w_proj, tfeat, inv_norm, tfeat_copy, D, E, ps);
     else launch_pdl(text_head_kernel<float>, C, HEAD_THREADS, smem, stream, x, row_stride, row_offset, (const float*)w_proj, tfeat, inv_norm, tfeat_copy, D, E, ps);
@@ -301,7 +315,7 @@ void text_head_bwd(const float* g, const float* tfeat, const float* inv_norm, co
     if (C == 0) return;
     TC_CHECK(D % 8 == 0 && E % 8 == 0, "text_head_bwd needs D %% 8 == 0 and E %% 8 == 0");
     TC_CHECK(cast_dt != DT_F16 && (w_dt == DT_F32) == (cast_dt == DT_F32), "text_head_bwd: gradients are bf16 or fp32, the projection 16-bit or fp32");
-    const size_t smem = (size_t)(D + E + 32) * sizeof(float);
+    const size_t smem = (size_t)(4 * D + E + 32) * sizeof(float);
     if (w_dt == DT_BF16) launch_pdl(text_head_bwd_kernel<bf16, bf16>, C, HEAD_THREADS, smem, stream, g, tfeat, inv_norm, (const bf16*)wt_proj, dx, (bf16*)dx_cast, row_stride, row_offset, D, E);
     else if (w_dt == DT_F16) launch_pdl(text_head_bwd_kernel<f16, bf16>, C, HEAD_THREADS, smem, stream, g, tfeat, inv_norm, (const f16*)wt_proj, dx, (bf16*)dx_cast, row_stride, row_offset, D, E);
     else launch_pdl(text_head_bwd_kernel<float, float>, C, HEAD_THREADS, smem, stream, g, tfeat, inv_norm, (const float*)wt_proj, dx, (float*)dx_cast, row_stride, row_offset, D, E);

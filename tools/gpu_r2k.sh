@@ -3,9 +3,8 @@ mkdir -p gpurun_out
 run() { name=$1; shift; timeout 1500 "$@" > gpurun_out/$name.log 2>&1; r=$?; echo "== $name exit $r"; tail -n ${TAILN:-6} gpurun_out/$name.log; }
 TAILN=8 run api python -m pytest tests/test_gpu_api.py tests/test_gpu_gemm.py -m gpu -q --tb=short -x -p no:cacheprovider
 TAILN=8 run parity python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -x -p no:cacheprovider -k "golden or layernorm_folded"
-TAILN=12 run fused_ln_bench python tools/fused_ln_bench.py
 B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline"
-for f in 0 2 0 2; do
+for f in 0 0; do
   TAPCLIP_FUSE_LN=$f $B > gpurun_out/bench_f$f.log 2>&1
   python - <<PY
 import json
