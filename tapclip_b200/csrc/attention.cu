@@ -267,15 +267,17 @@ attn_fwd_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward (text tower only: N <= 128): one CTA per (sequence, head), fp32 math in shared memory
+// backward, SIMT form (fp32 parity mode; 16-bit modes only for 128 < N <= 141, where the tensor-core kernel below does not
+// apply): one CTA per (sequence, head), fp32 math in shared memory, TQ = type of the saved qkv, TG = type of the gradients
 //   P = softmax(scale*QK^T); dV = P^T dO; dP = dO V^T; dS = P o (dP - rowsum(P o dP)) * scale;
 //   dQ = dS K; dK = dS^T Q
 // ------------------------------------------------------------------------------------------------
 constexpr int LDH = DH + 1;
 
-template <typename T>
+constexpr int BWD_KEYS_PER_LANE = 5;          // dS pass: one warp per query row, up to 160 keys
+template <typename TQ, typename TG>
 __global__ void __launch_bounds__(256)
-attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __restrict__ dqkv, int N, int H, float scale) {
+attn_bwd_kernel(const TQ* __restrict__ qkv, const TG* __restrict__ d_out, TG* __restrict__ dqkv, int N, int H, float scale) {
     pdl_wait_and_trigger();
     extern __shared__ __align__(16) float sm[];
     float* Q = sm;
@@ -287,13 +289,13 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __res
     const int s = blockIdx.x / H, h = blockIdx.x % H;
     const int d = H * DH;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    const T* base = qkv + (int64_t)s * N * 3 * d + h * DH;
+    const TQ* base = qkv + (int64_t)s * N * 3 * d + h * DH;
     for (int i = tid; i < N * DH; i += blockDim.x) {
         const int r = i / DH, c = i % DH;
-        Q[r * LDH + c] = to_f32<T>(base[(int64_t)r * 3 * d + c]);
-        K[r * LDH + c] = to_f32<T>(base[(int64_t)r * 3 * d + d + c]);
-        V[r * LDH + c] = to_f32<T>(base[(int64_t)r * 3 * d + 2 * d + c]);
-        dO[r * LDH + c] = to_f32<T>(d_out[((int64_t)s * N + r) * d + h * DH + c]);
+        Q[r * LDH + c] = to_f32<TQ>(base[(int64_t)r * 3 * d + c]);
+        K[r * LDH + c] = to_f32<TQ>(base[(int64_t)r * 3 * d + d + c]);
+        V[r * LDH + c] = to_f32<TQ>(base[(int64_t)r * 3 * d + 2 * d + c]);
+        dO[r * LDH + c] = to_f32<TG>(d_out[((int64_t)s * N + r) * d + h * DH + c]);
     }
     __syncthreads();
     // scores
@@ -318,20 +320,20 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __res
     }
     __syncthreads();
     // dV[j][c] = sum_i P[i][j] dO[i][c]
-    T* dbase = dqkv + (int64_t)s * N * 3 * d + h * DH;
+    TG* dbase = dqkv + (int64_t)s * N * 3 * d + h * DH;
     for (int i = tid; i < N * DH; i += blockDim.x) {
         const int j = i / DH, c = i % DH;
         float acc = 0.f;
         for (int r = 0; r < N; ++r) acc = fmaf(Pm[r * LDP + j], dO[r * LDH + c], acc);
-        dbase[(int64_t)j * 3 * d + 2 * d + c] = from_f32<T>(acc);
+        dbase[(int64_t)j * 3 * d + 2 * d + c] = from_f32<TG>(acc);
     }
     __syncthreads();
-    // dS in place of P (one warp per row; up to 4 keys per lane)
+    // dS in place of P (one warp per row; up to BWD_KEYS_PER_LANE keys per lane)
     for (int r = warp; r < N; r += nwarps) {
-        float dp[4], pv[4];
+        float dp[BWD_KEYS_PER_LANE], pv[BWD_KEYS_PER_LANE];
         float dsum = 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BWD_KEYS_PER_LANE; ++u) {
             const int c = lane + 32 * u;
             dp[u] = 0.f; pv[u] = 0.f;
             if (c < N) {
@@ -345,7 +347,7 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __res
         }
         dsum = warp_sum(dsum);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < BWD_KEYS_PER_LANE; ++u) {
             const int c = lane + 32 * u;
             if (c < N) Pm[r * LDP + c] = pv[u] * (dp[u] - dsum) * scale;
         }
@@ -359,8 +361,8 @@ attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ d_out, T* __res
             aq = fmaf(Pm[r * LDP + j], K[j * LDH + c], aq);
             ak = fmaf(Pm[j * LDP + r], Q[j * LDH + c], ak);
         }
-        dbase[(int64_t)r * 3 * d + c] = from_f32<T>(aq);
-        dbase[(int64_t)r * 3 * d + d + c] = from_f32<T>(ak);
+        dbase[(int64_t)r * 3 * d + c] = from_f32<TG>(aq);
+        dbase[(int64_t)r * 3 * d + d + c] = from_f32<TG>(ak);
     }
 }
 
@@ -659,16 +661,22 @@ void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, cons
 
 void attention_bwd(const void* qkv, int qkv_dt, const void* d_out, void* dqkv, int grad_dt, int S, int N, int H, cudaStream_t stream) {
     if (S == 0) return;
-    TC_CHECK(N <= 128, "attention backward supports sequence length <= 128 (got %d)", N);
-    if (grad_dt == DT_BF16) {
+    const size_t smem_simt = ((size_t)4 * N * LDH + (size_t)N * (N + 1)) * sizeof(float);
+    TC_CHECK(N <= 32 * BWD_KEYS_PER_LANE && smem_simt <= 227 * 1024, "attention backward supports sequence length <= 141 (got %d)", N);
+    if (grad_dt == DT_BF16 && N > 128) {
+        // beyond the tensor-core kernel's 128 tokens (prompt_len 52..64): the SIMT form, ~20x slower per layer, still exact math
+        ensure_dynamic_smem(qkv_dt == DT_F16 ? (const void*)attn_bwd_kernel<f16, bf16> : (const void*)attn_bwd_kernel<bf16, bf16>, smem_simt);
+        if (qkv_dt == DT_F16) launch_pdl(attn_bwd_kernel<f16, bf16>, S * H, 256, smem_simt, stream, (const f16*)qkv, (const bf16*)d_out, (bf16*)dqkv, N, H, 0.125f);
+        else if (qkv_dt == DT_BF16) launch_pdl(attn_bwd_kernel<bf16, bf16>, S * H, 256, smem_simt, stream, (const bf16*)qkv, (const bf16*)d_out, (bf16*)dqkv, N, H, 0.125f);
+        else TC_CHECK(false, "unsupported saved-activation dtype %d", qkv_dt);
+    } else if (grad_dt == DT_BF16) {
         if (qkv_dt == DT_BF16) dispatch_attn_bwd_mma<bf16>((const bf16*)qkv, (const bf16*)d_out, (bf16*)dqkv, S, N, H, stream);
         else if (qkv_dt == DT_F16) dispatch_attn_bwd_mma<f16>((const f16*)qkv, (const bf16*)d_out, (bf16*)dqkv, S, N, H, stream);
         else TC_CHECK(false, "unsupported saved-activation dtype %d", qkv_dt);
     } else {
         TC_CHECK(grad_dt == DT_F32 && qkv_dt == DT_F32, "unsupported dtype combination for attention backward");
-        const size_t smem = ((size_t)4 * N * LDH + (size_t)N * (N + 1)) * sizeof(float);
-        ensure_dynamic_smem((const void*)attn_bwd_kernel<float>, smem);
-        launch_pdl(attn_bwd_kernel<float>, S * H, 256, smem, stream, (const float*)qkv, (const float*)d_out, (float*)dqkv, N, H, 0.125f);
+        ensure_dynamic_smem((const void*)attn_bwd_kernel<float, float>, smem_simt);
+        launch_pdl(attn_bwd_kernel<float, float>, S * H, 256, smem_simt, stream, (const float*)qkv, (const float*)d_out, (float*)dqkv, N, H, 0.125f);
     }
     TC_LAUNCH_CHECK();
 }

@@ -125,28 +125,38 @@ __global__ void splice_bwd_kernel(const float* __restrict__ dx, const float* __r
 }
 
 // K3: head-mean (clip_wrapper.py:36) of the probed column, then attribution_monitor.py:29-32 softmax over P.
-// One warp per class; warp-shuffle reductions; P <= 64.
+// One warp per class; warp-shuffle reductions; P <= 192.
+constexpr int ATTR_PER_LANE = 6;              // P <= 192 (forward: P + 77 <= 256 tokens)
 __global__ void attribution_kernel(const float* __restrict__ probe, float* __restrict__ raw, float* __restrict__ attr,
                                    int C, int H, int P) {
     pdl_wait_and_trigger();
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
-    float r[2];
+    float r[ATTR_PER_LANE];
+    float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < ATTR_PER_LANE; ++j) {
         const int p = lane + 32 * j;
         float s = 0.f;
         if (p < P)
             for (int h = 0; h < H; ++h) s += probe[((int64_t)c * H + h) * P + p];
         r[j] = s / (float)H;
+        if (p < P) m = fmaxf(m, r[j]);
     }
-    float m = fmaxf(lane < P ? r[0] : -INFINITY, lane + 32 < P ? r[1] : -INFINITY);
     m = warp_max(m);
-    const float e0 = lane < P ? expf(r[0] - m) : 0.f, e1 = lane + 32 < P ? expf(r[1] - m) : 0.f;
-    const float sum = warp_sum(e0 + e1);
-    if (lane < P) { raw[(int64_t)c * P + lane] = r[0]; attr[(int64_t)c * P + lane] = e0 / sum; }
-    if (lane + 32 < P) { raw[(int64_t)c * P + lane + 32] = r[1]; attr[(int64_t)c * P + lane + 32] = e1 / sum; }
+    float e[ATTR_PER_LANE], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < ATTR_PER_LANE; ++j) {
+        e[j] = (lane + 32 * j < P) ? expf(r[j] - m) : 0.f;
+        sum += e[j];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < ATTR_PER_LANE; ++j) {
+        const int p = lane + 32 * j;
+        if (p < P) { raw[(int64_t)c * P + p] = r[j]; attr[(int64_t)c * P + p] = e[j] / sum; }
+    }
 }
 
 template <typename T>
@@ -394,7 +404,7 @@ void splice_bwd(const float* dx, const float* attr, int attr_p, float* dctx, int
 }
 
 void attribution_reduce(const float* probe, float* raw, float* attr, int C, int H, int P, cudaStream_t stream) {
-    TC_CHECK(P >= 1 && P <= 64, "prompt_len %d unsupported by the attribution kernel (1..64)", P);
+    TC_CHECK(P >= 1 && P <= 32 * ATTR_PER_LANE, "prompt_len %d unsupported by the attribution kernel (1..192)", P);
     if (C == 0) return;
     launch_pdl(attribution_kernel, (unsigned)ceil_div(C, 4), 128, 0, stream, probe, raw, attr, C, H, P);
     TC_LAUNCH_CHECK();

@@ -585,7 +585,7 @@ int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, i
     t_attr.ensure((int64_t)C * PA * 4);
     t_attr_raw.ensure((int64_t)C * PA * 4);
     if (save) {
-        TC_CHECK(T <= 128, "training needs prompt_len + context_length <= 128 (attention backward), got %d", T);
+        TC_CHECK(T <= 141, "training needs prompt_len + context_length <= 141 (attention backward), got %d", T);
         t_save_x.ensure((int64_t)2 * L * M * D * 4);
         t_save_qkv.ensure((int64_t)L * M * 3 * D * esz);
         t_save_h.ensure((int64_t)L * M * 4 * D * esz);
@@ -622,7 +622,7 @@ int64_t Engine::text_forward(const float* ctx, const float* tok, int C, int P, i
     float* x_end = nullptr; int64_t pool_stride = T, pool_offset = T - 1;
     if (mode == 1) {
         // attribution pass (rows A7/A8): un-adjusted prompt, probabilities of the last block only
-        TC_CHECK(P <= 64, "prompt_len %d unsupported (<= 64)", P);
+        TC_CHECK(T <= 256, "prompt_len + context_length = %d unsupported (<= 256: the attention kernels' probe)", T);
         t_probe.ensure((int64_t)C * H * P * 4);
         splice_prompts(ctx, tok, nullptr, 1, x, C, P, Lc, D, st); ++launches;
         run_blocks(x, true, false, x_end, pool_stride, pool_offset);

@@ -55,7 +55,9 @@ def test_forward_backward_vs_reference_golden(case, mode, dtype):
         raw_cuda = clip.get_attention_map().cpu()                 # compact probe = attn_map[:, :P, T-1] head-mean
         e_raw = ((raw_cuda - gold["attr_raw_dedup"]).abs() / gold["attr_raw_dedup"].abs()).max().item()
         print(f"[parity] raw attribution score rel err {e_raw:.3e}")
-        assert e_raw <= (1e-3 if dtype == "fp32" else 2e-2)      # bf16: probabilities from bf16 QK^T; softmaxed score is the gate
+        # north-star gate: 1e-3 relative on the RAW score too -- met by fp32 and by the product's 16-bit mode ('mixed': fp16 QK^T in
+        # the text tower, measured <= 7.8e-4); pure-bf16 probabilities (experimental mode) stay at their measured envelope
+        assert e_raw <= (2e-2 if dtype == "bf16" else 1e-3)
     else:
         assert torch.equal(attr, torch.ones(C, 1))
 
@@ -116,9 +118,45 @@ def test_other_architectures_vs_oracle(name, B, C, P, dtype):
     assert e_rows <= (1e-5 if dtype == "fp32" else 5e-3) and e_roll <= (1e-4 if dtype == "fp32" else 3e-2)
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "mixed"])
+@pytest.mark.parametrize("P,train", [(51, True), (64, True), (100, False), (179, False)])
+def test_long_prompts(P, train, dtype):
+    """Prompt-length limits: training up to P + 77 <= 141 tokens (P <= 51 on the tensor-core attention backward, 52..64 on the SIMT
+    form), inference up to P + 77 <= 256 (P <= 179); beyond that the engine refuses (no fallback).  The reference has no limit."""
+    B, C = 2, 3
+    ow, om = build_oracle("mini-16", C, P, "intended")
+    clip, model = build_cuda("mini-16", C, P, "intended", dtype, ow)
+    images, labels = synthetic_images(B, 64), synthetic_labels(B, C)
+    om.train(train); model.train(train)
+    if train:
+        ref = om.forward_dedup(images, labels, return_aux=True)
+        ref["loss"].backward()
+        out = model(images.cuda(), labels.cuda())
+        out["loss"].backward()
+        g_ref = torch.stack([om.prompt_learner.context_bank[n].grad for n in class_names(C)])
+        assert rel_err(ctx_grads(model, C), g_ref) <= GRAD_TOL[dtype]
+    else:
+        with torch.no_grad():
+            ref = om.forward_dedup(images, return_aux=True)
+            out = model(images.cuda())
+    assert max_abs(out["logits"], ref["logits"]) <= LOGIT_TOL[dtype]
+    attr = model.last_attribution.cpu()
+    assert ((attr - ref["attribution"]).abs() / ref["attribution"].abs()).max().item() <= 1e-3
+    # one token more than the limit of this mode is an error, not a silent fallback
+    P_bad = 65 if train else 180
+    _, bad = build_cuda("mini-16", C, P_bad, "intended", dtype, ow)
+    bad.train(train)
+    with pytest.raises(Exception, match="unsupported|<= 141|<= 256"):
+        if train:
+            bad(images.cuda(), labels.cuda())
+        else:
+            with torch.no_grad():
+                bad(images.cuda())
+
+
 @pytest.mark.parametrize("B,C,P", [(1, 1, 1), (5, 2, 27), (2, 9, 5)])
 def test_edge_shapes_fp32(B, C, P):
-    """Ragged / extreme shapes: single image, single class, one ctx token, the longest trainable prompt (P + 77 <= 104)."""
+    """Ragged / extreme shapes: single image, single class, one ctx token, a long prompt (P + 77 = 104)."""
     ow, om = build_oracle("mini-16", C, P, "intended")
     clip, model = build_cuda("mini-16", C, P, "intended", "fp32", ow)
     images, labels = synthetic_images(B, 64), synthetic_labels(B, C)
