@@ -104,11 +104,15 @@ class TextGather:
         self.hdl = symm.rendezvous(self.buf, group)
         torch.cuda.current_stream().synchronize()
         dist.barrier(group=shard.group)                   # every rank's zeroed buffer is mapped before the first peer store
-        engine.set_text_gather(list(self.hdl.buffer_ptrs), shard.rank, n_cls)
+        self.engine, self.rank = engine, shard.rank
         self.epoch = 0
 
     def next_epoch(self) -> int:
-        """Called once per forward on every rank (ranks run in lockstep: same sequence everywhere)."""
+        """Called once per forward on every rank (ranks run in lockstep: same sequence everywhere).  Also points the engine at
+        THIS gather's buffers: several FullModels may share one CLIPWrapper / engine (train + eval model), each with its own."""
+        if getattr(self.engine, "_active_text_gather", None) is not self:
+            self.engine.set_text_gather(list(self.hdl.buffer_ptrs), self.rank, self.n_cls)
+            self.engine._active_text_gather = self
         self.epoch += 1
         return self.epoch
 

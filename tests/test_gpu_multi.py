@@ -39,6 +39,13 @@ model.eval()
 model.cache_text_features = False
 with torch.no_grad():
     ev = model(images[mine].contiguous())["logits"]
+# a second model on the same CLIPWrapper (its own gather buffers) must not disturb the first one
+torch.manual_seed(9)
+other = tb.FullModel([f"class_{i:03d}" for i in range(C + 2)], clip, prompt_len=P, cache_text_features=False).eval()
+with torch.no_grad():
+    other(images[mine].contiguous())
+    ev2 = model(images[mine].contiguous())["logits"]
+assert torch.equal(ev, ev2)
 torch.save({"logits": out["logits"].detach().cpu(), "loss": out["loss"].detach().cpu(), "grad": grad.cpu(),
             "sgrad": model.logit_scale.grad.cpu(), "eval_logits": ev.cpu(), "fused_gather": model._tg is not None,
             "epoch": model._tg.epoch if model._tg is not None else 0},
@@ -81,7 +88,7 @@ def test_two_gpu_nccl_matches_single_gpu(fused_gather):
         ev = model(images)["logits"].cpu()
     assert all(p["fused_gather"] == (fused_gather == "1") for p in parts)
     if fused_gather == "1":
-        assert all(p["epoch"] == 4 for p in parts)                 # three train steps + one uncached eval forward
+        assert all(p["epoch"] == 5 for p in parts)                 # three train steps + two uncached eval forwards
     assert (torch.cat([p["eval_logits"] for p in parts], 0) - ev).abs().max().item() < 1e-5
     logits = torch.cat([p["logits"] for p in parts], 0)
     assert (logits - out["logits"].detach().cpu()).abs().max().item() < 1e-5
