@@ -8,7 +8,7 @@ timeout 1500 python -m pytest tests -m gpu -q --tb=short -s -p no:cacheprovider 
 echo "== pytest -m gpu exit $?"; tail -4 gpurun_out/pytest_gpu.log
 grep "\[parity\]" gpurun_out/pytest_gpu.log > gpurun_out/r02_parity_report.txt
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "== smoke exit $?"; tail -3 gpurun_out/smoke.log
-python bench.py > gpurun_out/r02_bench_train_c2.json 2> gpurun_out/bench_train_c2.err; echo "== bench train_c2 exit $?"; cut -c1-400 gpurun_out/r02_bench_train_c2.json
+SECONDS=0; python bench.py > gpurun_out/r02_bench_train_c2.json 2> gpurun_out/bench_train_c2.err; echo "== bench train_c2 exit $? in ${SECONDS}s"; cut -c1-400 gpurun_out/r02_bench_train_c2.json
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_reference.json 2>/dev/null; echo "== reference arm exit $?"
 for wl in fwd_c1 fwd_b128 eval_c3 train_c5 fwd_c4; do
   python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_$wl.json 2> gpurun_out/bench_$wl.err
