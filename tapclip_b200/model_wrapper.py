@@ -216,7 +216,13 @@ class FullModel(nn.Module):
             if not TextGather.available(device):
                 self.fused_gather = False
                 return None
-            self._tg = TextGather(self.clip.engine, shard, n_cls, self.clip.model.cfg.embed_dim, device)
+            try:
+                self._tg = TextGather(self.clip.engine, shard, n_cls, self.clip.model.cfg.embed_dim, device)
+            except Exception as e:                      # no peer access / symmetric memory on this system: every rank lands here alike
+                import warnings
+                warnings.warn(f"fused text-feature gather unavailable ({e!r}); using the NCCL all-gather")
+                self.fused_gather, self._tg = False, None
+                return None
         return self._tg
 
     def _adjusted_path(self):
