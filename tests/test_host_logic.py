@@ -177,3 +177,17 @@ def test_class_sharding_bounds():
                 assert hi - lo <= ClassSharding(r, world).max_shard(n)
                 cover += list(range(lo, hi))
             assert cover == list(range(n))
+
+
+def test_bench_line_helpers():
+    """bench.py pieces that need no GPU: both arms print the same `config` object, `roofline.traffic` is read from the committed
+    ncu capture (not a literal), and the CPU legs time the same sub-grid."""
+    import bench
+    name, B, C, P, train, desc = bench.WORKLOADS["train_c2"]
+    assert (name, B, C, P, train) == ("ViT-B-16-quickgelu", 128, 65, 16, True)          # BASELINE configs[1]
+    a = bench.config_dict(name, B, C, P, train, desc, 1)
+    assert set(a) == {"workload", "model", "batch_per_gpu", "global_batch", "n_cls", "prompt_len", "attribution", "optimizer", "parallelism"}
+    assert bench.config_dict(name, B, C, P, train, desc, 8)["global_batch"] == 8 * B
+    traffic, src = bench.ncu_gemm_traffic()
+    assert src is not None and src.startswith("r02") and 50e6 < traffic < 400e6           # ~164 MB per image-tower GEMM launch
+    assert bench.CPU_SAMPLE == (4, 8)
