@@ -40,7 +40,7 @@ __host__ __device__ constexpr uint32_t attn_idesc(int m, int n, bool f16, bool b
 
 #ifdef TAPCLIP_ATTN_TRACE
 // developer-only phase trace of CTA 0 (tools/micro/attn_trace.py builds a private copy of the library with this enabled)
-__device__ long long g_attn_trace[2 * 16 * 16];
+__device__ long long g_attn_trace[8 * 16 * 16];     // [group][warp quarter][item][slot]
 #define TRACE(slot) do { if (tr) tr[slot] = clock64(); } while (0)
 #else
 #define TRACE(slot) do { } while (0)
@@ -297,7 +297,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 // All hand-offs are mbarriers (no CTA-wide or group-wide bar.sync inside the loop).
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef ATTN_NRES
-#define ATTN_NRES 10
+#define ATTN_NRES 8
 #endif
 constexpr int ATTN2_THREADS = 384;
 constexpr int NSLOT = 3;
@@ -318,13 +318,17 @@ __device__ __forceinline__ void chunk_max(const uint32_t (&c)[16], int u, int N,
             if (u * 16 + j < N) m0 = fmaxf(m0, __uint_as_float(c[j]));
     }
 }
-constexpr int POLY_EVERY = 0;          // n > 0: every n-th exponential of the persistent kernel's softmax runs on the FMA pipe.
+#ifndef ATTN_POLY
+#define ATTN_POLY 0
+#endif
+constexpr int POLY_EVERY = ATTN_POLY;          // n > 0: every n-th exponential of the persistent kernel's softmax runs on the FMA pipe.
                                        // Measured (ViT-B/16 layer, B=128): 0 -> 62 us, 3 -> 77 us: the pass is latency/issue-bound, not MUFU-bound
 
 // exp2, row-sum, 16-bit pack and write-back of P chunk u (TMEM columns [8u, 8u+8) of the row); probe bookkeeping
 // CLS = float* : the CLS row's unnormalised p goes to global memory (scalar stores, any alignment);
 // CLS = uint32_t: to a 16-float-aligned shared-memory staging row (address; 0 = none) with four vector stores
-template <typename T16, bool MAYBE_MASKED, typename CLS>
+// SUM = false: the caller takes the row sum from the tensor core (ones column of the P.V product) instead
+template <typename T16, bool MAYBE_MASKED, bool SUM, typename CLS>
 __device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N, float scale_log2, float mneg, uint32_t trow,
                                           CLS cls_out, bool cls_lane, float& l0, float& l1, float& p_last) {
     float pv[16];
@@ -357,7 +361,7 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N,
     uint32_t pk[8];
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-        if (j & 2) l1 += pv[j] + pv[j + 1]; else l0 += pv[j] + pv[j + 1];
+        if constexpr (SUM) { if (j & 2) l1 += pv[j] + pv[j + 1]; else l0 += pv[j] + pv[j + 1]; }
         pk[j >> 1] = pack2<T16>(pv[j], pv[j + 1]);
     }
     tmem_st_32x8(trow + u * 8, pk);
@@ -366,11 +370,19 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N,
 // NCH = compile-time number of 16-key chunks the softmax handles (>= NKP/16: chunks past NKP are fully masked), so that every
 // register array below is indexed with constants; chunks below FIRST_MASKABLE are valid for every N this instance serves.
 constexpr int CLS_STAGE2 = 208;        // floats per group: the persistent kernel serves N <= 208
-template <bool F16, int NCH>
+// TCSUM (launches without a probe or lse output): the row sums come out of the tensor core.  The P.V product is issued with
+// N = 80: B columns 64..79 are a second MN-atom of the descriptor that points (leading byte offset) at 2 KB of ones, so O column
+// 64 of a row is the fp32 sum of exactly the 16-bit probabilities the product used -- and the softmax threads drop their 208
+// FADDs per row (measured with the phase trace: -1000 cycles of the exp2 pass per item).
+#ifndef ATTN_SUMN
+#define ATTN_SUMN 16
+#endif
+constexpr int ONES_OFF = 2048;         // bytes behind the operand slots: barriers + CLS staging come first
+template <bool F16, int NCH, bool TCSUM>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, void* __restrict__ out_,
                     int N, int H, int nkp, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out,
-                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out, int pair) {
+                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out, int pair, int excl) {
     using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -391,8 +403,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint64_t* bar_o = bars + 7;           // [2] O = PV complete
     uint64_t* bar_tfree = bars + 9;       // [2] O read out of TMEM by the group's 4 warps: the TMEM half may take the next S
     uint64_t* bar_free = bars + 11;       // [2] O stored: the operand slot (its Q tile doubles as store staging) may be refilled
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    float* cls_stage = reinterpret_cast<float*>(smem + nslot * slot_bytes + 128);   // [2 groups][CLS_STAGE2] unnormalised CLS-row p
+    uint64_t* bar_exp = bars + 13;        // [2 groups][4 warp quarters] exp2 pass of the warp's current item issued (excl mode)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    float* cls_stage = reinterpret_cast<float*>(smem + nslot * slot_bytes + 192);   // [2 groups][CLS_STAGE2] unnormalised CLS-row p
+    uint8_t* ones = smem + nslot * slot_bytes + ONES_OFF;                           // [16 keys x 128 B] of 1.0 (TCSUM)
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int d = H * DH;
@@ -408,10 +422,16 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 4); mbar_init(&bar_o[i], 1);
             mbar_init(&bar_tfree[i], 4); mbar_init(&bar_free[i], 4);
         }
+        for (int i = 0; i < 8; ++i) mbar_init(&bar_exp[i], 1);
         fence_mbar_init();
         fence_proxy_async_smem();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (TCSUM && warp == 2) {
+        const uint32_t one2 = F16 ? 0x3C003C00u : 0x3F803F80u;
+        for (int k = lane; k < 2048 / 16; k += 32) reinterpret_cast<uint4*>(ones)[k] = make_uint4(one2, one2, one2, one2);
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -454,7 +474,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         } else if (warp == 1) {
             // ---- MMA issuer (all 32 lanes run the control flow; elect.sync picks the issuing lane) ----
-            const uint32_t idesc_s = attn_idesc(128, nkp, F16, false), idesc_o = attn_idesc(128, DH, F16, true);
+            const uint32_t idesc_s = attn_idesc(128, nkp, F16, false), idesc_o = attn_idesc(128, TCSUM ? DH + ATTN_SUMN : DH, F16, true);
             const int nks = nkp / 16;
             auto issue_s = [&](int i) {
                 const int hf = i & 1;
@@ -473,10 +493,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const uint32_t thalf = tmem_base + hf * 256;
                 mbar_wait(&bar_p[hf], (uint32_t)((j >> 1) & 1));
                 tc_fence_after();
-                const uint64_t vd = smem_desc_sw128(smem_u32(smem + slot_of(j) * slot_bytes + q_bytes + nkp * 128));
+                const uint32_t v_addr = smem_u32(smem + slot_of(j) * slot_bytes + q_bytes + nkp * 128);
+                const uint64_t vd = smem_desc_sw128(v_addr);
+                // TCSUM: the second 64-column atom of B (leading byte offset, 16-byte units, bits 16..29) is the block of ones
+                const uint64_t lbo0 = TCSUM ? (uint64_t)(((smem_u32(ones) - v_addr) >> 4) - 1u) << 16 : 0ull;   // the descriptor already holds LBO = 1
 #pragma unroll
                 for (int ks = 0; ks < 13; ++ks)                        // NKP <= 208: at most 13 k-steps
-                    if (ks < nks) umma_ts_elect(thalf + O_COL, thalf + ks * 8, vd + (uint64_t)(ks * 128), idesc_o, ks != 0);
+                    if (ks < nks) umma_ts_elect(thalf + O_COL, thalf + ks * 8, vd + (uint64_t)(ks * 128) + (TCSUM ? lbo0 - ((uint64_t)(ks * 128) << 16) : 0ull),
+                                                idesc_o, ks != 0);
                 umma_commit_elect(&bar_o[hf]);
             };
             // steady-state event order of the two (out-of-phase) groups: P(j), tfree(j), P(j+1), tfree(j+1), ...
@@ -509,9 +533,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const bool cls_warp = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0;
             // CLS probe: lane 0 (query row 0) stages its unnormalised probabilities in shared memory during the exp2 pass; the
             // whole warp normalises them and writes the row to global memory with coalesced stores once l is known
-            const uint32_t cls_out = cls_warp ? smem_u32(cls_stage + g * CLS_STAGE2) : 0u;
+            const uint32_t cls_out = (!TCSUM && cls_warp) ? smem_u32(cls_stage + g * CLS_STAGE2) : 0u;
 #ifdef TAPCLIP_ATTN_TRACE
-            long long* tr = (blockIdx.x == 0 && lane == 0 && q == 0 && (i >> 1) < 16) ? g_attn_trace + (g * 16 + (i >> 1)) * 16 : nullptr;
+            long long* tr = (blockIdx.x == 0 && lane == 0 && (i >> 1) < 16) ? g_attn_trace + ((g * 4 + q) * 16 + (i >> 1)) * 16 : nullptr;
 #endif
             TRACE(0);
             mbar_wait(&bar_s[g], par);
@@ -549,12 +573,15 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     }
                 }
                 const float mneg = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2;
+                // excl: the two softmax warps of a sub-partition (same quarter, one per group) take turns in the MUFU-bound
+                // exp2 pass, in item order: item i starts it once item i-1 (the other group's) has issued its own
+                if (excl && i >= 1) mbar_wait(&bar_exp[(1 - g) * 4 + q], (uint32_t)(((i - 1) >> 1) & 1));
                 TRACE(6);
                 float l0 = 0.f, l1 = 0.f;
 #pragma unroll
                 for (int u = 0; u < NRES; ++u) {
-                    if (u < FIRST_MASKABLE) chunk_exp<T16, false>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
-                    else chunk_exp<T16, true>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                    if (u < FIRST_MASKABLE) chunk_exp<T16, false, !TCSUM>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                    else chunk_exp<T16, true, !TCSUM>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
                 }
                 if constexpr (NTAIL > 0) {
                     uint32_t t[NTAIL > 0 ? NTAIL : 1][16];
@@ -562,18 +589,24 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     for (int v = 0; v < NTAIL; ++v) tmem_ld_32x16(trow + (NRES + v) * 16, t[v]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int v = 0; v < NTAIL; ++v) chunk_exp<T16, true>(t[v], NRES + v, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                    for (int v = 0; v < NTAIL; ++v) chunk_exp<T16, true, !TCSUM>(t[v], NRES + v, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
                 }
-                l = l0 + l1;
-                if (lse_out && grow < N) lse_out[((int64_t)s * H + h) * N + grow] = log2f(l) - mneg;     // rollout statistics
+                if (excl && lane == 0) mbar_arrive(&bar_exp[g * 4 + q]);
+                if constexpr (!TCSUM) {
+                    l = l0 + l1;
+                    if (lse_out && grow < N) lse_out[((int64_t)s * H + h) * N + grow] = log2f(l) - mneg;     // rollout statistics
+                }
                 tmem_st_wait();
+            } else if (excl) {
+                if (i >= 1) mbar_wait(&bar_exp[(1 - g) * 4 + q], (uint32_t)(((i - 1) >> 1) & 1));     // keep the turn order
+                if (lane == 0) mbar_arrive(&bar_exp[g * 4 + q]);
             }
             TRACE(5);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_p[g]);                     // this warp's 32 rows of P are in TMEM
-            const float inv = __frcp_rn(l);
-            if (warp_active) {
+            float inv = __frcp_rn(l);
+            if (!TCSUM && warp_active) {
                 if (probe_mode == PROBE_TEXT_COL && grow < probe_P) probe_out[((int64_t)s * H + h) * probe_P + grow] = p_last * inv;
                 if (cls_warp) {
                     __syncwarp();                                          // lane 0's staged row is visible to the warp
@@ -591,14 +624,46 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (warp_active) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x16(trow + O_COL + c * 16, o[c]);
-                tmem_ld_wait();
+                if constexpr (TCSUM) {
+                    uint32_t lsum;
+                    tmem_ld_32x1(trow + O_COL + DH, lsum);            // row sum: the ones column of the product
+                    tmem_ld_wait();
+                    inv = __frcp_rn(__uint_as_float(lsum));
+                } else {
+                    tmem_ld_wait();
+                }
             }
+            TRACE(10);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tfree[g]);                 // O is in registers: the next S may overwrite this TMEM half
+#if defined(ATTN_ABL) && (ATTN_ABL & 16)
+            if (warp_active) {
+                // ablation: every lane stores its own 128-byte row segment straight from registers
+                uint4* gp = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_) + (((int64_t)s * N + grow) * d + h * DH) * 2);
+                uint4 xo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t* rr = &o[c >> 1][(c & 1) * 8];
+                    xo[c].x = pack2<T16>(__uint_as_float(rr[0]) * inv, __uint_as_float(rr[1]) * inv);
+                    xo[c].y = pack2<T16>(__uint_as_float(rr[2]) * inv, __uint_as_float(rr[3]) * inv);
+                    xo[c].z = pack2<T16>(__uint_as_float(rr[4]) * inv, __uint_as_float(rr[5]) * inv);
+                    xo[c].w = pack2<T16>(__uint_as_float(rr[6]) * inv, __uint_as_float(rr[7]) * inv);
+                }
+                TRACE(11); TRACE(12);
+                if (grow < N) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) gp[c] = xo[c];
+                }
+                TRACE(13);
+            }
+            if (false) {
+                const uint32_t stage = smem_u32(Qs) + (uint32_t)(q * 32) * 128u;
+#else
             if (warp_active) {
                 // O row (64 fp32 columns) -> scaled 16-bit -> XOR-swizzled staging in this warp's 4 KB of the item's Q tile
                 const uint32_t stage = smem_u32(Qs) + (uint32_t)(q * 32) * 128u;
+#endif
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint32_t* rr = &o[c >> 1][(c & 1) * 8];
@@ -609,6 +674,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)lane * 128u + (((uint32_t)c ^ ((uint32_t)lane & 7u)) << 4)),
                                  "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");
                 }
+                TRACE(11);
                 __syncwarp();
                 uint8_t* gbase = reinterpret_cast<uint8_t*>(out_) + (((int64_t)s * N + qt * 128 + q * 32) * d + h * DH) * 2 + rd_ch * 16;
                 const int rows_left = N - (qt * 128 + q * 32);
@@ -619,12 +685,16 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[it].x), "=r"(x[it].y), "=r"(x[it].z), "=r"(x[it].w)
                                  : "r"(stage + (uint32_t)rr * 128u + (((uint32_t)rd_ch ^ ((uint32_t)rr & 7u)) << 4)) : "memory");
                 }
+                TRACE(12);
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int rr = it * 4 + rd_row;
                     if (rr < rows_left) *reinterpret_cast<uint4*>(gbase + (int64_t)rr * d * 2) = x[it];
                 }
+                TRACE(13);
+#if !(defined(ATTN_ABL) && (ATTN_ABL & 8))
                 fence_proxy_async_smem();                              // generic-proxy staging writes before the slot's next TMA fill
+#endif
             }
             TRACE(9);
             __syncwarp();
@@ -822,7 +892,7 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     float l0 = 0.f, l1 = 0.f, pl = 0.f;
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
-                        chunk_exp<T16, true>(r[u], u, n_eff, scale_log2, mneg, trow, cls_out ? cls_out + (uint32_t)(j * KVB) * 4u : 0u, lane == 0, l0, l1, pl);
+                        chunk_exp<T16, true, true>(r[u], u, n_eff, scale_log2, mneg, trow, cls_out ? cls_out + (uint32_t)(j * KVB) * 4u : 0u, lane == 0, l0, l1, pl);
                     if (j == nkb - 1) p_last = pl;
                     l = fmaf(l, alpha, l0 + l1);
                     m_run = m_new;
@@ -923,7 +993,7 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
 #ifdef TAPCLIP_ATTN_TRACE
 extern "C" __attribute__((visibility("default"))) int tapclip_debug_attn_trace(long long* host_out) {
-    return (int)cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * 2 * 16 * 16);
+    return (int)cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * 8 * 16 * 16);
 }
 #endif
 
@@ -959,8 +1029,9 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         // (pair mode) 2 slots of (Q0 + Q1 + K + V), so that a head's K and V are loaded once
         static const int pair_env = getenv("TAPCLIP_ATTN_PAIR") ? atoi(getenv("TAPCLIP_ATTN_PAIR")) : 1;    // 0: measurement switch
         const int pair = (nqt == 2 && pair_env != 0) ? 1 : 0;
+        static const int excl = getenv("TAPCLIP_ATTN_EXCL") ? atoi(getenv("TAPCLIP_ATTN_EXCL")) : 0;        // exp2 passes of a sub-partition's two warps take turns
         const size_t slots = pair ? 2 * (2 * 128 * 128 + 2 * (size_t)nkp * 128) : NSLOT * (128 * 128 + 2 * (size_t)nkp * 128);
-        const size_t smem2 = slots + 128 + 2 * CLS_STAGE2 * sizeof(float) + 1024;   // + barriers/TMEM slot, CLS staging, alignment slack
+        const size_t smem2 = slots + ONES_OFF + 2048 + 1024;   // + barriers/TMEM slot/CLS staging (< ONES_OFF), ones block, alignment slack   // + barriers/TMEM slot, CLS staging, alignment slack
         const int num_sms = device_sm_count();
         const int n_items = pair ? S * H : S * H * nqt;        // scheduling units
         const unsigned grid2 = (unsigned)std::min(n_items, num_sms);
@@ -968,11 +1039,18 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         const int nch = nkp / 16;
         auto go = [&](auto kern) {
             ensure_dynamic_smem((const void*)kern, smem2);
-            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair);
+            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair, excl);
         };
-        if (nch <= 4) { if (f16) go(attn_fwd_tc2_kernel<true, 4>); else go(attn_fwd_tc2_kernel<false, 4>); }
-        else if (nch <= 8) { if (f16) go(attn_fwd_tc2_kernel<true, 8>); else go(attn_fwd_tc2_kernel<false, 8>); }
-        else { if (f16) go(attn_fwd_tc2_kernel<true, 13>); else go(attn_fwd_tc2_kernel<false, 13>); }
+        static const int tcsum_env = getenv("TAPCLIP_ATTN_TCSUM") ? atoi(getenv("TAPCLIP_ATTN_TCSUM")) : 1;   // 0: measurement switch
+        const bool tcsum = tcsum_env != 0 && probe.mode == PROBE_NONE && probe.lse_out == nullptr;
+        auto pick = [&](auto f16_c, auto nch_c) {
+            if (tcsum) go(attn_fwd_tc2_kernel<decltype(f16_c)::value, decltype(nch_c)::value, true>);
+            else go(attn_fwd_tc2_kernel<decltype(f16_c)::value, decltype(nch_c)::value, false>);
+        };
+        using std::integral_constant;
+        if (nch <= 4) { if (f16) pick(std::true_type{}, integral_constant<int, 4>{}); else pick(std::false_type{}, integral_constant<int, 4>{}); }
+        else if (nch <= 8) { if (f16) pick(std::true_type{}, integral_constant<int, 8>{}); else pick(std::false_type{}, integral_constant<int, 8>{}); }
+        else { if (f16) pick(std::true_type{}, integral_constant<int, 13>{}); else pick(std::false_type{}, integral_constant<int, 13>{}); }
         TC_LAUNCH_CHECK();
         return true;
     }
