@@ -378,9 +378,11 @@ constexpr int CLS_STAGE2 = 208;        // floats per group: the persistent kerne
 #define ATTN_SUMN 16
 #endif
 constexpr int ONES_OFF = 2048;         // bytes behind the operand slots: barriers + CLS staging come first
+constexpr int OSTAGE_OFF = 4096;       // then 8 x 4 KB of O staging (one 32-row x 128-byte tile per softmax warp), the source of the TMA stores
 template <bool F16, int NCH, bool TCSUM>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
-attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, void* __restrict__ out_,
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                    const __grid_constant__ CUtensorMap tmap_o, void* __restrict__ out_,
                     int N, int H, int nkp, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out,
                     int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out, int pair, int excl) {
     using T16 = typename std::conditional<F16, f16, bf16>::type;
@@ -417,6 +419,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_kv);
+        tma_prefetch_desc(&tmap_o);
         for (int i = 0; i < NSLOT; ++i) mbar_init(&bar_load[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 4); mbar_init(&bar_o[i], 1);
@@ -518,7 +521,6 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int q = warp & 3;                                        // TMEM lane quarter
         const int row = q * 32 + lane;
         const uint32_t trow = tmem_base + g * 256 + ((uint32_t)(q * 32) << 16);
-        const int rd_row = lane >> 3, rd_ch = lane & 7;                // store mapping: 8 lanes cover one 128-byte row segment
         // (q-tile, head, sequence) of the group's current item, advanced incrementally (no divisions inside the loop)
         // pair mode: the group keeps q-tile g and walks the CTA's heads; otherwise item ids b + i * grid, i = g, g + 2, ...
         const int step2 = 2 * (int)gridDim.x;
@@ -527,7 +529,6 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         int qt = pair ? g : id0 % nqt, h = pair ? (int)blockIdx.x % H : (id0 / nqt) % H, s = pair ? (int)blockIdx.x / H : (id0 / nqt) / H;
         for (int i = g; i < n_mine; i += 2) {
             const uint32_t par = (uint32_t)((i >> 1) & 1);
-            uint8_t* Qs = smem + slot_of(i) * slot_bytes + q_off(i);
             const int grow = qt * 128 + row;
             const bool warp_active = qt * 128 + q * 32 < N;            // else: all 32 rows of this warp are padding
             const bool cls_warp = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0;
@@ -637,33 +638,15 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tfree[g]);                 // O is in registers: the next S may overwrite this TMEM half
-#if defined(ATTN_ABL) && (ATTN_ABL & 16)
+            if (lane == 0) mbar_arrive(&bar_free[g]);                  // P.V has read K/V (and S = Q K^T the Q tile): the operand slot may be refilled
             if (warp_active) {
-                // ablation: every lane stores its own 128-byte row segment straight from registers
-                uint4* gp = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out_) + (((int64_t)s * N + grow) * d + h * DH) * 2);
-                uint4 xo[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t* rr = &o[c >> 1][(c & 1) * 8];
-                    xo[c].x = pack2<T16>(__uint_as_float(rr[0]) * inv, __uint_as_float(rr[1]) * inv);
-                    xo[c].y = pack2<T16>(__uint_as_float(rr[2]) * inv, __uint_as_float(rr[3]) * inv);
-                    xo[c].z = pack2<T16>(__uint_as_float(rr[4]) * inv, __uint_as_float(rr[5]) * inv);
-                    xo[c].w = pack2<T16>(__uint_as_float(rr[6]) * inv, __uint_as_float(rr[7]) * inv);
-                }
-                TRACE(11); TRACE(12);
-                if (grow < N) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) gp[c] = xo[c];
-                }
-                TRACE(13);
-            }
-            if (false) {
-                const uint32_t stage = smem_u32(Qs) + (uint32_t)(q * 32) * 128u;
-#else
-            if (warp_active) {
-                // O row (64 fp32 columns) -> scaled 16-bit -> XOR-swizzled staging in this warp's 4 KB of the item's Q tile
-                const uint32_t stage = smem_u32(Qs) + (uint32_t)(q * 32) * 128u;
-#endif
+                // O row (64 fp32 columns) -> scaled 16-bit -> this warp's 4 KB staging tile in the 128-byte-swizzle layout ->
+                // ONE TMA store of [32 rows x 128 B] (rows past N are clipped by the [S][N][d] map).  The register -> shared ->
+                // register -> global version spent 850 of the drain's 1500 cycles in its 8 LDS + 8 STG per warp, queued in the
+                // sub-partition's memory pipe behind the other group's MUFU stream.
+                const uint32_t stage = smem_u32(smem + nslot * slot_bytes + OSTAGE_OFF) + (uint32_t)(warp - 4) * 4096u;
+                if (lane == 0) tma_store_wait_read<0>();               // the previous item's store has read the tile
+                __syncwarp();
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint32_t* rr = &o[c >> 1][(c & 1) * 8];
@@ -675,36 +658,23 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                                  "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");
                 }
                 TRACE(11);
+                fence_proxy_async_smem();                              // generic-proxy writes -> visible to the TMA engine
                 __syncwarp();
-                uint8_t* gbase = reinterpret_cast<uint8_t*>(out_) + (((int64_t)s * N + qt * 128 + q * 32) * d + h * DH) * 2 + rd_ch * 16;
-                const int rows_left = N - (qt * 128 + q * 32);
-                uint4 x[8];
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {                       // all eight reads first: their latencies overlap
-                    const int rr = it * 4 + rd_row;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[it].x), "=r"(x[it].y), "=r"(x[it].z), "=r"(x[it].w)
-                                 : "r"(stage + (uint32_t)rr * 128u + (((uint32_t)rd_ch ^ ((uint32_t)rr & 7u)) << 4)) : "memory");
-                }
                 TRACE(12);
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int rr = it * 4 + rd_row;
-                    if (rr < rows_left) *reinterpret_cast<uint4*>(gbase + (int64_t)rr * d * 2) = x[it];
+                if (lane == 0) {
+                    tma_store_3d(&tmap_o, stage, h * DH, qt * 128 + q * 32, s);
+                    tma_store_commit();
                 }
                 TRACE(13);
-#if !(defined(ATTN_ABL) && (ATTN_ABL & 8))
-                fence_proxy_async_smem();                              // generic-proxy staging writes before the slot's next TMA fill
-#endif
             }
             TRACE(9);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_free[g]);                  // O stored: the operand slot may be refilled
             qt += step_qt;
             if (qt >= nqt) { qt -= nqt; ++h; }
             h += step_h;
             if (h >= H) { h -= H; ++s; }
             s += step_s;
         }
+        if (lane == 0) tma_store_wait_read<0>();                       // shared memory outlives the last store's read
     }
     tc_fence_before();
     __syncthreads();
@@ -1031,7 +1001,8 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         const int pair = (nqt == 2 && pair_env != 0) ? 1 : 0;
         static const int excl = getenv("TAPCLIP_ATTN_EXCL") ? atoi(getenv("TAPCLIP_ATTN_EXCL")) : 0;        // exp2 passes of a sub-partition's two warps take turns
         const size_t slots = pair ? 2 * (2 * 128 * 128 + 2 * (size_t)nkp * 128) : NSLOT * (128 * 128 + 2 * (size_t)nkp * 128);
-        const size_t smem2 = slots + ONES_OFF + 2048 + 1024;   // + barriers/TMEM slot/CLS staging (< ONES_OFF), ones block, alignment slack   // + barriers/TMEM slot, CLS staging, alignment slack
+        const size_t smem2 = slots + OSTAGE_OFF + 8 * 4096 + 1024;   // + barriers/TMEM slot/CLS staging, ones block, O staging, alignment slack
+        const CUtensorMap& to = make_tmap_seq(out, tdt, 2, S, N, d, d, 32, 64);   // + barriers/TMEM slot, CLS staging, alignment slack
         const int num_sms = device_sm_count();
         const int n_items = pair ? S * H : S * H * nqt;        // scheduling units
         const unsigned grid2 = (unsigned)std::min(n_items, num_sms);
@@ -1039,7 +1010,7 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         const int nch = nkp / 16;
         auto go = [&](auto kern) {
             ensure_dynamic_smem((const void*)kern, smem2);
-            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair, excl);
+            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, to, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair, excl);
         };
         static const int tcsum_env = getenv("TAPCLIP_ATTN_TCSUM") ? atoi(getenv("TAPCLIP_ATTN_TCSUM")) : 1;   // 0: measurement switch
         const bool tcsum = tcsum_env != 0 && probe.mode == PROBE_NONE && probe.lse_out == nullptr;

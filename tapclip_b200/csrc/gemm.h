@@ -56,6 +56,10 @@ int gemm_stats_parts(int64_t N);
 // Returned BY VALUE (128 bytes): a caller may hold two descriptors at once, and the cache evicts everything when it is full.
 CUtensorMap make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
                              int box_rows, int box_cols);
+// [S][N][cols] view (sequence-major rows, pitch ld elements): boxes of box_rows x box_cols inside ONE sequence -- rows past N are
+// clipped by the map, so a tile store never reaches the next sequence
+CUtensorMap make_tmap_seq(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t S, int64_t N, int64_t cols, int64_t ld,
+                          int box_rows, int box_cols);
 
 // tcgen05/TMEM/TMA path: A and W bf16 (or fp16, g.dt); out = same 16-bit type (EPI_BF16) or f32
 void gemm_tc(const GemmArgs& g, cudaStream_t stream);

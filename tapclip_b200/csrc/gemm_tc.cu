@@ -669,9 +669,9 @@ CUtensorMap encode_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes,
 // cuTensorMapEncodeTiled costs a few microseconds on the host; the engine's operands live in stable buffers, so the
 // encoded maps are cached by (pointer, geometry).  Single-threaded per handle/process by contract (include/tapclip.h).
 struct TmapKey {
-    const void* ptr; int dt; int64_t rows, cols, ld; int box_rows, box_cols;
+    const void* ptr; int dt; int64_t rows, cols, ld; int box_rows, box_cols; int64_t seqs = 0;      // seqs > 0: [seqs][rows][cols] map
     bool operator<(const TmapKey& o) const {
-        return std::tie(ptr, dt, rows, cols, ld, box_rows, box_cols) < std::tie(o.ptr, o.dt, o.rows, o.cols, o.ld, o.box_rows, o.box_cols);
+        return std::tie(ptr, dt, rows, cols, ld, box_rows, box_cols, seqs) < std::tie(o.ptr, o.dt, o.rows, o.cols, o.ld, o.box_rows, o.box_cols, o.seqs);
     }
 };
 std::map<TmapKey, CUtensorMap> g_tmap_cache;
@@ -683,6 +683,25 @@ CUtensorMap make_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, i
     if (it != g_tmap_cache.end()) return it->second;
     if (g_tmap_cache.size() > 4096) g_tmap_cache.clear();
     return g_tmap_cache.emplace(key, encode_tmap(ptr, dt, elem_bytes, rows, cols, ld, box_rows, box_cols)).first->second;
+}
+
+CUtensorMap make_tmap_seq(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t S, int64_t N, int64_t cols, int64_t ld,
+                          int box_rows, int box_cols) {
+    const TmapKey key{ptr, (int)dt, N, cols, ld, box_rows, box_cols, S};
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) return it->second;
+    if (g_tmap_cache.size() > 4096) g_tmap_cache.clear();
+    TC_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * elem_bytes) % 16 == 0, "TMA base pointer and row pitch must be 16-byte aligned");
+    TC_CHECK(box_cols * elem_bytes == 128 && box_rows >= 1 && box_rows <= 256, "box: 128 bytes x [1, 256] rows");
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)N, (cuuint64_t)S};
+    cuuint64_t strides[2] = {(cuuint64_t)(ld * elem_bytes), (cuuint64_t)(N * ld * elem_bytes)};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_fn()(&m, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with code %d", (int)r);
+    return g_tmap_cache.emplace(key, m).first->second;
 }
 
 CUtensorMap encode_tmap(const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols, int64_t ld,
