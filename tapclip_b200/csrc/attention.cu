@@ -629,9 +629,9 @@ void attention_fwd(const void* qkv, void* out, int dt, int S, int N, int H, cons
     if (probe.mode == PROBE_CLS_ROW) TC_CHECK(probe.out && probe.seq_stride >= (int64_t)H * N, "bad CLS probe");
     static const int impl = getenv("TAPCLIP_ATTN_IMPL") ? atoi(getenv("TAPCLIP_ATTN_IMPL")) : 0;   // 0 auto, 1 mma.sync, 2 tcgen05
     // auto: the persistent tcgen05 kernel for N <= 208 when there are enough (sequence, head, q-tile) items to keep its
-    // two softmax groups per SM busy (ViT-B/16 at B=128: 3072 items, 62 us vs 102 us); the mma.sync flash kernel for long
-    // sequences (ViT-L/14@336) and for small problems such as the C=65 text tower (520 items: ~10 us either way)
-    if (!probe.causal && (impl == 2 || (impl == 0 && attention_fwd_tc_supported(dt, N) && (N <= 208 || N > 256) && (int64_t)S * H * ((N + 127) / 128) >= 1024))) {   // (threshold on the full problem: a live_q_rows launch keeps the kernel choice)
+    // two softmax groups per SM busy (ViT-B/16 at B=128: 3072 items, 42 us vs 99 us; the C=65 text tower, 520 items at
+    // N=93: 9.7 us vs 12.4 us); the mma.sync flash kernel for 208 < N <= 256, causal launches and smaller problems
+    if (!probe.causal && (impl == 2 || (impl == 0 && attention_fwd_tc_supported(dt, N) && (N <= 208 || N > 256) && (int64_t)S * H * ((N + 127) / 128) >= 512))) {   // (threshold on the full problem: a live_q_rows launch keeps the kernel choice)
         if (!attention_fwd_tc(qkv, out, dt, S, N, H, probe, stream) && probe.lse_out) attention_lse(qkv, probe.lse_out, dt, S, N, H, stream);
         return;
     }

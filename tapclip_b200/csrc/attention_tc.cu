@@ -370,34 +370,36 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&c)[16], int u, int N,
 // NCH = compile-time number of 16-key chunks the softmax handles (>= NKP/16: chunks past NKP are fully masked), so that every
 // register array below is indexed with constants; chunks below FIRST_MASKABLE are valid for every N this instance serves.
 constexpr int CLS_STAGE2 = 208;        // floats per group: the persistent kernel serves N <= 208
-// TCSUM (launches without a probe or lse output): the row sums come out of the tensor core.  The P.V product is issued with
-// N = 80: B columns 64..79 are a second MN-atom of the descriptor that points (leading byte offset) at 2 KB of ones, so O column
-// 64 of a row is the fp32 sum of exactly the 16-bit probabilities the product used -- and the softmax threads drop their 208
-// FADDs per row (measured with the phase trace: -1000 cycles of the exp2 pass per item).
+// The row sums come out of the tensor core: the P.V product is issued with N = 80, where B columns 64..79 are a second MN-atom
+// of the descriptor that points (leading byte offset) at 2 KB of ones, so O column 64 of a row is the fp32 sum of exactly the
+// 16-bit probabilities the product used -- and the softmax threads drop their 208 FADDs per row (phase trace: -1000 cycles of
+// the exp2 pass per item).  O uses that sum in every launch, so a probe never changes O.  Launches that publish per-row
+// statistics -- the text-column probe (attribution) and the rollout's lse -- take the EXACT instance, whose threads also add
+// up the unrounded probabilities; the CLS-row probe sums its staged row with the whole warp.
 #ifndef ATTN_SUMN
 #define ATTN_SUMN 16
 #endif
 constexpr int ONES_OFF = 2048;         // bytes behind the operand slots: barriers + CLS staging come first
 constexpr int OSTAGE_OFF = 4096;       // then 8 x 4 KB of O staging (one 32-row x 128-byte tile per softmax warp), the source of the TMA stores
-template <bool F16, int NCH, bool TCSUM>
+template <bool F16, int NCH, bool EXACT>
 __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const __grid_constant__ CUtensorMap tmap_o, void* __restrict__ out_,
                     int N, int H, int nkp, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out,
-                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out, int pair, int excl) {
+                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out, int pair, int nslot_np) {
     using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // Operand slots.  pair = 0: NSLOT slots of [Q 16 KB | K | V], item i in slot i % NSLOT.
+    // Operand slots.  pair = 0: nslot_np (3, or 2 when three do not fit next to the staging) slots of [Q 16 KB | K | V], item i in slot i % nslot_np.
     // pair = 1 (two q-tiles per head, 128 < N <= 208): the scheduling unit is a head, its q-tiles are items 2p and 2p+1 (one per
     // softmax group) and share ONE slot [Q0 | Q1 | K | V] (slot p % 2): K and V cross L2 -> shared memory once per head.  All
     // three tcgen05 attention-side kernels were found sitting at ~3 TB/s of TMA loads; this removes 38 % of them here.
     const int q_bytes = pair ? 2 * 128 * 128 : 128 * 128;
     const int slot_bytes = q_bytes + 2 * nkp * 128;
-    const int nslot = pair ? 2 : NSLOT;
-    auto slot_of = [&](int i) { return pair ? ((i >> 1) & 1) : (i % NSLOT); };
+    const int nslot = pair ? 2 : nslot_np;
+    auto slot_of = [&](int i) { return pair ? ((i >> 1) & 1) : (i % nslot_np); };
     auto q_off = [&](int i) { return pair ? (i & 1) * 128 * 128 : 0; };
-    auto load_parity = [&](int i) { return (uint32_t)((pair ? (i >> 2) : (i / NSLOT)) & 1); };
+    auto load_parity = [&](int i) { return (uint32_t)((pair ? (i >> 2) : (i / nslot_np)) & 1); };
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nslot * slot_bytes);
     uint64_t* bar_load = bars;            // [3] TMA transaction barriers, one per operand slot
     uint64_t* bar_s = bars + 3;           // [2] S = QK^T complete (per group / TMEM half)
@@ -405,10 +407,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint64_t* bar_o = bars + 7;           // [2] O = PV complete
     uint64_t* bar_tfree = bars + 9;       // [2] O read out of TMEM by the group's 4 warps: the TMEM half may take the next S
     uint64_t* bar_free = bars + 11;       // [2] O stored: the operand slot (its Q tile doubles as store staging) may be refilled
-    uint64_t* bar_exp = bars + 13;        // [2 groups][4 warp quarters] exp2 pass of the warp's current item issued (excl mode)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
     float* cls_stage = reinterpret_cast<float*>(smem + nslot * slot_bytes + 192);   // [2 groups][CLS_STAGE2] unnormalised CLS-row p
-    uint8_t* ones = smem + nslot * slot_bytes + ONES_OFF;                           // [16 keys x 128 B] of 1.0 (TCSUM)
+    uint8_t* ones = smem + nslot * slot_bytes + ONES_OFF;                           // [16 keys x 128 B] of 1.0
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int d = H * DH;
@@ -425,12 +426,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_init(&bar_s[i], 1); mbar_init(&bar_p[i], 4); mbar_init(&bar_o[i], 1);
             mbar_init(&bar_tfree[i], 4); mbar_init(&bar_free[i], 4);
         }
-        for (int i = 0; i < 8; ++i) mbar_init(&bar_exp[i], 1);
         fence_mbar_init();
         fence_proxy_async_smem();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
-    if (TCSUM && warp == 2) {
+    if (warp == 2) {
         const uint32_t one2 = F16 ? 0x3C003C00u : 0x3F803F80u;
         for (int k = lane; k < 2048 / 16; k += 32) reinterpret_cast<uint4*>(ones)[k] = make_uint4(one2, one2, one2, one2);
         fence_proxy_async_smem();
@@ -464,11 +464,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             } else if (lane == 0) {
                 for (int i = 0; i < n_mine; ++i) {
                     // slot i%3 was last used by item i-3: operands dead after PV(i-3), staging (Q area) dead once its O is stored
-                    if (i >= NSLOT) mbar_wait(&bar_free[(i - NSLOT) & 1], (uint32_t)(((i - NSLOT) >> 1) & 1));
+                    if (i >= nslot_np) mbar_wait(&bar_free[(i - nslot_np) & 1], (uint32_t)(((i - nslot_np) >> 1) & 1));
                     const int id = (int)blockIdx.x + i * (int)gridDim.x;
                     const int qt = id % nqt, sh = id / nqt, s = sh / H, h = sh % H;
-                    uint8_t* Qs = smem + (i % NSLOT) * slot_bytes;
-                    uint64_t* bl = &bar_load[i % NSLOT];
+                    uint8_t* Qs = smem + (i % nslot_np) * slot_bytes;
+                    uint64_t* bl = &bar_load[i % nslot_np];
                     mbar_expect_tx(bl, (uint32_t)slot_bytes);
                     tma_load_2d(Qs, &tmap_q, h * DH, s * N + qt * 128, bl);
                     tma_load_2d(Qs + 128 * 128, &tmap_kv, d + h * DH, s * N, bl);
@@ -477,7 +477,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         } else if (warp == 1) {
             // ---- MMA issuer (all 32 lanes run the control flow; elect.sync picks the issuing lane) ----
-            const uint32_t idesc_s = attn_idesc(128, nkp, F16, false), idesc_o = attn_idesc(128, TCSUM ? DH + ATTN_SUMN : DH, F16, true);
+            const uint32_t idesc_s = attn_idesc(128, nkp, F16, false), idesc_o = attn_idesc(128, DH + ATTN_SUMN, F16, true);
             const int nks = nkp / 16;
             auto issue_s = [&](int i) {
                 const int hf = i & 1;
@@ -498,11 +498,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(smem + slot_of(j) * slot_bytes + q_bytes + nkp * 128);
                 const uint64_t vd = smem_desc_sw128(v_addr);
-                // TCSUM: the second 64-column atom of B (leading byte offset, 16-byte units, bits 16..29) is the block of ones
-                const uint64_t lbo0 = TCSUM ? (uint64_t)(((smem_u32(ones) - v_addr) >> 4) - 1u) << 16 : 0ull;   // the descriptor already holds LBO = 1
+                // the second 64-column atom of B (leading byte offset, 16-byte units, bits 16..29) is the block of ones
+                const uint64_t lbo0 = (uint64_t)(((smem_u32(ones) - v_addr) >> 4) - 1u) << 16;   // the descriptor already holds LBO = 1
 #pragma unroll
                 for (int ks = 0; ks < 13; ++ks)                        // NKP <= 208: at most 13 k-steps
-                    if (ks < nks) umma_ts_elect(thalf + O_COL, thalf + ks * 8, vd + (uint64_t)(ks * 128) + (TCSUM ? lbo0 - ((uint64_t)(ks * 128) << 16) : 0ull),
+                    if (ks < nks) umma_ts_elect(thalf + O_COL, thalf + ks * 8, vd + (uint64_t)(ks * 128) + lbo0 - ((uint64_t)(ks * 128) << 16),
                                                 idesc_o, ks != 0);
                 umma_commit_elect(&bar_o[hf]);
             };
@@ -534,7 +534,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const bool cls_warp = (probe_mode == PROBE_CLS_ROW) && qt == 0 && q == 0;
             // CLS probe: lane 0 (query row 0) stages its unnormalised probabilities in shared memory during the exp2 pass; the
             // whole warp normalises them and writes the row to global memory with coalesced stores once l is known
-            const uint32_t cls_out = (!TCSUM && cls_warp) ? smem_u32(cls_stage + g * CLS_STAGE2) : 0u;
+            const uint32_t cls_out = cls_warp ? smem_u32(cls_stage + g * CLS_STAGE2) : 0u;
 #ifdef TAPCLIP_ATTN_TRACE
             long long* tr = (blockIdx.x == 0 && lane == 0 && (i >> 1) < 16) ? g_attn_trace + ((g * 4 + q) * 16 + (i >> 1)) * 16 : nullptr;
 #endif
@@ -574,15 +574,12 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     }
                 }
                 const float mneg = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * scale_log2;
-                // excl: the two softmax warps of a sub-partition (same quarter, one per group) take turns in the MUFU-bound
-                // exp2 pass, in item order: item i starts it once item i-1 (the other group's) has issued its own
-                if (excl && i >= 1) mbar_wait(&bar_exp[(1 - g) * 4 + q], (uint32_t)(((i - 1) >> 1) & 1));
                 TRACE(6);
                 float l0 = 0.f, l1 = 0.f;
 #pragma unroll
                 for (int u = 0; u < NRES; ++u) {
-                    if (u < FIRST_MASKABLE) chunk_exp<T16, false, !TCSUM>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
-                    else chunk_exp<T16, true, !TCSUM>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                    if (u < FIRST_MASKABLE) chunk_exp<T16, false, EXACT>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                    else chunk_exp<T16, true, EXACT>(r[u], u, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
                 }
                 if constexpr (NTAIL > 0) {
                     uint32_t t[NTAIL > 0 ? NTAIL : 1][16];
@@ -590,30 +587,30 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     for (int v = 0; v < NTAIL; ++v) tmem_ld_32x16(trow + (NRES + v) * 16, t[v]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int v = 0; v < NTAIL; ++v) chunk_exp<T16, true, !TCSUM>(t[v], NRES + v, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
+                    for (int v = 0; v < NTAIL; ++v) chunk_exp<T16, true, EXACT>(t[v], NRES + v, N, scale_log2, mneg, trow, cls_out, lane == 0, l0, l1, p_last);
                 }
-                if (excl && lane == 0) mbar_arrive(&bar_exp[g * 4 + q]);
-                if constexpr (!TCSUM) {
+                if constexpr (EXACT) {
                     l = l0 + l1;
                     if (lse_out && grow < N) lse_out[((int64_t)s * H + h) * N + grow] = log2f(l) - mneg;     // rollout statistics
                 }
                 tmem_st_wait();
-            } else if (excl) {
-                if (i >= 1) mbar_wait(&bar_exp[(1 - g) * 4 + q], (uint32_t)(((i - 1) >> 1) & 1));     // keep the turn order
-                if (lane == 0) mbar_arrive(&bar_exp[g * 4 + q]);
             }
             TRACE(5);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_p[g]);                     // this warp's 32 rows of P are in TMEM
-            float inv = __frcp_rn(l);
-            if (!TCSUM && warp_active) {
-                if (probe_mode == PROBE_TEXT_COL && grow < probe_P) probe_out[((int64_t)s * H + h) * probe_P + grow] = p_last * inv;
+            if (warp_active) {
+                if (EXACT && probe_mode == PROBE_TEXT_COL && grow < probe_P) probe_out[((int64_t)s * H + h) * probe_P + grow] = p_last * __frcp_rn(l);
                 if (cls_warp) {
                     __syncwarp();                                          // lane 0's staged row is visible to the warp
-                    const float inv0 = __shfl_sync(0xffffffffu, inv, 0);
+                    const float* st = cls_stage + g * CLS_STAGE2;
+                    float part = 0.f;
+                    for (int key = lane; key < N; key += 32) part += st[key];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    const float inv0 = __frcp_rn(part);
                     float* cls_gl = probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N;
-                    for (int key = lane; key < N; key += 32) cls_gl[key] = cls_stage[g * CLS_STAGE2 + key] * inv0;
+                    for (int key = lane; key < N; key += 32) cls_gl[key] = st[key] * inv0;
                     __syncwarp();                                          // staging may be overwritten by the group's next item
                 }
             }
@@ -622,17 +619,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             TRACE(8);
             tc_fence_after();
             uint32_t o[4][16];
+            float inv = 1.f;
             if (warp_active) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x16(trow + O_COL + c * 16, o[c]);
-                if constexpr (TCSUM) {
-                    uint32_t lsum;
-                    tmem_ld_32x1(trow + O_COL + DH, lsum);            // row sum: the ones column of the product
-                    tmem_ld_wait();
-                    inv = __frcp_rn(__uint_as_float(lsum));
-                } else {
-                    tmem_ld_wait();
-                }
+                uint32_t lsum;
+                tmem_ld_32x1(trow + O_COL + DH, lsum);                // row sum: the ones column of the product
+                tmem_ld_wait();
+                inv = __frcp_rn(__uint_as_float(lsum));
             }
             TRACE(10);
             tc_fence_before();
@@ -999,9 +993,10 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         // (pair mode) 2 slots of (Q0 + Q1 + K + V), so that a head's K and V are loaded once
         static const int pair_env = getenv("TAPCLIP_ATTN_PAIR") ? atoi(getenv("TAPCLIP_ATTN_PAIR")) : 1;    // 0: measurement switch
         const int pair = (nqt == 2 && pair_env != 0) ? 1 : 0;
-        static const int excl = getenv("TAPCLIP_ATTN_EXCL") ? atoi(getenv("TAPCLIP_ATTN_EXCL")) : 0;        // exp2 passes of a sub-partition's two warps take turns
-        const size_t slots = pair ? 2 * (2 * 128 * 128 + 2 * (size_t)nkp * 128) : NSLOT * (128 * 128 + 2 * (size_t)nkp * 128);
-        const size_t smem2 = slots + OSTAGE_OFF + 8 * 4096 + 1024;   // + barriers/TMEM slot/CLS staging, ones block, O staging, alignment slack
+        const size_t slot1 = 128 * 128 + 2 * (size_t)nkp * 128, tail = OSTAGE_OFF + 8 * 4096 + 1024;
+        const int nslot_np = NSLOT * slot1 + tail <= 227 * 1024 ? NSLOT : 2;      // e.g. the one-q-tile launch of a ViT-B/16 CLS-only last layer (N = 197): 2
+        const size_t slots = pair ? 2 * (2 * 128 * 128 + 2 * (size_t)nkp * 128) : nslot_np * slot1;
+        const size_t smem2 = slots + tail;   // + barriers/TMEM slot/CLS staging, ones block, O staging, alignment slack
         const CUtensorMap& to = make_tmap_seq(out, tdt, 2, S, N, d, d, 32, 64);   // + barriers/TMEM slot, CLS staging, alignment slack
         const int num_sms = device_sm_count();
         const int n_items = pair ? S * H : S * H * nqt;        // scheduling units
@@ -1010,12 +1005,11 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         const int nch = nkp / 16;
         auto go = [&](auto kern) {
             ensure_dynamic_smem((const void*)kern, smem2);
-            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, to, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair, excl);
+            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, to, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair, nslot_np);
         };
-        static const int tcsum_env = getenv("TAPCLIP_ATTN_TCSUM") ? atoi(getenv("TAPCLIP_ATTN_TCSUM")) : 1;   // 0: measurement switch
-        const bool tcsum = tcsum_env != 0 && probe.mode == PROBE_NONE && probe.lse_out == nullptr;
+        const bool exact = probe.mode == PROBE_TEXT_COL || probe.lse_out != nullptr;     // launches that publish per-row statistics
         auto pick = [&](auto f16_c, auto nch_c) {
-            if (tcsum) go(attn_fwd_tc2_kernel<decltype(f16_c)::value, decltype(nch_c)::value, true>);
+            if (exact) go(attn_fwd_tc2_kernel<decltype(f16_c)::value, decltype(nch_c)::value, true>);
             else go(attn_fwd_tc2_kernel<decltype(f16_c)::value, decltype(nch_c)::value, false>);
         };
         using std::integral_constant;

@@ -116,7 +116,7 @@ def test_attention_fwd_tcgen05_persistent_kernel(S, N, H, dtype):
     out3 = torch.empty_like(out)
     L.check(lib.tapclip_op_attention(L.ptr(qkv), L.ptr(out3), L.DTYPE[dtype], S, N, H, L.PROBE_NONE, None, 0, 0, L.stream_ptr()))
     torch.cuda.synchronize()
-    assert torch.equal(out3, out)
+    assert torch.equal(out3, out)                                     # a probe never changes O
 
 
 @pytest.mark.parametrize("S,N,H", [(5, 93, 8), (2, 82, 4), (3, 17, 2), (1, 128, 8)])
