@@ -513,11 +513,13 @@ def run_ours(args, wl):
     # work-normalised scaling: with the class-sharded text tower the per-GPU work SHRINKS as N grows, so img/s over-states
     # the scaling; per-GPU fraction of peak on per-GPU algorithmic FLOPs is the figure to compare across N
     frac_1gpu = None
-    try:
-        with open(os.path.join(ROOT, "profiles", f"r02_bench_{wl}.json")) as f:
-            frac_1gpu = json.load(f)["roofline"]["step_frac_of_peak"]
-    except Exception:
-        pass
+    for rnd in ("r02b", "r02"):                    # newest committed 1-GPU line of this workload
+        try:
+            with open(os.path.join(ROOT, "profiles", f"{rnd}_bench_{wl}.json")) as f:
+                frac_1gpu = json.load(f)["roofline"]["step_frac_of_peak"]
+            break
+        except Exception:
+            pass
     cfg_line = config_dict(model_name, B, C, P, train, desc, world)
     cfg_line["l2_policy"] = (f"ring of {n_ring} distinct input batches ({n_ring * B * 3 * cfg.image_size ** 2 * 4 / 1e6:.0f} MB) > 126 MB L2; "
                              "per-step activations (>1 GB) exceed L2")
@@ -558,7 +560,7 @@ def run_ours(args, wl):
             "frac_of_peak_at_1_gpu": frac_1gpu,
             "efficiency_vs_1_gpu": (step_frac / frac_1gpu) if frac_1gpu else None,
             "note": "per-GPU work falls with N (class-sharded text tower): compare per_gpu_frac_of_peak across N, not images/s; "
-                    "frac_of_peak_at_1_gpu is the committed 1-GPU line profiles/r02_bench_<workload>.json",
+                    "frac_of_peak_at_1_gpu is the newest committed 1-GPU line profiles/r02b_bench_<workload>.json",
         },
     }
     if fwd is not None:

@@ -322,7 +322,8 @@ __device__ __forceinline__ void chunk_max(const uint32_t (&c)[16], int u, int N,
 #define ATTN_POLY 0
 #endif
 constexpr int POLY_EVERY = ATTN_POLY;          // n > 0: every n-th exponential of the persistent kernel's softmax runs on the FMA pipe.
-                                       // Measured (ViT-B/16 layer, B=128): 0 -> 62 us, 3 -> 77 us: the pass is latency/issue-bound, not MUFU-bound
+                                       // Measured (ViT-B/16 layer, B=128): 0 -> 62 us, 3 -> 77 us (round 1); with the tensor-core row sums, item
+                                       // period in cycles: 0 -> 7330, 4 -> 7500, 8 -> 7250: the pass is not MUFU-throughput-bound
 
 // exp2, row-sum, 16-bit pack and write-back of P chunk u (TMEM columns [8u, 8u+8) of the row); probe bookkeeping
 // CLS = float* : the CLS row's unnormalised p goes to global memory (scalar stores, any alignment);
@@ -377,7 +378,7 @@ constexpr int CLS_STAGE2 = 208;        // floats per group: the persistent kerne
 // statistics -- the text-column probe (attribution) and the rollout's lse -- take the EXACT instance, whose threads also add
 // up the unrounded probabilities; the CLS-row probe sums its staged row with the whole warp.
 #ifndef ATTN_SUMN
-#define ATTN_SUMN 16
+#define ATTN_SUMN 16                   // extra B columns of the P.V product (item period: 16 -> 7330, 32 -> 7470, 64 -> 7580 cycles)
 #endif
 constexpr int ONES_OFF = 2048;         // bytes behind the operand slots: barriers + CLS staging come first
 constexpr int OSTAGE_OFF = 4096;       // then 8 x 4 KB of O staging (one 32-row x 128-byte tile per softmax warp), the source of the TMA stores
