@@ -1,7 +1,7 @@
 """Developer tool: one attention layer through the op-level C-ABI (tapclip_op_attention), timed with CUDA events over inputs
 rotated through a ring larger than L2, and checked against torch SDPA.  Shapes: ViT-B/16 image tower (S=128, N=197, H=12, bf16)
 and the text tower of the C2 step (S=130, N=93, H=8, fp16).
-  TAPCLIP_ATTN_EXCL=1 python tools/micro/attn_bench.py
+  TAPCLIP_ATTN_IMPL=1|2 python tools/micro/attn_bench.py     # 1 = mma.sync kernel, 2 = tcgen05 kernel, unset = dispatch
 """
 import ctypes as C, os, sys
 import torch
