@@ -4,9 +4,10 @@
 // Work item = (sequence, head, 128-query tile):
 //   TMA   Q tile [128 x 64], K and V [NKP x 64] (NKP = keys padded to 16) into 128B-swizzled smem
 //   MMA1  S = Q K^T        tcgen05.mma  M=128, N=NKP, K=64  (A, B K-major from smem)  -> TMEM columns [0, NKP)
-//   softmax: one thread per query row reads its S row from TMEM, takes the max, computes exp2 / row sum, writes the 16-bit
+//   softmax: one thread per query row reads its S row from TMEM, takes the max, computes exp2, writes the 16-bit
 //         probabilities BACK INTO TMEM over the S columns (two keys per 32-bit column) and emits the probe
-//   MMA2  O = P V          tcgen05.mma  M=128, N=64, K=NKP   (A = P from TMEM, B = V as stored: MN-major smem descriptor)
+//   MMA2  O = P V          tcgen05.mma  M=128, N=64 (80 in the persistent kernel: 16 columns of ones give the row sum),
+//         K=NKP   (A = P from TMEM, B = V as stored: MN-major smem descriptor)
 //   epilogue: O / rowsum -> 16-bit -> global
 // S, P and O never touch shared memory or HBM; the N x N map is never materialised.
 // Two kernels: attn_fwd_tc2_kernel (NKP <= 208: persistent, warp-specialised, described at its definition) and
@@ -290,10 +291,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 //               (tools/micro/mma_issue_bench.cu: 13 P.V MMAs issue in 395 instead of 900 cycles)
 //   warps 2,3   idle: they pad warpgroup 0 so that setmaxnreg can hand its registers to the softmax warpgroups
 //   warps 4..11 two softmax groups of 4 warps (one thread per query row).  setmaxnreg gives these threads 232 registers,
-//               so the WHOLE S row (up to 208 fp32) is read from TMEM once and stays in registers for the max and the
-//               exp2/sum/pack pass; P goes back into TMEM over the S columns; then the group waits for O = P V, scales it,
-//               transposes it through the (dead) Q tile of the item's slot and stores 128-byte row segments.
-// The two groups run out of phase, so one group's MUFU-bound exp2 pass overlaps the other's TMEM/LSU phases.
+//               so up to ATTN_NRES 16-key chunks of the S row are read from TMEM once and stay in registers for the max
+//               and the exp2/pack pass (the rest are read twice); P goes back into TMEM over the S columns; then the group
+//               waits for O = P V (whose extra ones column carries the row sum), scales it, writes it into the warp's private
+//               4 KB staging tile and hands it to ONE TMA store.
+// The two groups run out of phase, so one group's exp2 pass overlaps the other's TMEM / shared-memory phases.
 // All hand-offs are mbarriers (no CTA-wide or group-wide bar.sync inside the loop).
 // ------------------------------------------------------------------------------------------------------------------
 #ifndef ATTN_NRES
