@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(ATTN2_THREADS, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const __grid_constant__ CUtensorMap tmap_o, void* __restrict__ out_,
                     int N, int H, int nkp, int nqt, int n_items, float scale_log2, int probe_mode, float* __restrict__ probe_out,
-                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out, int pair, int nslot_np) {
+                    int probe_P, int64_t probe_seq_stride, float* __restrict__ lse_out, int pair, int nslot_np, int s_early) {
     using T16 = typename std::conditional<F16, f16, bf16>::type;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -480,18 +480,32 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         } else if (warp == 1) {
             // ---- MMA issuer (all 32 lanes run the control flow; elect.sync picks the issuing lane) ----
-            const uint32_t idesc_s = attn_idesc(128, nkp, F16, false), idesc_o = attn_idesc(128, DH + ATTN_SUMN, F16, true);
+            const uint32_t idesc_o = attn_idesc(128, DH + ATTN_SUMN, F16, true);
             const int nks = nkp / 16;
+            // S(i) is issued in two column ranges.  TMEM columns [0, 128) of the half only ever held P(i-2), which P.V(i-2) -- issued
+            // before, and the tensor pipe executes in order -- has consumed: these key columns go out as soon as the operands have
+            // landed.  Columns [128, NKP) are shared with O(i-2) and wait until the softmax group has read it.  (Before, the whole
+            // S waited for O(i-2): 130..480 cycles of "S wait" per item in the phase trace; sequences of up to 128 keys -- the text
+            // tower -- now never wait.)
+            const int n_a = (s_early && nkp > 128) ? 128 : nkp, n_b = nkp - n_a;    // s_early = 0 (measurement switch): one range, after O(i-2)
+            const uint32_t idesc_sa = attn_idesc(128, n_a, F16, false), idesc_sb = attn_idesc(128, n_b > 0 ? n_b : 16, F16, false);
             auto issue_s = [&](int i) {
                 const int hf = i & 1;
                 uint8_t* slot = smem + slot_of(i) * slot_bytes;
                 mbar_wait(&bar_load[slot_of(i)], load_parity(i));
-                if (i >= 2) mbar_wait(&bar_tfree[hf], (uint32_t)(((i >> 1) - 1) & 1));     // O(i-2) has left this TMEM half
+                if (!s_early && i >= 2) mbar_wait(&bar_tfree[hf], (uint32_t)(((i >> 1) - 1) & 1));
                 tc_fence_after();
                 const uint32_t thalf = tmem_base + hf * 256;
                 const uint64_t qd = smem_desc_sw128(smem_u32(slot + q_off(i))), kd = smem_desc_sw128(smem_u32(slot + q_bytes));
 #pragma unroll
-                for (int k = 0; k < DH / 16; ++k) umma_ss_elect(thalf, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+                for (int k = 0; k < DH / 16; ++k) umma_ss_elect(thalf, qd + 2 * k, kd + 2 * k, idesc_sa, k != 0);
+                if (n_b > 0) {
+                    if (i >= 2) mbar_wait(&bar_tfree[hf], (uint32_t)(((i >> 1) - 1) & 1));     // O(i-2) has left columns [128, 208)
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < DH / 16; ++k)       // keys 128..: 128 rows x 128 B further into the K tile
+                        umma_ss_elect(thalf + 128, qd + 2 * k, kd + 1024 + 2 * k, idesc_sb, k != 0);
+                }
                 umma_commit_elect(&bar_s[hf]);
             };
             auto issue_pv = [&](int j) {
@@ -996,6 +1010,7 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         // (pair mode) 2 slots of (Q0 + Q1 + K + V), so that a head's K and V are loaded once
         static const int pair_env = getenv("TAPCLIP_ATTN_PAIR") ? atoi(getenv("TAPCLIP_ATTN_PAIR")) : 1;    // 0: measurement switch
         const int pair = (nqt == 2 && pair_env != 0) ? 1 : 0;
+        static const int s_early = getenv("TAPCLIP_ATTN_SEARLY") ? atoi(getenv("TAPCLIP_ATTN_SEARLY")) : 1;      // 0: measurement switch
         const size_t slot1 = 128 * 128 + 2 * (size_t)nkp * 128, tail = OSTAGE_OFF + 8 * 4096 + 1024;
         const int nslot_np = NSLOT * slot1 + tail <= 227 * 1024 ? NSLOT : 2;      // e.g. the one-q-tile launch of a ViT-B/16 CLS-only last layer (N = 197): 2
         const size_t slots = pair ? 2 * (2 * 128 * 128 + 2 * (size_t)nkp * 128) : nslot_np * slot1;
@@ -1008,7 +1023,7 @@ bool attention_fwd_tc(const void* qkv, void* out, int dt, int S, int N, int H, c
         const int nch = nkp / 16;
         auto go = [&](auto kern) {
             ensure_dynamic_smem((const void*)kern, smem2);
-            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, to, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair, nslot_np);
+            launch_pdl(kern, grid2, ATTN2_THREADS, smem2, stream, tq, tkv, to, out, N, H, nkp, nqt, n_items, sl2, probe.mode, probe.out, probe.P, probe.seq_stride, probe.lse_out, pair, nslot_np, s_early);
         };
         const bool exact = probe.mode == PROBE_TEXT_COL || probe.lse_out != nullptr;     // launches that publish per-row statistics
         auto pick = [&](auto f16_c, auto nch_c) {
