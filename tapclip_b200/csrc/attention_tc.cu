@@ -731,6 +731,7 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint64_t* bar_o = bar_s + 4;          // [2]
     uint64_t* bar_tfree = bar_s + 6;      // [2] count 4: O of the finished item has left TMEM
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 8);
+    float* mblk_s = reinterpret_cast<float*>(kvbuf + KV_STAGES * KV_STAGE_BYTES + 192);   // [2 groups][8]: the CLS row's max at each key block
     float* cls_stage = reinterpret_cast<float*>(kvbuf + KV_STAGES * KV_STAGE_BYTES + 256);   // only present (and touched) with PROBE_CLS_ROW
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -854,7 +855,6 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             // rescales, normalises and stores the row coalesced at the end of the item
             const uint32_t cls_out = cls_warp ? smem_u32(cls_stage + g * CLS_STAGE3) : 0u;
             float m_run = -INFINITY, l = 0.f, p_last = 0.f;
-            float m_blk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // the CLS row's max at each block (probe rescaling)
             for (int j = 0; j < nkb; ++j, ++blk) {
                 mbar_wait(&bar_s[g], blk & 1u);
                 tc_fence_after();
@@ -877,7 +877,7 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     if (j == nkb - 1) p_last = pl;
                     l = fmaf(l, alpha, l0 + l1);
                     m_run = m_new;
-                    if (cls_thread) m_blk[j & 7] = m_new;
+                    if (cls_thread) mblk_s[g * 8 + (j & 7)] = m_new;          // (shared memory: a dynamically indexed register array lives in local memory)
                     if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.f)) {
                         // O *= alpha (PV_{j-1} is complete: S_j was only issued after it)
                         uint32_t o[4][16];
@@ -919,7 +919,7 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     const float inv0 = __shfl_sync(0xffffffffu, inv, 0), m0 = __shfl_sync(0xffffffffu, m_run, 0);
                     float fb[8];                                       // per key block: 2^((m_block - m_final) c) / l
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) fb[b] = fast_exp2((__shfl_sync(0xffffffffu, m_blk[b], 0) - m0) * scale_log2) * inv0;
+                    for (int b = 0; b < 8; ++b) fb[b] = b < nkb ? fast_exp2((mblk_s[g * 8 + b] - m0) * scale_log2) * inv0 : 0.f;
                     float* cls_gl = probe_out + (int64_t)s * probe_seq_stride + (int64_t)h * N;
 #pragma unroll
                     for (int b = 0; b < 8; ++b)
