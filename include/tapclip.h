@@ -13,6 +13,9 @@
  *     library) unless stated; tensors are dense row-major fp32 unless stated; `stream` is a cudaStream_t
  *     passed as void* (0 = default stream).  All work is enqueued on `stream`; no hidden host syncs.
  *   - a handle owns its converted weights and workspaces; it is not thread-safe; one handle per device.
+ *     The library also keeps process-wide launch caches (tensor maps, kernel attributes, per-device scratch): drive it
+ *     from ONE host thread per process (the deployment model is one process per GPU; several devices from one thread
+ *     are supported).
  */
 #ifndef TAPCLIP_H_
 #define TAPCLIP_H_
