@@ -865,6 +865,11 @@ void gemm_tc(const GemmArgs& g, cudaStream_t stream) {
         TC_CHECK(bn == 0 || bn == choose_block_n(g.N), "the residual epilogue fixes the tile shape (statistics layout)");
         bn = 0;
     }
+    // TAPCLIP_GEMM_QKV2CTA=1: the image tower's QKV projection (large M, N >= 2048, short K, plain 16-bit store) on 2-CTA pairs,
+    // the one shape where the pair wins in isolation (69.8 vs 74.2 us, above cuBLAS 71.5).  In the step (three runs each, one box):
+    // 8.274 / 8.290 / 8.384 ms with it, 8.290 / 8.312 / 8.382 without -- below the noise, so it stays off.
+    static const int qkv2 = getenv("TAPCLIP_GEMM_QKV2CTA") ? atoi(getenv("TAPCLIP_GEMM_QKV2CTA")) : 0;
+    if (bn == 0 && qkv2 && g.M >= 16384 && g.N >= 2048 && g.N % 256 == 0 && g.K <= 1024 && g.epi == EPI_BF16 && g.act == ACT_NONE && g.out_pre == nullptr && !fixed_shape) bn = 512;
     if (bn == 0) {
         // Measured (tools/gemm_bench.py, B200): 128x256 single-CTA tiles are within 3 % of the 2-CTA 256x256 tiles on the
         // image-tower shapes (both ~0.95 of cuBLAS: the mainloop is not L2-feed-bound) and 10-15 % faster on the small
